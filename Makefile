@@ -1,0 +1,46 @@
+# Builds libsuperman_b200.so (C host + sm_100a CUDA kernels) and the `perman` CLI, in-tree.
+#   make -j8            everything
+#   make oracle         the CPU oracle (test infrastructure) and, when /root/reference exists,
+#                       the reference shim under oracle/_ref/
+NVCC      ?= nvcc
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Isuperman_b200/csrc
+CFLAGS    := -O2 -std=c11 -fPIC -Wall -Wextra -Iinclude -Isuperman_b200/host -pthread
+CUDA_HOME ?= /usr/local/cuda
+
+BUILD   := build
+PKG     := superman_b200
+LIB     := $(PKG)/libsuperman_b200.so
+CLI     := $(PKG)/perman
+
+GROUPS  := 0 1 2 3 4 5 6 7
+CU_SRCS := sp_device sp_dense
+CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o)
+C_SRCS  := sp_sched sp_api
+C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
+
+all: $(LIB)
+
+$(BUILD):
+	mkdir -p $(BUILD)
+
+$(BUILD)/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(BUILD)/sp_dense_inst_g%.o: $(PKG)/csrc/sp_dense_inst.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DSPB_GROUP=$* -c $< -o $@
+
+$(BUILD)/%.o: $(PKG)/host/%.c $(wildcard $(PKG)/host/*.h include/*.h) | $(BUILD)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(C_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread -lm
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf $(BUILD) $(LIB) $(CLI)
+
+.PHONY: all oracle clean

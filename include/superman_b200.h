@@ -1,0 +1,100 @@
+/* superman_b200.h -- C-ABI of libsuperman_b200.so, the B200-native drop-in for SUPerman's
+ * GPU permanent paths.
+ *
+ * The reference has no FFI on its GPU path: main.cu textually #includes the four .cu files and
+ * RunAlgo (main.cu:20-248) calls the templated host wrappers gpu_perman64_* directly.  Its only
+ * extern "C" surface is the CPU-only shim interface_connector.c:61-231.  The entry points below are
+ * therefore (1) one function per gpu_perman64_* wrapper family -- same argument meaning, element
+ * type widened to double (int / float matrix files are exactly representable) -- and (2) the
+ * reader / CRS-CCS / ordering helpers of util.h that main.cu calls before them, so that a
+ * maintainer can rebind RunAlgo to this library line by line (INTEGRATION.md shows the stub).
+ *
+ * Ownership: the caller allocates and frees every host array it passes in; arrays returned through
+ * an sp_matrix are owned by that struct and released by sp_matrix_free.  The library owns all
+ * device memory and never keeps a host pointer after a call returns.
+ * Errors: a failing call returns NaN (functions returning double) or a negative SP_E* code and
+ * sets sp_last_error(); `stats->error` carries the same code.  The reference checks no CUDA call
+ * at all; a success path prints exactly what the reference prints.
+ * There is no CPU fallback: with no CUDA device every compute entry point fails with SP_ENODEV.
+ */
+#ifndef SUPERMAN_B200_H
+#define SUPERMAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_OK        0
+#define SP_ENODEV   -1
+#define SP_EINVAL   -2
+#define SP_ECUDA    -3
+#define SP_ENOMEM   -4
+#define SP_ELIMIT   -5
+#define SP_EIO      -6
+#define SP_EALGO    -7   /* "Unknown Algorithm ID" (main.cu:75) */
+
+#define SP_MAX_DEVICES 16
+
+typedef struct sp_stats {
+  double kernel_ms;            /* max over devices of the CUDA-event time of their launches */
+  double wall_ms;              /* host wall clock of the whole call */
+  double device_ms[SP_MAX_DEVICES];       /* per device: sum of CUDA-event times */
+  double device_partial[SP_MAX_DEVICES];  /* per device: its partial result (rank-order summed) */
+  unsigned long long device_units[SP_MAX_DEVICES]; /* Gray indices / trials handled per device */
+  unsigned long long units;    /* Gray indices in the range (exact) or trials run (approx) */
+  unsigned long long visited;  /* Skipper: indices evaluated */
+  double std_error;            /* approximations: standard error of the mean estimate */
+  int devices;                 /* devices used */
+  int chunks;                  /* chunks scheduled (dynamic paths), else == devices */
+  int launches;                /* kernel launches */
+  int path;                    /* SPD_PATH_* of the dominant kernel */
+  int tile_log2;
+  int error;                   /* SP_OK or SP_E* */
+} sp_stats;
+
+const char *sp_last_error(void);
+int         sp_device_count(void);
+const char *sp_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense exact (Ryser / Nijenhuis-Wilf), ids -p0..-p6 of main.cu:34-75.
+ * mat is row-major nov x nov (mat[i*nov+j]), as produced by ReadMatrix (util.h:343-358).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces gpu_perman64_xglobal / _xlocal / _xshared / _xshared_coalescing /
+ * _xshared_coalescing_mshared (gpu_exact_dense.cu:401,459,518,576,640; ids 0-4: one device),
+ * _mshared_multigpu (gpu_exact_dense.cu:701; id 5: static split over gpu_num devices) and
+ * _mshared_multigpucpu_chunks (gpu_exact_dense.cu:776; id 6: dynamic chunk queue over gpu_num
+ * devices).  All ids run the same sm_100a kernel; the id selects the partition only.
+ * use_cpu / threads are accepted for signature parity (id 6's "-c -tN" CPU helper thread,
+ * gpu_exact_dense.cu:822-845) and ignored: this library has no CPU compute path.
+ * Returns the permanent.  Single-device ids use device 0 (the reference hard-codes device 1,
+ * gpu_exact_dense.cu:664). */
+double sp_dense_ryser(const double *mat, int nov, int algo_id, int gpu_num, int use_cpu, int threads,
+                      sp_stats *stats);
+
+/* The kernel-level contract of kernel_xshared_coalescing_mshared(mat_t, x, p, nov, start, end)
+ * (gpu_exact_dense.cu:329-399) and of cpu_perman64(mat_t, x, nov, start, end, threads)
+ * (gpu_exact_dense.cu:6-69): the signed sum of the Ryser terms with Gray index in [start, end) on
+ * one device, WITHOUT the base term and WITHOUT the final (4*(nov&1)-2) factor -- except that
+ * start == 0 is allowed and then includes index 0, the base term prod_j x_j.  This is what a
+ * multi-process launcher (one rank per GPU) calls with its own slice. */
+double sp_dense_ryser_range(const double *mat, int nov, int device, long long start, long long end,
+                            sp_stats *stats);
+
+/* Resident variant: upload once, run ranges many times (no H2D in the run). */
+typedef struct sp_dense_handle sp_dense_handle;
+int    sp_dense_open(const double *mat, int nov, int device, sp_dense_handle **h);
+double sp_dense_run(sp_dense_handle *h, long long start, long long end, sp_stats *stats);
+void   sp_dense_close(sp_dense_handle *h);
+
+/* (4*(nov&1)-2): the factor every wrapper applies to base + sum (gpu_exact_dense.cu:698). */
+double sp_nw_factor(int nov);
+
+/* Measured FP64 instruction issue rate of a device (thread-level instr/s); roofline denominator. */
+double sp_fp64_peak(int device, int millis);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

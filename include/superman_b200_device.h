@@ -1,0 +1,82 @@
+/* superman_b200_device.h -- the thin C-ABI layer between the C host code and the sm_100a CUDA
+ * kernels (BASELINE.json north_star: "Host code in C ... calls CUDA through a thin C-ABI layer").
+ *
+ * Nothing here knows about files, flags or algorithm ids: a "plan" is one matrix made resident on
+ * one device, and a "run" is one kernel pass over a range of Gray indices (exact paths) or trial
+ * indices (approximations) that leaves ONE double on the host.  The reference has no such layer:
+ * its host wrappers (gpu_perman64_*, e.g. gpu_exact_dense.cu:640-699) cudaMalloc / cudaMemcpy /
+ * launch / copy back grid*block partial sums / cudaFree on every call.  The functions below are
+ * what those wrappers' CUDA halves become.
+ *
+ * Threading: a plan belongs to one device; calls on different plans may come from different host
+ * threads concurrently (one host thread per device is how the scheduler drives them).  Calls on the
+ * same plan must be serialised by the caller.
+ * Errors: every function returns 0 on success or a negative SPD_E* code; spd_last_error() returns
+ * a thread-local message.  There is NO CPU fallback: without a usable CUDA device every entry
+ * point fails with SPD_ENODEV.
+ */
+#ifndef SUPERMAN_B200_DEVICE_H
+#define SUPERMAN_B200_DEVICE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPD_OK        0
+#define SPD_ENODEV   -1   /* no CUDA device / driver */
+#define SPD_EINVAL   -2   /* bad argument */
+#define SPD_ECUDA    -3   /* CUDA runtime error (message in spd_last_error) */
+#define SPD_ENOMEM   -4
+#define SPD_ELIMIT   -5   /* size outside what the kernels support */
+
+/* Per-run measurements, filled by every *_run / *_wait call. */
+typedef struct spd_run_info {
+  double kernel_ms;         /* CUDA-event time on the plan's stream around this run's launches */
+  unsigned long long units; /* Gray indices covered (exact) or trials executed (approximations) */
+  unsigned long long visited; /* Skipper: indices actually evaluated; otherwise == units */
+  int launches;             /* kernels launched by this run */
+  int path;                 /* SPD_PATH_* of the dominant kernel */
+  int tile_log2;            /* log2 of the per-thread tile (exact register paths), else 0 */
+  int reserved;
+} spd_run_info;
+
+#define SPD_PATH_DENSE_REG      1   /* X in registers, templated on n            */
+#define SPD_PATH_DENSE_SMEM     2   /* X in shared memory, any n <= 64           */
+#define SPD_PATH_SPARSE_REG     3
+#define SPD_PATH_SPARSE_SMEM    4
+#define SPD_PATH_SKIPPER        5
+#define SPD_PATH_RASMUSSEN      6
+#define SPD_PATH_SCALING        7
+
+int         spd_device_count(void);               /* >= 0, or SPD_ENODEV */
+const char *spd_last_error(void);
+void        spd_shutdown(void);                   /* release pooled streams / buffers */
+int         spd_device_name(int device, char *buf, int buflen);
+int         spd_device_sm_count(int device);
+int         spd_device_sm_clock_khz(int device);  /* max SM clock */
+
+/* Measured FP64 issue rate of `device`: runs a register-only DFMA chain kernel for about
+ * `millis` ms and returns warp-level FP64 instructions * 32 per second (thread-level FP64
+ * instr/s), the denominator of the dense roofline.  Negative on error. */
+double      spd_fp64_peak_instr_per_s(int device, int millis);
+
+/* ---- dense Ryser --------------------------------------------------------------------------- */
+typedef struct spd_dense_plan spd_dense_plan;
+
+/* mat_t[k*nov + j] = A[j][k] (the transposed matrix the reference uploads, gpu_exact_dense.cu:657-674),
+ * xbase[j] = A[j][nov-1] - rowsum_j/2 (gpu_exact_dense.cu:647-654).  2 <= nov <= 64. */
+int  spd_dense_plan_create(int device, const double *mat_t, const double *xbase, int nov,
+                           spd_dense_plan **plan);
+void spd_dense_plan_destroy(spd_dense_plan *plan);
+/* Signed sum of the Ryser terms with Gray index in [lo, hi), 0 <= lo <= hi <= 2^(nov-1); index 0
+ * is the NW base term prod(xbase).  Synchronous: returns when *sum is valid. */
+int  spd_dense_plan_run(spd_dense_plan *plan, unsigned long long lo, unsigned long long hi,
+                        double *sum, spd_run_info *info);
+/* Asynchronous pair (launch on the plan's stream / wait + fetch). */
+int  spd_dense_plan_launch(spd_dense_plan *plan, unsigned long long lo, unsigned long long hi);
+int  spd_dense_plan_wait(spd_dense_plan *plan, double *sum, spd_run_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,142 @@
+"""Host-side mirror of the reference's wrapper interface (same names, argument meaning and
+return value as the templated gpu_perman64_* functions in gpu_exact_dense.cu etc.), implemented
+as thin calls into the C-ABI of libsuperman_b200.so.  No arithmetic happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import SpStats, lib
+
+__all__ = [
+    "SupermanError", "device_count", "fp64_peak", "nw_factor",
+    "dense_ryser", "dense_ryser_range", "DenseHandle",
+    "gpu_perman64_xglobal", "gpu_perman64_xlocal", "gpu_perman64_xshared",
+    "gpu_perman64_xshared_coalescing", "gpu_perman64_xshared_coalescing_mshared",
+    "gpu_perman64_xshared_coalescing_mshared_multigpu",
+    "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks",
+]
+
+
+class SupermanError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"superman_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _dmat(mat, nov=None) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(mat, dtype=np.float64))
+    if nov is None:
+        nov = a.shape[0]
+    a = a.reshape(nov * nov)
+    return a
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _check(value: float, st: SpStats) -> float:
+    if st.error != 0 or (isinstance(value, float) and math.isnan(value) and st.error != 0):
+        raise SupermanError(st.error, _ffi.last_error())
+    return value
+
+
+def device_count() -> int:
+    return lib.sp_device_count()
+
+
+def nw_factor(nov: int) -> float:
+    return lib.sp_nw_factor(nov)
+
+
+def fp64_peak(device: int = 0, millis: int = 200) -> float:
+    r = lib.sp_fp64_peak(device, millis)
+    if r < 0:
+        raise SupermanError(-1, _ffi.last_error())
+    return r
+
+
+def dense_ryser(mat, nov=None, algo_id=4, gpu_num=1, cpu=False, threads=16, stats: SpStats | None = None) -> float:
+    a = _dmat(mat, nov)
+    nov = int(round(math.sqrt(a.size)))
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_dense_ryser(_ptr(a), nov, algo_id, gpu_num, int(cpu), threads, C.byref(st))
+    return _check(v, st)
+
+
+def dense_ryser_range(mat, start, end, nov=None, device=0, stats: SpStats | None = None) -> float:
+    a = _dmat(mat, nov)
+    nov = int(round(math.sqrt(a.size)))
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_dense_ryser_range(_ptr(a), nov, device, start, end, C.byref(st))
+    return _check(v, st)
+
+
+class DenseHandle:
+    """Matrix resident on one device (sp_dense_open / sp_dense_run / sp_dense_close)."""
+
+    def __init__(self, mat, nov=None, device=0):
+        a = _dmat(mat, nov)
+        self.nov = int(round(math.sqrt(a.size)))
+        self._h = C.c_void_p()
+        rc = lib.sp_dense_open(_ptr(a), self.nov, device, C.byref(self._h))
+        if rc != 0:
+            raise SupermanError(rc, _ffi.last_error())
+
+    def run(self, start: int, end: int, stats: SpStats | None = None) -> float:
+        st = stats if stats is not None else SpStats()
+        v = lib.sp_dense_run(self._h, start, end, C.byref(st))
+        return _check(v, st)
+
+    def close(self):
+        if self._h:
+            lib.sp_dense_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- reference wrapper names (gpu_exact_dense.cu:401,459,518,576,640,701,776) -------------------
+# grid_dim / block_dim are accepted for signature parity and ignored: launch geometry is chosen by
+# the library (RunAlgo hard-codes 2048 x {128,256}, main.cu:24-28).
+def gpu_perman64_xglobal(mat, nov, grid_dim=2048, block_dim=256):
+    return dense_ryser(mat, nov, 0)
+
+
+def gpu_perman64_xlocal(mat, nov, grid_dim=2048, block_dim=256):
+    return dense_ryser(mat, nov, 1)
+
+
+def gpu_perman64_xshared(mat, nov, grid_dim=2048, block_dim=256):
+    return dense_ryser(mat, nov, 2)
+
+
+def gpu_perman64_xshared_coalescing(mat, nov, grid_dim=2048, block_dim=256):
+    return dense_ryser(mat, nov, 3)
+
+
+def gpu_perman64_xshared_coalescing_mshared(mat, nov, grid_dim=2048, block_dim=256):
+    return dense_ryser(mat, nov, 4)
+
+
+def gpu_perman64_xshared_coalescing_mshared_multigpu(mat, nov, gpu_num, grid_dim=2048, block_dim=256):
+    return dense_ryser(mat, nov, 5, gpu_num)
+
+
+def gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks(mat, nov, gpu_num, cpu=False, threads=16,
+                                                               grid_dim=2048, block_dim=256):
+    return dense_ryser(mat, nov, 6, gpu_num, cpu, threads)

@@ -1,0 +1,158 @@
+// Dense Nijenhuis-Wilf / Ryser Gray-code kernel for sm_100a, X vector in registers.
+//
+// Replaces kernel_xshared_coalescing_mshared (reference gpu_exact_dense.cu:329-399), which
+// keeps X as float in shared memory, finds the flipped column with __ffsll every step and
+// walks "for every Gray index: for every row".  Here every thread owns one tile of 2^c
+// consecutive Gray indices (aligned to 2^c) and the loop nest is turned inside out:
+//
+//   for each aligned block of 2^B indices of the tile:            (runtime loop)
+//     for each row j:                                             (unrolled, X[j] in a register)
+//       v = X[j] +/- A[j][k_hi]                                   (the one "high" column flipped
+//                                                                  at the block start, k_hi >= B,
+//                                                                  identical for the whole grid:
+//                                                                  shared-memory broadcast)
+//       P[0] *= v
+//       for u = 1 .. 2^B-1:  v +/-= A[j][ctz(u)];  P[u] *= v      (columns < B, direction known
+//                                                                  at compile time)
+//       X[j] = v
+//     acc += P[0] - P[1] + P[2] - ...
+//
+// so the B most frequently flipped columns of a row are loaded once per block (2 LDS.128 per
+// row for B = 4) instead of once per Gray index, every X[j] is consumed the moment it is
+// produced (no second copy of X alive while a product is still pending), and the 2^B running
+// products P[u] are independent DMUL chains that cover the FP64 latency inside one warp.
+// Signed terms are accumulated per thread and closed with a warp-shuffle + block reduction
+// into one double per block (no per-thread partial array, no host sum over 2^18 doubles).
+//
+// FP64 instructions per Gray index: N DADD/DFMA (x update) + (N-1) DMUL + 1 DADD = 2N.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spb {
+
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void lds_f64(uint32_t addr, double& a) {
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr));
+}
+
+__host__ __device__ constexpr int ctz_c(int u) { int k = 0; while (((u >> k) & 1) == 0) ++k; return k; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Shared-memory image used by the register kernel (doubles):
+//   colT[k * NP + j] = A[j][k]   k in [0, N-1), NP = N rounded up to even   (column-major)
+//   lowR[j * LB + k] = A[j][k]   k in [0, B),   LB = B rounded up to even   (row-major, low columns)
+template <int N, int B>
+struct RegLayout {
+  static constexpr int NP = N + (N & 1);
+  static constexpr int LB = B + (B & 1);
+  static constexpr int COLT = 0;
+  static constexpr int LOWR = COLT + N * NP;
+  static constexpr int TOTAL = LOWR + N * LB;
+};
+
+// Tiles [tile_first, tile_first + n_tiles) of 2^c indices each; thread t of the grid owns tile
+// tile_first + t.  partials[blockIdx.x] receives the block's signed sum.  Index 0 (the NW base
+// term that the reference adds on the host, gpu_exact_dense.cu:653,691) is an ordinary tile
+// start here, so a launch over [0, 2^(n-1)) yields the complete sum.
+// Requires B + 1 <= c <= N - 1 and N - 1 > B.
+template <int N, int B, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+ryser_reg_kernel(const double* __restrict__ mat_t,   // mat_t[k*N + j] = A[j][k]
+                 const double* __restrict__ xbase,   // NW start vector (gpu_exact_dense.cu:647-654)
+                 double* __restrict__ partials, unsigned long long tile_first,
+                 unsigned long long n_tiles, int c) {
+  using L = RegLayout<N, B>;
+  constexpr int NP = L::NP, LB = L::LB, NB = 1 << B;
+  __shared__ __align__(16) double sm[L::TOTAL];
+  __shared__ double warp_part[THREADS / 32];
+  for (int e = threadIdx.x; e < N * N; e += THREADS) {
+    const int k = e / N, j = e % N;
+    const double v = mat_t[e];
+    sm[L::COLT + k * NP + j] = v;
+    if (k < B) sm[L::LOWR + j * LB + k] = v;
+  }
+  __syncthreads();
+  const uint32_t sm_colT = (uint32_t)__cvta_generic_to_shared(sm + L::COLT);
+  const uint32_t sm_lowR = (uint32_t)__cvta_generic_to_shared(sm + L::LOWR);
+
+  const unsigned long long t = (unsigned long long)blockIdx.x * THREADS + threadIdx.x;
+  const bool active = t < n_tiles;
+  const unsigned long long s = (tile_first + (active ? t : 0ull)) << c;   // first index of the tile
+  const unsigned long long g = s ^ (s >> 1);                              // Gray code at the tile start
+  double x[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = xbase[j];
+  // explicit X at the tile start (cf. gpu_exact_dense.cu:363-371).  Bits below c-1 of g are
+  // zero; every lane reads the same column (broadcast) and masks it with its own Gray bit.
+  for (int k = c - 1; k < N - 1; ++k) {
+    const double f = (double)((g >> k) & 1ull);
+    const double* col = sm + L::COLT + k * NP;
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = fma(f, col[j], x[j]);
+  }
+
+  double acc = 0.0;
+  const int nblk = 1 << (c - B);
+  unsigned long long i0 = s;
+#pragma unroll 1
+  for (int blk = 0; blk < nblk; ++blk, i0 += (unsigned long long)NB) {
+    // high column flipped at the block start: k = ctz(i0) = B + ctz(blk), same for all threads.
+    // Gray bit k after the flip is 1 ^ bit(k+1) of i0 -> add (+1) when that bit is clear.
+    // blk == 0 is the tile start, where X is already explicit: weight 0 leaves it unchanged.
+    const int k = (blk != 0) ? (B + __ffs(blk) - 1) : B;
+    const double sg = (blk != 0) ? (((i0 >> (k + 1)) & 1ull) ? -1.0 : 1.0) : 0.0;
+    // column B-1 flips in the middle of the block; its direction is bit B of i0
+    const double sg_top = (blk & 1) ? -1.0 : 1.0;
+    const uint32_t hi_addr = sm_colT + (uint32_t)(k * NP * 8);
+
+    double P[NB];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double m[LB];
+#pragma unroll
+      for (int q = 0; q < LB; q += 2) lds_f64x2(sm_lowR + (uint32_t)((j * LB + q) * 8), m[q], m[q + 1]);
+      double d;
+      lds_f64(hi_addr + (uint32_t)(j * 8), d);
+      double v = fma(sg, d, x[j]);
+      P[0] = (j == 0) ? v : P[0] * v;
+#pragma unroll
+      for (int u = 1; u < NB; ++u) {
+        const int K = ctz_c(u);
+        if (K == B - 1) {
+          v = fma(sg_top, m[K], v);
+        } else if (((u >> (K + 1)) & 1) == 0) {
+          v += m[K];
+        } else {
+          v -= m[K];
+        }
+        P[u] = (j == 0) ? v : P[u] * v;
+      }
+      x[j] = v;
+    }
+    // term sign (-1)^i: block start is even
+    double blk_sum = 0.0;
+#pragma unroll
+    for (int u = 0; u < NB; u += 2) blk_sum += (P[u] - P[u + 1]);
+    acc += blk_sum;
+  }
+
+  acc = warp_sum(active ? acc : 0.0);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) v += warp_part[w];
+    partials[blockIdx.x] = v;
+  }
+}
+
+}  // namespace spb

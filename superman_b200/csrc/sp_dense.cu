@@ -1,0 +1,312 @@
+// Dense Ryser on one device: plan (matrix resident in HBM), range planner and the
+// shared-memory-X kernel used for ragged range ends and for n outside the register kernels.
+//
+// Reference path replaced: gpu_perman64_xshared_coalescing_mshared and its kernel
+// (gpu_exact_dense.cu:329-399, 640-699); the [lo, hi) contract is that of the kernel's
+// (start, end) arguments, which the multi-GPU wrappers slice (gpu_exact_dense.cu:729-752, 786-889).
+#include "sp_internal.cuh"
+#include "sp_dense_reg.h"
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+namespace spb {
+
+#define SMEMK_THREADS 128
+
+// X in shared memory as doubles, x_j of thread t at X[j*THREADS + t]: consecutive lanes touch
+// consecutive 8-byte words, so every access is conflict-free (the reference's float X with the
+// same layout, gpu_exact_dense.cu:336,389, is what north_star's "shared memory for large n,
+// laid out free of bank conflicts" refers to).  Each thread owns the contiguous index range
+// [lo + t*per_thread, lo + (t+1)*per_thread) ∩ [lo, hi) and initialises X explicitly at its start
+// (gpu_exact_dense.cu:363-371).
+__global__ void __launch_bounds__(SMEMK_THREADS)
+ryser_smem_kernel(const double* __restrict__ mat_t, const double* __restrict__ xbase, int n,
+                  unsigned long long lo, unsigned long long hi, unsigned long long per_thread,
+                  double* __restrict__ partials) {
+  extern __shared__ __align__(16) double dsm[];
+  double* colT = dsm;                 // colT[k*n + j] = A[j][k]
+  double* X = dsm + n * n;            // X[j*THREADS + t]
+  __shared__ double warp_part[SMEMK_THREADS / 32];
+  for (int e = threadIdx.x; e < n * n; e += SMEMK_THREADS) colT[e] = mat_t[e];
+  double* x = X + threadIdx.x;
+  for (int j = 0; j < n; ++j) x[j * SMEMK_THREADS] = xbase[j];
+  __syncthreads();
+
+  const unsigned long long gid = (unsigned long long)blockIdx.x * SMEMK_THREADS + threadIdx.x;
+  // gid * per_thread cannot overflow: the host keeps grid*per_thread < 2^63
+  unsigned long long i = lo + gid * per_thread;
+  unsigned long long end = i + per_thread;
+  if (end > hi) end = hi;
+  double acc = 0.0;
+  if (i < end) {
+    unsigned long long g = 0;
+    if (i == 0) {
+      double p0 = 1.0, p1 = 1.0;
+      for (int j = 0; j + 1 < n; j += 2) { p0 *= x[j * SMEMK_THREADS]; p1 *= x[(j + 1) * SMEMK_THREADS]; }
+      if (n & 1) p0 *= x[(n - 1) * SMEMK_THREADS];
+      acc = p0 * p1;                  // NW base term, index 0
+      i = 1;
+    } else {
+      g = (i - 1) ^ ((i - 1) >> 1);
+      for (int k = 0; k < n - 1; ++k) {
+        if ((g >> k) & 1ull) {
+          const double* col = colT + k * n;
+          for (int j = 0; j < n; ++j) x[j * SMEMK_THREADS] += col[j];
+        }
+      }
+    }
+    for (; i < end; ++i) {
+      const int k = __ffsll((long long)i) - 1;
+      g ^= (1ull << k);
+      const double s = ((g >> k) & 1ull) ? 1.0 : -1.0;
+      const double* col = colT + k * n;
+      double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+      int j = 0;
+      for (; j + 3 < n; j += 4) {
+        const double a0 = fma(s, col[j], x[j * SMEMK_THREADS]);
+        const double a1 = fma(s, col[j + 1], x[(j + 1) * SMEMK_THREADS]);
+        const double a2 = fma(s, col[j + 2], x[(j + 2) * SMEMK_THREADS]);
+        const double a3 = fma(s, col[j + 3], x[(j + 3) * SMEMK_THREADS]);
+        x[j * SMEMK_THREADS] = a0; x[(j + 1) * SMEMK_THREADS] = a1;
+        x[(j + 2) * SMEMK_THREADS] = a2; x[(j + 3) * SMEMK_THREADS] = a3;
+        p0 *= a0; p1 *= a1; p2 *= a2; p3 *= a3;
+      }
+      for (; j < n; ++j) {
+        const double a0 = fma(s, col[j], x[j * SMEMK_THREADS]);
+        x[j * SMEMK_THREADS] = a0;
+        p0 *= a0;
+      }
+      const double prod = (p0 * p1) * (p2 * p3);
+      acc += (i & 1ull) ? -prod : prod;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < SMEMK_THREADS / 32; ++w) v += warp_part[w];
+    partials[blockIdx.x] = v;
+  }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  if (!s || !*s) return dflt;
+  return atoi(s);
+}
+
+static int reg_launch(int n, int B, cudaStream_t st, const double* mat_t, const double* xbase,
+                      double* partials, unsigned long long tile_first, unsigned long long n_tiles,
+                      int c, unsigned* blocks_out) {
+  switch (n % SPB_NGROUPS) {
+    case 0: return spb_reg_launch_g0(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    case 1: return spb_reg_launch_g1(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    case 2: return spb_reg_launch_g2(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    case 3: return spb_reg_launch_g3(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    case 4: return spb_reg_launch_g4(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    case 5: return spb_reg_launch_g5(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    case 6: return spb_reg_launch_g6(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    default: return spb_reg_launch_g7(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+  }
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+struct spd_dense_plan {
+  Lane* lanep = nullptr;
+  int n = 0;
+  double* d_mat_t = nullptr;
+  double* d_xbase = nullptr;
+  size_t smem_bytes = 0;
+  bool pending = false;
+  spd_run_info info;
+};
+
+static int ilog2_ull(unsigned long long v) {
+  int r = -1;
+  while (v) { v >>= 1; ++r; }
+  return r;
+}
+
+// ragged piece [lo, hi) through the shared-memory kernel; appends its blocks to the partial array
+static int enqueue_smem(spd_dense_plan* p, unsigned long long lo, unsigned long long hi,
+                        size_t* pcount, int* launches) {
+  if (hi <= lo) return SPD_OK;
+  const unsigned long long len = hi - lo;
+  const unsigned long long want_threads = (unsigned long long)p->lanep->sm_count * 4 * SMEMK_THREADS;
+  unsigned long long per_thread = (len + want_threads - 1) / want_threads;
+  unsigned long long pt = 16;       // at least 16 indices per thread: amortises the explicit X start
+  while (pt < per_thread) pt <<= 1; // power of two keeps the flipped column warp-uniform
+  per_thread = pt;
+  const unsigned long long threads = (len + per_thread - 1) / per_thread;
+  const unsigned long long blocks = (threads + SMEMK_THREADS - 1) / SMEMK_THREADS;
+  int rc = lane_reserve_partials(p->lanep, *pcount + (size_t)blocks);
+  if (rc != SPD_OK) return rc;
+  ryser_smem_kernel<<<(unsigned)blocks, SMEMK_THREADS, p->smem_bytes, p->lanep->stream>>>(
+      p->d_mat_t, p->d_xbase, p->n, lo, hi, per_thread, p->lanep->d_partials + *pcount);
+  SPB_CUDA(cudaGetLastError());
+  *pcount += (size_t)blocks;
+  *launches += 1;
+  return SPD_OK;
+}
+
+static int dense_enqueue(spd_dense_plan* p, unsigned long long lo, unsigned long long hi) {
+  const int n = p->n;
+  const unsigned long long full = 1ull << (n - 1);
+  if (lo > hi || hi > full) {
+    set_error("dense range [%llu, %llu) outside [0, 2^%d]", lo, hi, n - 1);
+    return SPD_EINVAL;
+  }
+  Lane& L = *p->lanep;
+  SPB_CUDA(cudaSetDevice(L.device));
+  memset(&p->info, 0, sizeof(p->info));
+  p->info.units = hi - lo;
+  p->info.visited = hi - lo;
+  p->info.path = SPD_PATH_DENSE_SMEM;
+  SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
+  int launches = 0;
+  bool first_reduce = true;
+  size_t pcount = 0;
+  const unsigned long long len = hi - lo;
+
+  int B = env_int("SP_DENSE_LOWCOLS", 4);
+  if (B != 3 && B != 4) B = 4;
+  const bool reg_ok = (n >= SPB_REG_NMIN && n <= SPB_REG_NMAX && env_int("SP_DENSE_FORCE_SMEM", 0) == 0);
+  unsigned long long body_lo = lo, body_hi = lo;   // empty body by default
+  int c = 0;
+  if (reg_ok && len >= (1ull << (B + 1))) {
+    // tile = 2^c indices per thread: large enough to amortise the explicit X start (n-c+1 column
+    // adds), small enough that a launch has >= 2^tiles_log2 tiles to balance over the SMs.
+    const int tiles_log2 = env_int("SP_DENSE_TILES_LOG2", 22);
+    c = env_int("SP_DENSE_TILE_LOG2", 0);
+    if (c <= 0) {
+      c = ilog2_ull(len) - tiles_log2;
+      if (c > 14) c = 14;
+    }
+    if (c < B + 1) c = B + 1;
+    if (c > n - 1) c = n - 1;
+    const unsigned long long T = 1ull << c;
+    body_lo = (lo + T - 1) & ~(T - 1);
+    body_hi = hi & ~(T - 1);
+    if (body_hi <= body_lo) { body_lo = body_hi = lo; }
+  }
+
+  int rc;
+  if (body_hi > body_lo) {
+    p->info.path = SPD_PATH_DENSE_REG;
+    p->info.tile_log2 = c;
+    unsigned long long tile = body_lo >> c;
+    unsigned long long tiles_left = (body_hi - body_lo) >> c;
+    const unsigned long long max_tiles = 1ull << 27;   // <= 2^20 blocks (8 MiB of partials) per launch
+    while (tiles_left) {
+      const unsigned long long nt = tiles_left < max_tiles ? tiles_left : max_tiles;
+      const size_t blocks = (size_t)((nt + SPB_REG_THREADS - 1) / SPB_REG_THREADS);
+      if (pcount + blocks > (1u << 21)) {   // flush what we have
+        rc = launch_reduce(L, L.d_partials, pcount, L.d_result, 0, !first_reduce);
+        if (rc != SPD_OK) return rc;
+        first_reduce = false; pcount = 0; ++launches;
+      }
+      rc = lane_reserve_partials(&L, pcount + blocks);
+      if (rc != SPD_OK) return rc;
+      unsigned nb = 0;
+      rc = reg_launch(n, B, L.stream, p->d_mat_t, p->d_xbase, L.d_partials + pcount, tile, nt, c, &nb);
+      if (rc != SPD_OK) { set_error("no register kernel for n=%d B=%d", n, B); return rc; }
+      SPB_CUDA(cudaGetLastError());
+      pcount += nb; ++launches;
+      tile += nt; tiles_left -= nt;
+    }
+    rc = enqueue_smem(p, lo, body_lo, &pcount, &launches);
+    if (rc != SPD_OK) return rc;
+    rc = enqueue_smem(p, body_hi, hi, &pcount, &launches);
+    if (rc != SPD_OK) return rc;
+  } else {
+    rc = enqueue_smem(p, lo, hi, &pcount, &launches);
+    if (rc != SPD_OK) return rc;
+  }
+  if (pcount > 0 || first_reduce) {
+    rc = lane_reserve_partials(&L, 1);
+    if (rc != SPD_OK) return rc;
+    rc = launch_reduce(L, L.d_partials, pcount, L.d_result, 0, !first_reduce);
+    if (rc != SPD_OK) return rc;
+    ++launches;
+  }
+  SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+  SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
+  p->info.launches = launches;
+  p->pending = true;
+  return SPD_OK;
+}
+
+extern "C" {
+
+int spd_dense_plan_create(int device, const double* mat_t, const double* xbase, int nov,
+                          spd_dense_plan** out) {
+  if (!mat_t || !xbase || !out) { set_error("null argument"); return SPD_EINVAL; }
+  if (nov < 2 || nov > 64) { set_error("dense Ryser supports 2 <= n <= 64 (got %d)", nov); return SPD_ELIMIT; }
+  spd_dense_plan* p = new (std::nothrow) spd_dense_plan();
+  if (!p) return SPD_ENOMEM;
+  int rc = lane_acquire(device, &p->lanep);
+  if (rc != SPD_OK) { delete p; return rc; }
+  Lane& L = *p->lanep;
+  p->n = nov;
+  p->smem_bytes = ((size_t)nov * nov + (size_t)nov * SMEMK_THREADS) * sizeof(double);
+  auto fail = [&](int code) { spd_dense_plan_destroy(p); return code; };
+  if ((rc = lane_arena_alloc(&L, (size_t)nov * nov * sizeof(double), (void**)&p->d_mat_t)) != SPD_OK) return fail(rc);
+  if ((rc = lane_arena_alloc(&L, (size_t)nov * sizeof(double), (void**)&p->d_xbase)) != SPD_OK) return fail(rc);
+  cudaError_t e;
+  // pageable sources: the copies are staged by the runtime before returning, so the caller's
+  // arrays are not referenced after this function
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(p->d_mat_t, mat_t, (size_t)nov * nov * sizeof(double), cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(p->d_xbase, xbase, (size_t)nov * sizeof(double), cudaMemcpyHostToDevice, L.stream)) != cudaSuccess) {
+    set_error("dense plan upload: %s", cudaGetErrorString(e));
+    return fail(SPD_ECUDA);
+  }
+  if (p->smem_bytes > 48 * 1024) {
+    e = cudaFuncSetAttribute(ryser_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->smem_bytes, cudaGetErrorString(e)); return fail(SPD_ECUDA); }
+  }
+  rc = lane_reserve_partials(&L, (1u << 21) + 4096);
+  if (rc != SPD_OK) return fail(rc);
+  *out = p;
+  return SPD_OK;
+}
+
+void spd_dense_plan_destroy(spd_dense_plan* p) {
+  if (!p) return;
+  lane_release(p->lanep);
+  delete p;
+}
+
+int spd_dense_plan_launch(spd_dense_plan* p, unsigned long long lo, unsigned long long hi) {
+  if (!p) { set_error("null plan"); return SPD_EINVAL; }
+  if (p->pending) { set_error("plan already has a pending run"); return SPD_EINVAL; }
+  return dense_enqueue(p, lo, hi);
+}
+
+int spd_dense_plan_wait(spd_dense_plan* p, double* sum, spd_run_info* info) {
+  if (!p || !p->pending) { set_error("no pending run"); return SPD_EINVAL; }
+  p->pending = false;
+  SPB_CUDA(cudaSetDevice(p->lanep->device));
+  SPB_CUDA(cudaEventSynchronize(p->lanep->ev1));
+  float ms = 0.f;
+  SPB_CUDA(cudaEventElapsedTime(&ms, p->lanep->ev0, p->lanep->ev1));
+  p->info.kernel_ms = ms;
+  if (sum) *sum = p->lanep->h_result[0];
+  if (info) *info = p->info;
+  return SPD_OK;
+}
+
+int spd_dense_plan_run(spd_dense_plan* p, unsigned long long lo, unsigned long long hi, double* sum,
+                       spd_run_info* info) {
+  int rc = spd_dense_plan_launch(p, lo, hi);
+  if (rc != SPD_OK) return rc;
+  return spd_dense_plan_wait(p, sum, info);
+}
+
+}  // extern "C"

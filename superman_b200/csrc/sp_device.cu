@@ -1,0 +1,286 @@
+// Device plumbing of libsuperman_b200.so: error reporting, per-plan lanes (stream + events +
+// pinned result slot), the deterministic partial-sum reduction and the FP64 issue-rate probe.
+#include "sp_internal.cuh"
+#include <string.h>
+#include <mutex>
+
+namespace spb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no usable CUDA device (%s); libsuperman_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return SPD_ENODEV;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (have %d)", device, n);
+    return SPD_EINVAL;
+  }
+  return SPD_OK;
+}
+
+static int lane_create(int device, Lane* lane) {
+  SPB_CUDA(cudaSetDevice(device));
+  lane->device = device;
+  SPB_CUDA(cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking));
+  SPB_CUDA(cudaEventCreate(&lane->ev0));
+  SPB_CUDA(cudaEventCreate(&lane->ev1));
+  SPB_CUDA(cudaMallocHost(&lane->h_result, 8 * sizeof(double)));
+  SPB_CUDA(cudaMalloc(&lane->d_result, 8 * sizeof(double)));
+  lane->arena_cap = 4u << 20;
+  SPB_CUDA(cudaMalloc(&lane->d_arena, lane->arena_cap));
+  SPB_CUDA(cudaDeviceGetAttribute(&lane->sm_count, cudaDevAttrMultiProcessorCount, device));
+  return SPD_OK;
+}
+
+static void lane_destroy(Lane* lane) {
+  if (lane->device < 0) return;
+  cudaSetDevice(lane->device);
+  if (lane->stream) cudaStreamSynchronize(lane->stream);
+  if (lane->d_partials) cudaFree(lane->d_partials);
+  if (lane->d_arena) cudaFree(lane->d_arena);
+  if (lane->d_result) cudaFree(lane->d_result);
+  if (lane->h_result) cudaFreeHost(lane->h_result);
+  if (lane->ev0) cudaEventDestroy(lane->ev0);
+  if (lane->ev1) cudaEventDestroy(lane->ev1);
+  if (lane->stream) cudaStreamDestroy(lane->stream);
+  *lane = Lane();
+}
+
+#define SPB_MAX_LANES 256
+static std::mutex g_pool_mu;
+static Lane* g_pool[SPB_MAX_LANES];
+static int g_pool_n = 0;
+
+int lane_acquire(int device, Lane** out) {
+  int rc = check_device(device);
+  if (rc != SPD_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (int i = 0; i < g_pool_n; ++i) {
+      if (g_pool[i]->device == device && !g_pool[i]->busy) {
+        g_pool[i]->busy = true;
+        g_pool[i]->arena_used = 0;
+        *out = g_pool[i];
+        return SPD_OK;
+      }
+    }
+    if (g_pool_n >= SPB_MAX_LANES) { set_error("too many concurrent plans"); return SPD_ELIMIT; }
+  }
+  Lane* lane = new Lane();
+  rc = lane_create(device, lane);   // outside the lock: context creation can take 100s of ms
+  if (rc != SPD_OK) { lane_destroy(lane); delete lane; return rc; }
+  lane->busy = true;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool_n >= SPB_MAX_LANES) { lane_destroy(lane); delete lane; set_error("too many concurrent plans"); return SPD_ELIMIT; }
+  g_pool[g_pool_n++] = lane;
+  *out = lane;
+  return SPD_OK;
+}
+
+void lane_release(Lane* lane) {
+  if (!lane) return;
+  if (lane->stream) { cudaSetDevice(lane->device); cudaStreamSynchronize(lane->stream); }
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  lane->arena_used = 0;
+  lane->busy = false;
+}
+
+int lane_arena_alloc(Lane* lane, size_t bytes, void** ptr) {
+  const size_t off = (lane->arena_used + 255) & ~(size_t)255;
+  if (off + bytes > lane->arena_cap) {
+    set_error("plan inputs (%zu B) exceed the device arena (%zu B)", off + bytes, lane->arena_cap);
+    return SPD_ELIMIT;
+  }
+  *ptr = lane->d_arena + off;
+  lane->arena_used = off + bytes;
+  return SPD_OK;
+}
+
+int lane_reserve_partials(Lane* lane, size_t count) {
+  if (count <= lane->partials_cap) return SPD_OK;
+  SPB_CUDA(cudaSetDevice(lane->device));
+  size_t cap = 1024;
+  while (cap < count) cap <<= 1;
+  double* fresh = nullptr;
+  SPB_CUDA(cudaMalloc(&fresh, cap * sizeof(double)));
+  if (lane->d_partials) {
+    // partial sums of kernels already queued on the stream must survive the move
+    SPB_CUDA(cudaMemcpyAsync(fresh, lane->d_partials, lane->partials_cap * sizeof(double),
+                             cudaMemcpyDeviceToDevice, lane->stream));
+    SPB_CUDA(cudaStreamSynchronize(lane->stream));
+    SPB_CUDA(cudaFree(lane->d_partials));
+  }
+  lane->d_partials = fresh;
+  lane->partials_cap = cap;
+  return SPD_OK;
+}
+
+// ---- deterministic reduction ------------------------------------------------------------------
+// One block; thread t adds partials[t], partials[t+1024], ... as a double-double (error-free
+// TwoSum), then the 1024 double-doubles are merged by a fixed binary tree.  The result depends
+// only on the values and their order, never on scheduling, so a permanent is bit-reproducible
+// from run to run (the reference adds 2^18 per-thread partials serially on the host,
+// gpu_exact_dense.cu:691-693).
+__device__ __forceinline__ void two_sum(double a, double b, double& s, double& e) {
+  s = a + b;
+  const double bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+
+__global__ void __launch_bounds__(1024, 1)
+reduce_kernel(const double* __restrict__ partials, unsigned long long count, double* out, int slot,
+              int accumulate) {
+  __shared__ double hi[1024];
+  __shared__ double lo[1024];
+  double h = 0.0, l = 0.0;
+  for (unsigned long long i = threadIdx.x; i < count; i += 1024) {
+    double s, e;
+    two_sum(h, partials[i], s, e);
+    h = s;
+    l += e;
+  }
+  hi[threadIdx.x] = h;
+  lo[threadIdx.x] = l;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      double s, e;
+      two_sum(hi[threadIdx.x], hi[threadIdx.x + w], s, e);
+      hi[threadIdx.x] = s;
+      lo[threadIdx.x] = lo[threadIdx.x] + lo[threadIdx.x + w] + e;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double v = hi[0] + lo[0];
+    out[slot] = accumulate ? out[slot] + v : v;
+  }
+}
+
+int launch_reduce(const Lane& lane, const double* partials, size_t count, double* out, int slot,
+                  bool accumulate) {
+  reduce_kernel<<<1, 1024, 0, lane.stream>>>(partials, (unsigned long long)count, out, slot,
+                                             accumulate ? 1 : 0);
+  SPB_CUDA(cudaGetLastError());
+  return SPD_OK;
+}
+
+// ---- FP64 issue-rate probe -----------------------------------------------------------------------
+// 8 independent DFMA chains per thread, nothing else in the loop: the rate this sustains is the
+// ceiling of the dense Ryser kernel, whose work is 2n FP64 instructions per Gray index and no
+// memory traffic (peak = #SM x 64 lanes x f_SM, to be measured).
+__global__ void __launch_bounds__(256, 2)
+fp64_probe_kernel(double* out, double a, double b, int iters) {
+  double c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5,
+         c6 = c0 + 6, c7 = c0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      c0 = fma(c0, a, b); c1 = fma(c1, a, b); c2 = fma(c2, a, b); c3 = fma(c3, a, b);
+      c4 = fma(c4, a, b); c5 = fma(c5, a, b); c6 = fma(c6, a, b); c7 = fma(c7, a, b);
+    }
+  }
+  const double s = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
+  if (s == 12345.678) out[0] = s;   // never true for the probe's inputs; keeps the chains alive
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" {
+
+int spd_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return SPD_ENODEV;
+  }
+  return n;
+}
+
+const char* spd_last_error(void) { return g_err; }
+
+void spd_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (int i = 0; i < g_pool_n; ++i) { lane_destroy(g_pool[i]); delete g_pool[i]; }
+  g_pool_n = 0;
+}
+
+int spd_device_name(int device, char* buf, int buflen) {
+  int rc = check_device(device);
+  if (rc != SPD_OK) return rc;
+  cudaDeviceProp p;
+  SPB_CUDA(cudaGetDeviceProperties(&p, device));
+  snprintf(buf, (size_t)buflen, "%s", p.name);
+  return SPD_OK;
+}
+
+int spd_device_sm_count(int device) {
+  int rc = check_device(device);
+  if (rc != SPD_OK) return rc;
+  int v = 0;
+  SPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+  return v;
+}
+
+int spd_device_sm_clock_khz(int device) {
+  int rc = check_device(device);
+  if (rc != SPD_OK) return rc;
+  int v = 0;
+  SPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device));
+  return v;
+}
+
+double spd_fp64_peak_instr_per_s(int device, int millis) {
+  Lane* lp = nullptr;
+  if (lane_acquire(device, &lp) != SPD_OK) return -1.0;
+  Lane& lane = *lp;
+  cudaSetDevice(device);
+  const int threads = 256, blocks = lane.sm_count * 8;
+  const double per_iter = 16.0 * 8.0;   // DFMA per thread per loop trip
+  auto run = [&](int iters, float* ms) -> int {
+    SPB_CUDA(cudaEventRecord(lane.ev0, lane.stream));
+    fp64_probe_kernel<<<blocks, threads, 0, lane.stream>>>(lane.d_result, 1.0000001, 1e-9, iters);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(lane.ev1, lane.stream));
+    SPB_CUDA(cudaEventSynchronize(lane.ev1));
+    SPB_CUDA(cudaEventElapsedTime(ms, lane.ev0, lane.ev1));
+    return SPD_OK;
+  };
+  float ms = 0.f;
+  int iters = 2000;
+  double best = -1.0;
+  if (run(iters, &ms) == SPD_OK && run(iters, &ms) == SPD_OK && ms > 0.f) {
+    // scale to the requested duration, then take the best of 3
+    double scale = (double)(millis > 0 ? millis : 50) / ms;
+    long long it2 = (long long)(iters * scale);
+    if (it2 < 1000) it2 = 1000;
+    if (it2 > 50000000) it2 = 50000000;
+    for (int rep = 0; rep < 3; ++rep) {
+      if (run((int)it2, &ms) != SPD_OK) { best = -1.0; break; }
+      const double rate = per_iter * (double)it2 * (double)threads * (double)blocks / (ms * 1e-3);
+      if (rate > best) best = rate;
+    }
+  }
+  lane_release(lp);
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+/* C-ABI entry points of libsuperman_b200.so: the host halves of the reference's gpu_perman64_*
+ * wrappers (NW preamble, transpose, partition choice, final factor), in C, on top of the device
+ * layer (superman_b200_device.h) and the chunk scheduler (sp_sched.h). */
+#define _POSIX_C_SOURCE 200809L
+#include "superman_b200.h"
+#include "superman_b200_device.h"
+#include "sp_sched.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+const char *sp_version(void) { return "superman_b200 0.1 (sm_100a)"; }
+
+int sp_device_count(void) {
+  int n = spd_device_count();
+  if (n < 0) sp_set_error("%s", spd_last_error());
+  return n;
+}
+
+double sp_nw_factor(int nov) { return (double)(4 * (nov & 1) - 2); }
+
+double sp_fp64_peak(int device, int millis) {
+  double r = spd_fp64_peak_instr_per_s(device, millis);
+  if (r < 0) sp_set_error("%s", spd_last_error());
+  return r;
+}
+
+static void stats_clear(sp_stats *st) {
+  if (st) memset(st, 0, sizeof(*st));
+}
+
+static double fail(sp_stats *st, int code) {
+  if (st) st->error = code;
+  return NAN;
+}
+
+/* ---- Nijenhuis-Wilf preamble (gpu_exact_dense.cu:642-662) ------------------------------------ */
+/* x[j] = A[j][n-1] - rowsum_j / 2, and the transposed matrix mat_t[k*n+j] = A[j][k]. */
+static void nw_preamble(const double *mat, int nov, double *x, double *mat_t) {
+  for (int j = 0; j < nov; ++j) {
+    double rs = 0.0;
+    for (int k = 0; k < nov; ++k) rs += mat[j * nov + k];
+    x[j] = mat[j * nov + (nov - 1)] - rs / 2;
+  }
+  if (mat_t) {
+    for (int i = 0; i < nov; ++i)
+      for (int j = 0; j < nov; ++j) mat_t[i * nov + j] = mat[j * nov + i];
+  }
+}
+
+/* ---- dense job for the scheduler ------------------------------------------------------------- */
+typedef struct dense_job {
+  const double *mat_t;
+  const double *x;
+  int nov;
+} dense_job;
+
+static int dense_open(const void *job, int device, void **plan) {
+  const dense_job *j = (const dense_job *)job;
+  return spd_dense_plan_create(device, j->mat_t, j->x, j->nov, (spd_dense_plan **)plan);
+}
+static int dense_launch(void *plan, unsigned long long lo, unsigned long long hi) {
+  return spd_dense_plan_launch((spd_dense_plan *)plan, lo, hi);
+}
+static int dense_wait(void *plan, double *sum, spd_run_info *info) {
+  return spd_dense_plan_wait((spd_dense_plan *)plan, sum, info);
+}
+static void dense_close(void *plan) { spd_dense_plan_destroy((spd_dense_plan *)plan); }
+
+static const sp_job_ops g_dense_ops = {dense_open, dense_launch, dense_wait, dense_close};
+
+/* number of chunks of the dynamic paths: the reference uses 2^(nov-29) (dense,
+ * gpu_exact_dense.cu:786-793) or 2^(nov-30) (sparse, gpu_exact_sparse.cu:1005-1008), i.e. chunks of
+ * about 2^28 / 2^29 indices; we keep that rule but never hand a device fewer than 8 chunks to
+ * balance, as long as a chunk still has 2^22 indices. */
+unsigned long long sp_dynamic_chunks(int nov, int ref_base, int gpu_num) {
+  unsigned long long chunks = 1;
+  for (int i = ref_base; i < nov; ++i) chunks *= 2;
+  const unsigned long long want = 8ull * (unsigned long long)(gpu_num > 0 ? gpu_num : 1);
+  const unsigned long long total = 1ull << (nov - 1);
+  while (chunks < want && total / (chunks * 2) >= (1ull << 22)) chunks *= 2;
+  return chunks;
+}
+
+static int check_dense_args(const double *mat, int nov, sp_stats *st) {
+  if (!mat) { sp_set_error("mat is NULL"); if (st) st->error = SP_EINVAL; return SP_EINVAL; }
+  if (nov < 1 || nov > 64) {
+    sp_set_error("dense Ryser supports 1 <= n <= 64 (got %d)", nov);
+    if (st) st->error = SP_ELIMIT;
+    return SP_ELIMIT;
+  }
+  return SP_OK;
+}
+
+double sp_dense_ryser(const double *mat, int nov, int algo_id, int gpu_num, int use_cpu, int threads,
+                      sp_stats *stats) {
+  (void)use_cpu; (void)threads;
+  const double t0 = sp_now_ms();
+  stats_clear(stats);
+  if (check_dense_args(mat, nov, stats) != SP_OK) return NAN;
+  int mode = SP_SCHED_STATIC;
+  switch (algo_id) {
+    case 0: case 1: case 2: case 3: case 4: gpu_num = 1; break;   /* main.cu:34-58 */
+    case 5: break;                                                 /* main.cu:59-63 */
+    case 6: mode = SP_SCHED_DYNAMIC; break;                        /* main.cu:64-68 */
+    default:
+      sp_set_error("Unknown Algorithm ID");
+      return fail(stats, SP_EALGO);
+  }
+  if (gpu_num < 1) gpu_num = 1;
+  if (nov == 1) {
+    if (spd_device_count() <= 0) { sp_set_error("no CUDA device: %s", spd_last_error()); return fail(stats, SP_ENODEV); }
+    if (stats) stats->wall_ms = sp_now_ms() - t0;
+    return mat[0];
+  }
+  double x[64];
+  double *mat_t = (double *)malloc((size_t)nov * nov * sizeof(double));
+  if (!mat_t) { sp_set_error("out of memory"); return fail(stats, SP_ENOMEM); }
+  nw_preamble(mat, nov, x, mat_t);
+  dense_job job = {mat_t, x, nov};
+  const unsigned long long end = 1ull << (nov - 1);
+  /* never more devices than 2^14-index tiles */
+  while (gpu_num > 1 && (end >> 14) < (unsigned long long)gpu_num) gpu_num--;
+  const unsigned long long chunks = (mode == SP_SCHED_DYNAMIC) ? sp_dynamic_chunks(nov, 29, gpu_num) : 0;
+  double sum = 0.0;
+  /* index 0 (the base term p = prod x, gpu_exact_dense.cu:653) is part of device 0's range */
+  int rc = sp_sched_run(&g_dense_ops, &job, mode, gpu_num, 0, 0ull, end, 14, chunks, &sum, stats);
+  free(mat_t);
+  if (stats) stats->wall_ms = sp_now_ms() - t0;
+  if (rc != SP_OK) return fail(stats, rc);
+  return sp_nw_factor(nov) * sum;
+}
+
+struct sp_dense_handle {
+  spd_dense_plan *plan;
+  int nov;
+  int device;
+};
+
+int sp_dense_open(const double *mat, int nov, int device, sp_dense_handle **h) {
+  if (!h) { sp_set_error("null handle pointer"); return SP_EINVAL; }
+  int rc = check_dense_args(mat, nov, NULL);
+  if (rc != SP_OK) return rc;
+  if (nov < 2) { sp_set_error("resident dense handle needs n >= 2"); return SP_ELIMIT; }
+  double x[64];
+  double *mat_t = (double *)malloc((size_t)nov * nov * sizeof(double));
+  sp_dense_handle *hh = (sp_dense_handle *)calloc(1, sizeof(*hh));
+  if (!mat_t || !hh) { free(mat_t); free(hh); sp_set_error("out of memory"); return SP_ENOMEM; }
+  nw_preamble(mat, nov, x, mat_t);
+  rc = spd_dense_plan_create(device, mat_t, x, nov, &hh->plan);
+  free(mat_t);
+  if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); free(hh); return rc; }
+  hh->nov = nov; hh->device = device;
+  *h = hh;
+  return SP_OK;
+}
+
+double sp_dense_run(sp_dense_handle *h, long long start, long long end, sp_stats *stats) {
+  const double t0 = sp_now_ms();
+  stats_clear(stats);
+  if (!h || !h->plan) { sp_set_error("null handle"); return fail(stats, SP_EINVAL); }
+  if (start < 0 || end < start) { sp_set_error("bad range [%lld, %lld)", start, end); return fail(stats, SP_EINVAL); }
+  double sum = 0.0;
+  spd_run_info info;
+  int rc = spd_dense_plan_run(h->plan, (unsigned long long)start, (unsigned long long)end, &sum, &info);
+  if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
+  if (stats) {
+    stats->kernel_ms = info.kernel_ms;
+    stats->device_ms[0] = info.kernel_ms;
+    stats->device_partial[0] = sum;
+    stats->device_units[0] = info.units;
+    stats->units = info.units; stats->visited = info.visited;
+    stats->devices = 1; stats->chunks = 1; stats->launches = info.launches;
+    stats->path = info.path; stats->tile_log2 = info.tile_log2;
+    stats->wall_ms = sp_now_ms() - t0;
+  }
+  return sum;
+}
+
+void sp_dense_close(sp_dense_handle *h) {
+  if (!h) return;
+  spd_dense_plan_destroy(h->plan);
+  free(h);
+}
+
+double sp_dense_ryser_range(const double *mat, int nov, int device, long long start, long long end,
+                            sp_stats *stats) {
+  const double t0 = sp_now_ms();
+  sp_dense_handle *h = NULL;
+  stats_clear(stats);
+  int rc = sp_dense_open(mat, nov, device, &h);
+  if (rc != SP_OK) return fail(stats, rc);
+  double r = sp_dense_run(h, start, end, stats);
+  sp_dense_close(h);
+  if (stats) stats->wall_ms = sp_now_ms() - t0;
+  return r;
+}

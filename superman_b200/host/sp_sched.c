@@ -1,0 +1,246 @@
+/* Per-device chunk scheduler -- see sp_sched.h. */
+#define _POSIX_C_SOURCE 200809L
+#include "sp_sched.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdatomic.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+static _Thread_local char g_sp_err[512];
+
+void sp_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_sp_err, sizeof(g_sp_err), fmt, ap);
+  va_end(ap);
+}
+
+const char *sp_last_error(void) { return g_sp_err; }
+
+double sp_now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec * 1e3 + (double)ts.tv_nsec * 1e-6;
+}
+
+unsigned long long sp_sched_boundary(unsigned long long lo, unsigned long long hi,
+                                     unsigned long long parts, unsigned long long idx, int align_log2) {
+  if (idx == 0 || parts == 0) return lo;
+  if (idx >= parts) return hi;
+  const unsigned long long len = hi - lo;
+  const unsigned long long q = len / parts, r = len % parts;
+  unsigned long long b = lo + q * idx + (idx < r ? idx : r);
+  if (align_log2 > 0 && align_log2 < 63) {
+    const unsigned long long mask = (1ull << align_log2) - 1ull;
+    b &= ~mask;
+  }
+  if (b < lo) b = lo;
+  if (b > hi) b = hi;
+  return b;
+}
+
+typedef struct sched_shared {
+  const sp_job_ops *ops;
+  const void *job;
+  int mode;
+  int gpu_num, first_device;
+  unsigned long long lo, hi;
+  int align_log2;
+  unsigned long long n_chunks;
+  atomic_ullong next_chunk;
+  atomic_int failed;
+  double *chunk_sum;          /* n_chunks doubles */
+  pthread_mutex_t err_mu;
+  int err_code;
+  char err_msg[512];
+} sched_shared;
+
+typedef struct sched_worker {
+  sched_shared *sh;
+  int rank;                   /* 0 .. gpu_num-1 */
+  double ms;
+  double partial;
+  unsigned long long units, visited;
+  int launches, chunks, path, tile_log2;
+} sched_worker;
+
+static void worker_fail(sched_shared *sh, int code) {
+  pthread_mutex_lock(&sh->err_mu);
+  if (sh->err_code == 0) {
+    sh->err_code = code;
+    snprintf(sh->err_msg, sizeof(sh->err_msg), "%s", spd_last_error());
+  }
+  pthread_mutex_unlock(&sh->err_mu);
+  atomic_store(&sh->failed, 1);
+}
+
+static void worker_account(sched_worker *w, const spd_run_info *info, double sum) {
+  /* dynamic mode keeps two chunks in flight on two streams: their event times overlap, so the
+   * device's busy time is taken from the host clock around its whole loop instead */
+  if (w->sh->mode == SP_SCHED_STATIC) w->ms += info->kernel_ms;
+  w->partial += sum;
+  w->units += info->units;
+  w->visited += info->visited;
+  w->launches += info->launches;
+  w->chunks += 1;
+  w->path = info->path;
+  if (info->tile_log2 > w->tile_log2) w->tile_log2 = info->tile_log2;
+}
+
+static void *worker_main(void *arg) {
+  sched_worker *w = (sched_worker *)arg;
+  sched_shared *sh = w->sh;
+  const sp_job_ops *ops = sh->ops;
+  const int device = sh->first_device + w->rank;
+  void *plan[2] = {NULL, NULL};
+  int rc;
+
+  if (sh->mode == SP_SCHED_STATIC) {
+    const unsigned long long a = sp_sched_boundary(sh->lo, sh->hi, (unsigned long long)sh->gpu_num,
+                                                   (unsigned long long)w->rank, sh->align_log2);
+    const unsigned long long b = sp_sched_boundary(sh->lo, sh->hi, (unsigned long long)sh->gpu_num,
+                                                   (unsigned long long)w->rank + 1, sh->align_log2);
+    if ((rc = ops->open(sh->job, device, &plan[0])) != SPD_OK) { worker_fail(sh, rc); return NULL; }
+    double sum = 0.0;
+    spd_run_info info;
+    if ((rc = ops->launch(plan[0], a, b)) != SPD_OK || (rc = ops->wait(plan[0], &sum, &info)) != SPD_OK) {
+      worker_fail(sh, rc);
+    } else {
+      worker_account(w, &info, sum);
+      sh->chunk_sum[w->rank] = sum;
+    }
+    ops->close(plan[0]);
+    return NULL;
+  }
+
+  /* dynamic: two plans per device, each holding one in-flight chunk */
+  unsigned long long inflight[2];
+  int busy[2] = {0, 0};
+  for (int s = 0; s < 2; ++s) {
+    if ((rc = ops->open(sh->job, device, &plan[s])) != SPD_OK) {
+      worker_fail(sh, rc);
+      if (s == 1) ops->close(plan[0]);
+      return NULL;
+    }
+  }
+  int slot = 0;
+  const double t0 = sp_now_ms();
+  for (;;) {
+    /* refill every idle slot */
+    for (int s = 0; s < 2; ++s) {
+      if (busy[s] || atomic_load(&sh->failed)) continue;
+      const unsigned long long c = atomic_fetch_add(&sh->next_chunk, 1ull);
+      if (c >= sh->n_chunks) continue;
+      const unsigned long long a = sp_sched_boundary(sh->lo, sh->hi, sh->n_chunks, c, sh->align_log2);
+      const unsigned long long b = sp_sched_boundary(sh->lo, sh->hi, sh->n_chunks, c + 1, sh->align_log2);
+      if ((rc = ops->launch(plan[s], a, b)) != SPD_OK) { worker_fail(sh, rc); continue; }
+      inflight[s] = c;
+      busy[s] = 1;
+    }
+    if (!busy[0] && !busy[1]) break;
+    if (!busy[slot]) slot ^= 1;     /* oldest in-flight chunk first */
+    double sum = 0.0;
+    spd_run_info info;
+    rc = ops->wait(plan[slot], &sum, &info);
+    busy[slot] = 0;
+    if (rc != SPD_OK) {
+      worker_fail(sh, rc);
+    } else {
+      worker_account(w, &info, sum);
+      sh->chunk_sum[inflight[slot]] = sum;
+    }
+    slot ^= 1;
+  }
+  w->ms = sp_now_ms() - t0;
+  ops->close(plan[0]);
+  ops->close(plan[1]);
+  return NULL;
+}
+
+int sp_sched_run(const sp_job_ops *ops, const void *job, int mode, int gpu_num, int first_device,
+                 unsigned long long lo, unsigned long long hi, int align_log2,
+                 unsigned long long n_chunks, double *total, sp_stats *stats) {
+  if (gpu_num < 1) gpu_num = 1;
+  if (gpu_num > SP_MAX_DEVICES) {
+    sp_set_error("at most %d devices are supported (asked for %d)", SP_MAX_DEVICES, gpu_num);
+    return SP_ELIMIT;
+  }
+  const int have = spd_device_count();
+  if (have <= 0) {
+    sp_set_error("no CUDA device: %s (libsuperman_b200 has no CPU fallback)", spd_last_error());
+    return SP_ENODEV;
+  }
+  if (first_device + gpu_num > have) {
+    sp_set_error("asked for %d device(s) starting at %d but only %d visible", gpu_num, first_device, have);
+    return SP_EINVAL;
+  }
+  if (mode == SP_SCHED_STATIC) n_chunks = (unsigned long long)gpu_num;
+  if (n_chunks < 1) n_chunks = 1;
+
+  sched_shared sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.ops = ops; sh.job = job; sh.mode = mode;
+  sh.gpu_num = gpu_num; sh.first_device = first_device;
+  sh.lo = lo; sh.hi = hi; sh.align_log2 = align_log2; sh.n_chunks = n_chunks;
+  atomic_init(&sh.next_chunk, 0ull);
+  atomic_init(&sh.failed, 0);
+  sh.chunk_sum = (double *)calloc((size_t)n_chunks, sizeof(double));
+  if (!sh.chunk_sum) { sp_set_error("out of memory"); return SP_ENOMEM; }
+  pthread_mutex_init(&sh.err_mu, NULL);
+
+  sched_worker workers[SP_MAX_DEVICES];
+  pthread_t tids[SP_MAX_DEVICES];
+  memset(workers, 0, sizeof(workers));
+  for (int g = 0; g < gpu_num; ++g) { workers[g].sh = &sh; workers[g].rank = g; }
+  /* rank 0 runs on the calling thread: a single-device call creates no thread at all */
+  for (int g = 1; g < gpu_num; ++g) {
+    if (pthread_create(&tids[g], NULL, worker_main, &workers[g]) != 0) {
+      atomic_store(&sh.failed, 1);
+      sh.err_code = SP_ENOMEM;
+      snprintf(sh.err_msg, sizeof(sh.err_msg), "pthread_create failed");
+      gpu_num = g;
+      break;
+    }
+  }
+  worker_main(&workers[0]);
+  for (int g = 1; g < gpu_num; ++g) pthread_join(tids[g], NULL);
+  pthread_mutex_destroy(&sh.err_mu);
+
+  int rc = SP_OK;
+  if (sh.err_code != 0) {
+    sp_set_error("%s", sh.err_msg);
+    rc = sh.err_code;
+    *total = NAN;
+  } else {
+    /* fixed order: chunk 0, 1, 2, ... (== device rank order for the static split,
+     * gpu_exact_dense.cu:769-771) */
+    double t = 0.0;
+    for (unsigned long long c = 0; c < n_chunks; ++c) t += sh.chunk_sum[c];
+    *total = t;
+  }
+  if (stats) {
+    stats->devices = gpu_num;
+    stats->chunks = (int)(n_chunks > 0x7fffffffULL ? 0x7fffffff : n_chunks);
+    stats->kernel_ms = 0.0;
+    stats->units = 0; stats->visited = 0; stats->launches = 0;
+    for (int g = 0; g < gpu_num; ++g) {
+      stats->device_ms[g] = workers[g].ms;
+      stats->device_partial[g] = workers[g].partial;
+      stats->device_units[g] = workers[g].units;
+      if (workers[g].ms > stats->kernel_ms) stats->kernel_ms = workers[g].ms;
+      stats->units += workers[g].units;
+      stats->visited += workers[g].visited;
+      stats->launches += workers[g].launches;
+      if (workers[g].path) stats->path = workers[g].path;
+      if (workers[g].tile_log2 > stats->tile_log2) stats->tile_log2 = workers[g].tile_log2;
+    }
+    stats->error = rc;
+  }
+  free(sh.chunk_sum);
+  return rc;
+}
