@@ -3,7 +3,7 @@
 #   make oracle         the CPU oracle (test infrastructure) and, when /root/reference exists,
 #                       the reference shim under oracle/_ref/
 NVCC      ?= nvcc
-CC        ?= gcc
+CC        := gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Isuperman_b200/csrc
 CFLAGS    := -O2 -std=c11 -fPIC -Wall -Wextra -Iinclude -Isuperman_b200/host -pthread
@@ -17,7 +17,7 @@ CLI     := $(PKG)/perman
 GROUPS  := 0 1 2 3 4 5 6 7
 CU_SRCS := sp_device sp_dense
 CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o)
-C_SRCS  := sp_sched sp_api
+C_SRCS  := sp_sched sp_api sp_matrix
 C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
 
 all: $(LIB)

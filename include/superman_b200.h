@@ -57,6 +57,37 @@ int         sp_device_count(void);
 const char *sp_version(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Matrix input and preprocessing (host, C): what main.cu does before RunAlgo.
+ * ------------------------------------------------------------------------------------------- */
+#define SP_TYPE_INT    0
+#define SP_TYPE_FLOAT  1
+#define SP_TYPE_DOUBLE 2
+#define SP_MAX_NOV     8192
+
+typedef struct sp_matrix {
+  int nov;          /* order */
+  int nnz;          /* number of entries > 0 (what CRS/CCS hold), counted */
+  int header_nnz;   /* the `nnz` field of the file header (main.cu:497), informational */
+  int type;         /* SP_TYPE_* declared by the file header */
+  double *mat;      /* row-major nov*nov, zero-initialised (fixes main.cu:501,531,564) */
+  int *cptrs, *rows;   double *cvals;   /* CCS: column pointers [nov+1], row ids, values */
+  int *rptrs, *cols;   double *rvals;   /* CRS: row pointers [nov+1], column ids, values */
+} sp_matrix;
+
+/* Header sniff + ReadMatrix<T> (main.cu:494-498, util.h:343-358): `nov nnz {int|float|double}`
+ * then `i j val` lines, 0-based; unparsable lines are skipped; binary != 0 is the -b flag (every
+ * listed entry becomes 1). */
+int  sp_matrix_read(const char *path, int binary, sp_matrix *out);
+int  sp_matrix_from_dense(const double *mat, int nov, sp_matrix *out);
+/* matrix2compressed (preprocessing 0, util.h:522-551), _sortOrder (1, util.h:553-619; rewrites
+ * mat in the new column order) or _skipOrder (2, util.h:621-684; permutes rows and columns). */
+int  sp_matrix_compress(sp_matrix *m, int preprocessing);
+/* gridGraph2compressed (util.h:403-520): biadjacency matrix of the m x n grid, nov = m*n/2,
+ * with CRS and CCS.  Fails when both dimensions are odd. */
+int  sp_matrix_grid(int m, int n, sp_matrix *out);
+void sp_matrix_free(sp_matrix *m);
+
+/* ---------------------------------------------------------------------------------------------
  * Dense exact (Ryser / Nijenhuis-Wilf), ids -p0..-p6 of main.cu:34-75.
  * mat is row-major nov x nov (mat[i*nov+j]), as produced by ReadMatrix (util.h:343-358).
  * ------------------------------------------------------------------------------------------- */

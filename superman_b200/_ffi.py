@@ -91,5 +91,13 @@ _sig("sp_dense_run", C.c_double, [C.c_void_p, C.c_longlong, C.c_longlong, _sp])
 _sig("sp_dense_close", None, [C.c_void_p])
 
 
+_mp = C.POINTER(SpMatrix)
+_sig("sp_matrix_read", C.c_int, [C.c_char_p, C.c_int, _mp])
+_sig("sp_matrix_from_dense", C.c_int, [_dp, C.c_int, _mp])
+_sig("sp_matrix_compress", C.c_int, [_mp, C.c_int])
+_sig("sp_matrix_grid", C.c_int, [C.c_int, C.c_int, _mp])
+_sig("sp_matrix_free", None, [_mp])
+
+
 def last_error() -> str:
     return lib.sp_last_error().decode("utf-8", "replace")

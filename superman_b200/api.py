@@ -12,7 +12,7 @@ from . import _ffi
 from ._ffi import SpStats, lib
 
 __all__ = [
-    "SupermanError", "device_count", "fp64_peak", "nw_factor",
+    "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
     "dense_ryser", "dense_ryser_range", "DenseHandle",
     "gpu_perman64_xglobal", "gpu_perman64_xlocal", "gpu_perman64_xshared",
     "gpu_perman64_xshared_coalescing", "gpu_perman64_xshared_coalescing_mshared",
@@ -43,6 +43,85 @@ def _check(value: float, st: SpStats) -> float:
     if st.error != 0 or (isinstance(value, float) and math.isnan(value) and st.error != 0):
         raise SupermanError(st.error, _ffi.last_error())
     return value
+
+
+class Matrix:
+    """Owner of an sp_matrix: dense row-major `mat` plus CRS/CCS once `compress()` ran.
+    Mirrors what main.cu holds between ReadMatrix and RunAlgo (main.cu:500-528)."""
+
+    def __init__(self):
+        self._m = _ffi.SpMatrix()
+        self._live = False
+
+    # -- constructors -------------------------------------------------------------------------
+    @classmethod
+    def read(cls, path: str, binary: bool = False) -> "Matrix":
+        self = cls()
+        rc = lib.sp_matrix_read(str(path).encode(), int(binary), C.byref(self._m))
+        if rc != 0:
+            raise SupermanError(rc, _ffi.last_error())
+        self._live = True
+        return self
+
+    @classmethod
+    def from_dense(cls, mat, nov=None) -> "Matrix":
+        a = _dmat(mat, nov)
+        n = int(round(math.sqrt(a.size)))
+        self = cls()
+        rc = lib.sp_matrix_from_dense(_ptr(a), n, C.byref(self._m))
+        if rc != 0:
+            raise SupermanError(rc, _ffi.last_error())
+        self._live = True
+        return self
+
+    @classmethod
+    def grid(cls, m: int, n: int) -> "Matrix":
+        self = cls()
+        rc = lib.sp_matrix_grid(m, n, C.byref(self._m))
+        if rc != 0:
+            raise SupermanError(rc, _ffi.last_error())
+        self._live = True
+        return self
+
+    def compress(self, preprocessing: int = 0) -> "Matrix":
+        rc = lib.sp_matrix_compress(C.byref(self._m), preprocessing)
+        if rc != 0:
+            raise SupermanError(rc, _ffi.last_error())
+        return self
+
+    # -- views (copies) ------------------------------------------------------------------------
+    nov = property(lambda self: self._m.nov)
+    nnz = property(lambda self: self._m.nnz)
+    header_nnz = property(lambda self: self._m.header_nnz)
+    type = property(lambda self: ("int", "float", "double")[self._m.type])
+
+    def _arr(self, ptr, count, dtype):
+        if not ptr:
+            return None
+        return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+    @property
+    def mat(self):
+        n = self._m.nov
+        return self._arr(self._m.mat, n * n, np.float64).reshape(n, n)
+
+    cptrs = property(lambda self: self._arr(self._m.cptrs, self._m.nov + 1, np.int32))
+    rptrs = property(lambda self: self._arr(self._m.rptrs, self._m.nov + 1, np.int32))
+    rows = property(lambda self: self._arr(self._m.rows, self._m.nnz, np.int32))
+    cols = property(lambda self: self._arr(self._m.cols, self._m.nnz, np.int32))
+    cvals = property(lambda self: self._arr(self._m.cvals, self._m.nnz, np.float64))
+    rvals = property(lambda self: self._arr(self._m.rvals, self._m.nnz, np.float64))
+
+    def free(self):
+        if self._live:
+            lib.sp_matrix_free(C.byref(self._m))
+            self._live = False
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def device_count() -> int:
