@@ -15,8 +15,8 @@ LIB     := $(PKG)/libsuperman_b200.so
 CLI     := $(PKG)/perman
 
 GROUPS  := 0 1 2 3 4 5 6 7
-CU_SRCS := sp_device sp_dense
-CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o)
+CU_SRCS := sp_device sp_dense sp_sparse
+CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o) $(GROUPS:%=$(BUILD)/sp_sparse_inst_g%.o)
 C_SRCS  := sp_sched sp_api sp_matrix
 C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
 
@@ -29,6 +29,9 @@ $(BUILD)/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h incl
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(BUILD)/sp_dense_inst_g%.o: $(PKG)/csrc/sp_dense_inst.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DSPB_GROUP=$* -c $< -o $@
+
+$(BUILD)/sp_sparse_inst_g%.o: $(PKG)/csrc/sp_sparse_inst.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DSPB_GROUP=$* -c $< -o $@
 
 $(BUILD)/%.o: $(PKG)/host/%.c $(wildcard $(PKG)/host/*.h include/*.h) | $(BUILD)

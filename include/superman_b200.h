@@ -119,6 +119,34 @@ int    sp_dense_open(const double *mat, int nov, int device, sp_dense_handle **h
 double sp_dense_run(sp_dense_handle *h, long long start, long long end, sp_stats *stats);
 void   sp_dense_close(sp_dense_handle *h);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sparse exact: SpaRyser (ids -s -p1..-p6, main.cu:107-136) and SkipPer (ids -s -p7/-p8,
+ * main.cu:137-146).  mat is the dense matrix AFTER the chosen preprocessing (sp_matrix_compress
+ * rewrites it, as util.h:608-618 / 670-681 do), cptrs/rows/cvals its CCS, rptrs/cols its CRS.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces gpu_perman64_xlocal_sparse / _xshared_sparse / _xshared_coalescing_sparse /
+ * _xshared_coalescing_mshared_sparse (gpu_exact_sparse.cu:672,732,792,853; ids 1-4: one device),
+ * _mshared_multigpu_sparse (:916; id 5: static split) and _mshared_multigpucpu_chunks_sparse
+ * (:995; id 6: dynamic chunks of 2^(nov-30)).  Returns the permanent. */
+double sp_sparse_ryser(const double *mat, const int *cptrs, const int *rows, const double *cvals,
+                       int nov, int algo_id, int gpu_num, int use_cpu, int threads, sp_stats *stats);
+
+/* Replaces gpu_perman64_xshared_coalescing_mshared_skipper (gpu_exact_sparse.cu:1123; id 7: one
+ * device) and _mshared_multigpucpu_chunks_skipper (:1192; id 8: dynamic chunks).  rptrs/cols are
+ * accepted for signature parity: the skip test here needs only the column structure.
+ * stats->visited reports how many Gray indices were actually evaluated. */
+double sp_skipper(const double *mat, const int *rptrs, const int *cols, const int *cptrs,
+                  const int *rows, const double *cvals, int nov, int algo_id, int gpu_num, int use_cpu,
+                  int threads, sp_stats *stats);
+
+/* Kernel-level contract (start, end) of the two sparse kernels (gpu_exact_sparse.cu:456, 556) and
+ * of cpu_perman64_sparse / cpu_perman64_skipper (:7, :90): signed sum over Gray indices in
+ * [start, end) on one device, no base term (unless start == 0), no final factor. */
+double sp_sparse_ryser_range(const double *mat, const int *cptrs, const int *rows, const double *cvals,
+                             int nov, int skipper, int device, long long start, long long end,
+                             sp_stats *stats);
+
 /* (4*(nov&1)-2): the factor every wrapper applies to base + sum (gpu_exact_dense.cu:698). */
 double sp_nw_factor(int nov);
 

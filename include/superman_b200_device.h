@@ -76,6 +76,23 @@ int  spd_dense_plan_run(spd_dense_plan *plan, unsigned long long lo, unsigned lo
 int  spd_dense_plan_launch(spd_dense_plan *plan, unsigned long long lo, unsigned long long hi);
 int  spd_dense_plan_wait(spd_dense_plan *plan, double *sum, spd_run_info *info);
 
+/* ---- SpaRyser / SkipPer --------------------------------------------------------------------- */
+typedef struct spd_sparse_plan spd_sparse_plan;
+
+/* dmat_t[k*nov + j] = D[j][k], where D is the CCS (cptrs, rows, cvals) the reference's sparse
+ * kernels iterate over, scattered back to dense form (gpu_exact_sparse.cu:467-476, 521-549);
+ * xbase as for the dense plan but with row sums over the non-zeros of mat
+ * (gpu_exact_sparse.cu:861-871).  skip != 0 selects SkipPer (zero products are skipped,
+ * gpu_exact_sparse.cu:634-666), else SpaRyser.  7 <= nov <= 48 runs the register kernel; other
+ * orders up to 64 run the shared-memory kernel on D. */
+int  spd_sparse_plan_create(int device, const double *dmat_t, const double *xbase, int nov, int skip,
+                            spd_sparse_plan **plan);
+void spd_sparse_plan_destroy(spd_sparse_plan *plan);
+int  spd_sparse_plan_run(spd_sparse_plan *plan, unsigned long long lo, unsigned long long hi,
+                         double *sum, spd_run_info *info);
+int  spd_sparse_plan_launch(spd_sparse_plan *plan, unsigned long long lo, unsigned long long hi);
+int  spd_sparse_plan_wait(spd_sparse_plan *plan, double *sum, spd_run_info *info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,10 @@ _sig("sp_dense_run", C.c_double, [C.c_void_p, C.c_longlong, C.c_longlong, _sp])
 _sig("sp_dense_close", None, [C.c_void_p])
 
 
+_sig("sp_sparse_ryser", C.c_double, [_dp, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _sp])
+_sig("sp_skipper", C.c_double, [_dp, _ip, _ip, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _sp])
+_sig("sp_sparse_ryser_range", C.c_double, [_dp, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, _sp])
+
 _mp = C.POINTER(SpMatrix)
 _sig("sp_matrix_read", C.c_int, [C.c_char_p, C.c_int, _mp])
 _sig("sp_matrix_from_dense", C.c_int, [_dp, C.c_int, _mp])

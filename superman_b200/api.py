@@ -14,6 +14,12 @@ from ._ffi import SpStats, lib
 __all__ = [
     "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
     "dense_ryser", "dense_ryser_range", "DenseHandle",
+    "sparse_ryser", "skipper", "sparse_ryser_range",
+    "gpu_perman64_xlocal_sparse", "gpu_perman64_xshared_sparse", "gpu_perman64_xshared_coalescing_sparse",
+    "gpu_perman64_xshared_coalescing_mshared_sparse", "gpu_perman64_xshared_coalescing_mshared_multigpu_sparse",
+    "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_sparse",
+    "gpu_perman64_xshared_coalescing_mshared_skipper",
+    "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_skipper",
     "gpu_perman64_xglobal", "gpu_perman64_xlocal", "gpu_perman64_xshared",
     "gpu_perman64_xshared_coalescing", "gpu_perman64_xshared_coalescing_mshared",
     "gpu_perman64_xshared_coalescing_mshared_multigpu",
@@ -187,6 +193,88 @@ class DenseHandle:
             self.close()
         except Exception:
             pass
+
+
+def _iarr(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def _iptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _darr(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def sparse_ryser(mat, cptrs, rows, cvals, nov=None, algo_id=4, gpu_num=1, cpu=False, threads=16,
+                 stats: SpStats | None = None) -> float:
+    a = _dmat(mat, nov)
+    nov = int(round(math.sqrt(a.size)))
+    cp, ro, cv = _iarr(cptrs), _iarr(rows), _darr(cvals)
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_sparse_ryser(_ptr(a), _iptr(cp), _iptr(ro), _ptr(cv), nov, algo_id, gpu_num, int(cpu), threads, C.byref(st))
+    return _check(v, st)
+
+
+def skipper(mat, rptrs, cols, cptrs, rows, cvals, nov=None, algo_id=7, gpu_num=1, cpu=False, threads=16,
+            stats: SpStats | None = None) -> float:
+    a = _dmat(mat, nov)
+    nov = int(round(math.sqrt(a.size)))
+    rp, co, cp, ro, cv = _iarr(rptrs), _iarr(cols), _iarr(cptrs), _iarr(rows), _darr(cvals)
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_skipper(_ptr(a), _iptr(rp), _iptr(co), _iptr(cp), _iptr(ro), _ptr(cv), nov, algo_id, gpu_num,
+                       int(cpu), threads, C.byref(st))
+    return _check(v, st)
+
+
+def sparse_ryser_range(mat, cptrs, rows, cvals, start, end, nov=None, skipper=False, device=0,
+                       stats: SpStats | None = None) -> float:
+    a = _dmat(mat, nov)
+    nov = int(round(math.sqrt(a.size)))
+    cp, ro, cv = _iarr(cptrs), _iarr(rows), _darr(cvals)
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_sparse_ryser_range(_ptr(a), _iptr(cp), _iptr(ro), _ptr(cv), nov, int(skipper), device, start, end, C.byref(st))
+    return _check(v, st)
+
+
+# ---- reference wrapper names (gpu_exact_sparse.cu:672,732,792,853,916,995,1123,1192) ------------
+def gpu_perman64_xlocal_sparse(mat, cptrs, rows, cvals, nov, grid_dim=2048, block_dim=256):
+    return sparse_ryser(mat, cptrs, rows, cvals, nov, 1)
+
+
+def gpu_perman64_xshared_sparse(mat, cptrs, rows, cvals, nov, grid_dim=2048, block_dim=256):
+    return sparse_ryser(mat, cptrs, rows, cvals, nov, 2)
+
+
+def gpu_perman64_xshared_coalescing_sparse(mat, cptrs, rows, cvals, nov, grid_dim=2048, block_dim=256):
+    return sparse_ryser(mat, cptrs, rows, cvals, nov, 3)
+
+
+def gpu_perman64_xshared_coalescing_mshared_sparse(mat, cptrs, rows, cvals, nov, grid_dim=2048, block_dim=256):
+    return sparse_ryser(mat, cptrs, rows, cvals, nov, 4)
+
+
+def gpu_perman64_xshared_coalescing_mshared_multigpu_sparse(mat, cptrs, rows, cvals, nov, gpu_num,
+                                                            grid_dim=2048, block_dim=256):
+    return sparse_ryser(mat, cptrs, rows, cvals, nov, 5, gpu_num)
+
+
+def gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_sparse(mat, cptrs, rows, cvals, nov, gpu_num,
+                                                                      cpu=False, threads=16,
+                                                                      grid_dim=2048, block_dim=256):
+    return sparse_ryser(mat, cptrs, rows, cvals, nov, 6, gpu_num, cpu, threads)
+
+
+def gpu_perman64_xshared_coalescing_mshared_skipper(mat, rptrs, cols, cptrs, rows, cvals, nov,
+                                                    grid_dim=2048, block_dim=256):
+    return skipper(mat, rptrs, cols, cptrs, rows, cvals, nov, 7)
+
+
+def gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_skipper(mat, rptrs, cols, cptrs, rows, cvals, nov,
+                                                                       gpu_num, cpu=False, threads=16,
+                                                                       grid_dim=2048, block_dim=256):
+    return skipper(mat, rptrs, cols, cptrs, rows, cvals, nov, 8, gpu_num, cpu, threads)
 
 
 # ---- reference wrapper names (gpu_exact_dense.cu:401,459,518,576,640,701,776) -------------------

@@ -92,12 +92,6 @@ ryser_smem_kernel(const double* __restrict__ mat_t, const double* __restrict__ x
   }
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  if (!s || !*s) return dflt;
-  return atoi(s);
-}
-
 static int reg_launch(int n, int B, cudaStream_t st, const double* mat_t, const double* xbase,
                       double* partials, unsigned long long tile_first, unsigned long long n_tiles,
                       int c, unsigned* blocks_out) {
@@ -113,6 +107,40 @@ static int reg_launch(int n, int B, cudaStream_t st, const double* mat_t, const 
   }
 }
 
+// ragged piece [lo, hi) through the shared-memory kernel; appends its blocks to the partial array
+int enqueue_smem_range(Lane* L, const double* d_mat_t, const double* d_xbase, int n,
+                       unsigned long long lo, unsigned long long hi, size_t* pcount, int* launches) {
+  if (hi <= lo) return SPD_OK;
+  const size_t smem_bytes = ((size_t)n * n + (size_t)n * SMEMK_THREADS) * sizeof(double);
+  const unsigned long long len = hi - lo;
+  const unsigned long long want_threads = (unsigned long long)L->sm_count * 4 * SMEMK_THREADS;
+  unsigned long long per_thread = (len + want_threads - 1) / want_threads;
+  unsigned long long pt = 16;       // at least 16 indices per thread: amortises the explicit X start
+  while (pt < per_thread) pt <<= 1; // power of two keeps the flipped column warp-uniform
+  per_thread = pt;
+  const unsigned long long threads = (len + per_thread - 1) / per_thread;
+  const unsigned long long blocks = (threads + SMEMK_THREADS - 1) / SMEMK_THREADS;
+  int rc = lane_reserve_partials(L, *pcount + (size_t)blocks);
+  if (rc != SPD_OK) return rc;
+  ryser_smem_kernel<<<(unsigned)blocks, SMEMK_THREADS, smem_bytes, L->stream>>>(
+      d_mat_t, d_xbase, n, lo, hi, per_thread, L->d_partials + *pcount);
+  SPB_CUDA(cudaGetLastError());
+  *pcount += (size_t)blocks;
+  *launches += 1;
+  return SPD_OK;
+}
+
+// opt in to > 48 KiB of dynamic shared memory when n needs it (the reference never does and
+// silently fails to launch)
+int smem_kernel_prepare(int n) {
+  const size_t smem_bytes = ((size_t)n * n + (size_t)n * SMEMK_THREADS) * sizeof(double);
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ryser_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", smem_bytes, cudaGetErrorString(e)); return SPD_ECUDA; }
+  }
+  return SPD_OK;
+}
+
 }  // namespace spb
 
 using namespace spb;
@@ -122,37 +150,13 @@ struct spd_dense_plan {
   int n = 0;
   double* d_mat_t = nullptr;
   double* d_xbase = nullptr;
-  size_t smem_bytes = 0;
   bool pending = false;
   spd_run_info info;
 };
 
-static int ilog2_ull(unsigned long long v) {
-  int r = -1;
-  while (v) { v >>= 1; ++r; }
-  return r;
-}
-
-// ragged piece [lo, hi) through the shared-memory kernel; appends its blocks to the partial array
 static int enqueue_smem(spd_dense_plan* p, unsigned long long lo, unsigned long long hi,
                         size_t* pcount, int* launches) {
-  if (hi <= lo) return SPD_OK;
-  const unsigned long long len = hi - lo;
-  const unsigned long long want_threads = (unsigned long long)p->lanep->sm_count * 4 * SMEMK_THREADS;
-  unsigned long long per_thread = (len + want_threads - 1) / want_threads;
-  unsigned long long pt = 16;       // at least 16 indices per thread: amortises the explicit X start
-  while (pt < per_thread) pt <<= 1; // power of two keeps the flipped column warp-uniform
-  per_thread = pt;
-  const unsigned long long threads = (len + per_thread - 1) / per_thread;
-  const unsigned long long blocks = (threads + SMEMK_THREADS - 1) / SMEMK_THREADS;
-  int rc = lane_reserve_partials(p->lanep, *pcount + (size_t)blocks);
-  if (rc != SPD_OK) return rc;
-  ryser_smem_kernel<<<(unsigned)blocks, SMEMK_THREADS, p->smem_bytes, p->lanep->stream>>>(
-      p->d_mat_t, p->d_xbase, p->n, lo, hi, per_thread, p->lanep->d_partials + *pcount);
-  SPB_CUDA(cudaGetLastError());
-  *pcount += (size_t)blocks;
-  *launches += 1;
-  return SPD_OK;
+  return enqueue_smem_range(p->lanep, p->d_mat_t, p->d_xbase, p->n, lo, hi, pcount, launches);
 }
 
 static int dense_enqueue(spd_dense_plan* p, unsigned long long lo, unsigned long long hi) {
@@ -254,7 +258,6 @@ int spd_dense_plan_create(int device, const double* mat_t, const double* xbase, 
   if (rc != SPD_OK) { delete p; return rc; }
   Lane& L = *p->lanep;
   p->n = nov;
-  p->smem_bytes = ((size_t)nov * nov + (size_t)nov * SMEMK_THREADS) * sizeof(double);
   auto fail = [&](int code) { spd_dense_plan_destroy(p); return code; };
   if ((rc = lane_arena_alloc(&L, (size_t)nov * nov * sizeof(double), (void**)&p->d_mat_t)) != SPD_OK) return fail(rc);
   if ((rc = lane_arena_alloc(&L, (size_t)nov * sizeof(double), (void**)&p->d_xbase)) != SPD_OK) return fail(rc);
@@ -267,10 +270,7 @@ int spd_dense_plan_create(int device, const double* mat_t, const double* xbase, 
     set_error("dense plan upload: %s", cudaGetErrorString(e));
     return fail(SPD_ECUDA);
   }
-  if (p->smem_bytes > 48 * 1024) {
-    e = cudaFuncSetAttribute(ryser_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
-    if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->smem_bytes, cudaGetErrorString(e)); return fail(SPD_ECUDA); }
-  }
+  if ((rc = smem_kernel_prepare(nov)) != SPD_OK) return fail(rc);
   rc = lane_reserve_partials(&L, (1u << 21) + 4096);
   if (rc != SPD_OK) return fail(rc);
   *out = p;

@@ -1,6 +1,7 @@
 // Device plumbing of libsuperman_b200.so: error reporting, per-plan lanes (stream + events +
 // pinned result slot), the deterministic partial-sum reduction and the FP64 issue-rate probe.
 #include "sp_internal.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
@@ -51,6 +52,7 @@ static void lane_destroy(Lane* lane) {
   if (lane->stream) cudaStreamSynchronize(lane->stream);
   if (lane->d_partials) cudaFree(lane->d_partials);
   if (lane->d_arena) cudaFree(lane->d_arena);
+  if (lane->d_aux) cudaFree(lane->d_aux);
   if (lane->d_result) cudaFree(lane->d_result);
   if (lane->h_result) cudaFreeHost(lane->h_result);
   if (lane->ev0) cudaEventDestroy(lane->ev0);
@@ -128,6 +130,36 @@ int lane_reserve_partials(Lane* lane, size_t count) {
   return SPD_OK;
 }
 
+int lane_reserve_aux(Lane* lane, size_t count) {
+  if (count <= lane->aux_cap) return SPD_OK;
+  SPB_CUDA(cudaSetDevice(lane->device));
+  size_t cap = 1024;
+  while (cap < count) cap <<= 1;
+  unsigned long long* fresh = nullptr;
+  SPB_CUDA(cudaMalloc(&fresh, cap * sizeof(unsigned long long)));
+  if (lane->d_aux) {
+    SPB_CUDA(cudaMemcpyAsync(fresh, lane->d_aux, lane->aux_cap * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToDevice, lane->stream));
+    SPB_CUDA(cudaStreamSynchronize(lane->stream));
+    SPB_CUDA(cudaFree(lane->d_aux));
+  }
+  lane->d_aux = fresh;
+  lane->aux_cap = cap;
+  return SPD_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  if (!s || !*s) return dflt;
+  return atoi(s);
+}
+
+int ilog2_ull(unsigned long long v) {
+  int r = -1;
+  while (v) { v >>= 1; ++r; }
+  return r;
+}
+
 // ---- deterministic reduction ------------------------------------------------------------------
 // One block; thread t adds partials[t], partials[t+1024], ... as a double-double (error-free
 // TwoSum), then the 1024 double-doubles are merged by a fixed binary tree.  The result depends
@@ -168,6 +200,30 @@ reduce_kernel(const double* __restrict__ partials, unsigned long long count, dou
     const double v = hi[0] + lo[0];
     out[slot] = accumulate ? out[slot] + v : v;
   }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+reduce_u64_kernel(const unsigned long long* __restrict__ counts, unsigned long long n,
+                  unsigned long long* out, int accumulate) {
+  __shared__ unsigned long long sh[1024];
+  unsigned long long v = 0;
+  for (unsigned long long i = threadIdx.x; i < n; i += 1024) v += counts[i];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = accumulate ? *out + sh[0] : sh[0];
+}
+
+int launch_reduce_u64(const Lane& lane, const unsigned long long* counts, size_t count, double* out,
+                      int slot, bool accumulate) {
+  reduce_u64_kernel<<<1, 1024, 0, lane.stream>>>(counts, (unsigned long long)count,
+                                                 reinterpret_cast<unsigned long long*>(out + slot),
+                                                 accumulate ? 1 : 0);
+  SPB_CUDA(cudaGetLastError());
+  return SPD_OK;
 }
 
 int launch_reduce(const Lane& lane, const double* partials, size_t count, double* out, int slot,

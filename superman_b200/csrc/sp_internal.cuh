@@ -29,6 +29,8 @@ struct Lane {
   double* d_result = nullptr;   // 8 doubles
   double* d_partials = nullptr; // per-block partial sums
   size_t partials_cap = 0;      // in doubles
+  unsigned long long* d_aux = nullptr;   // per-block integer counters (visited blocks)
+  size_t aux_cap = 0;
   char* d_arena = nullptr;      // plan inputs (matrix, CRS/CCS, ...) live here
   size_t arena_cap = 0, arena_used = 0;
   int sm_count = 0;
@@ -41,6 +43,7 @@ struct Lane {
 int lane_acquire(int device, Lane** lane);
 void lane_release(Lane* lane);
 int lane_reserve_partials(Lane* lane, size_t count);
+int lane_reserve_aux(Lane* lane, size_t count);
 // 256-byte aligned sub-allocation from the lane's device arena (reset by lane_release)
 int lane_arena_alloc(Lane* lane, size_t bytes, void** ptr);
 
@@ -48,6 +51,17 @@ int lane_arena_alloc(Lane* lane, size_t bytes, void** ptr);
 int launch_reduce(const Lane& lane, const double* partials, size_t count, double* out, int slot,
                   bool accumulate);
 
+// out[slot] (as u64) = (accumulate ? out[slot] : 0) + sum of counts
+int launch_reduce_u64(const Lane& lane, const unsigned long long* counts, size_t count, double* out,
+                      int slot, bool accumulate);
+
 int check_device(int device);
+
+// shared-memory-X dense kernel on [lo, hi) (sp_dense.cu); appends its blocks at partials[*pcount]
+int enqueue_smem_range(Lane* L, const double* d_mat_t, const double* d_xbase, int n,
+                       unsigned long long lo, unsigned long long hi, size_t* pcount, int* launches);
+int smem_kernel_prepare(int n);
+int env_int(const char* name, int dflt);
+int ilog2_ull(unsigned long long v);
 
 }  // namespace spb

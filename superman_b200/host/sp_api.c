@@ -197,3 +197,149 @@ double sp_dense_ryser_range(const double *mat, int nov, int device, long long st
   if (stats) stats->wall_ms = sp_now_ms() - t0;
   return r;
 }
+
+/* ================================================================================================
+ * Sparse exact paths
+ * ============================================================================================== */
+
+/* NW start vector of the sparse wrappers (gpu_exact_sparse.cu:861-871): row sums over the
+ * non-zeros of the dense matrix; and D, the CCS scattered back to dense (transposed). */
+static int sparse_preamble(const double *mat, const int *cptrs, const int *rows, const double *cvals,
+                           int nov, double *x, double *dmat_t) {
+  for (int j = 0; j < nov; ++j) {
+    double rs = 0.0;
+    for (int k = 0; k < nov; ++k)
+      if (mat[j * nov + k] != 0) rs += mat[j * nov + k];
+    x[j] = mat[j * nov + (nov - 1)] - rs / 2;
+  }
+  memset(dmat_t, 0, (size_t)nov * nov * sizeof(double));
+  for (int k = 0; k < nov; ++k) {
+    if (cptrs[k] > cptrs[k + 1] || cptrs[k] < 0) { sp_set_error("malformed CCS column pointers"); return SP_EINVAL; }
+    for (int t = cptrs[k]; t < cptrs[k + 1]; ++t) {
+      const int r = rows[t];
+      if (r < 0 || r >= nov) { sp_set_error("CCS row index %d out of range", r); return SP_EINVAL; }
+      dmat_t[(size_t)k * nov + r] += cvals[t];
+    }
+  }
+  return SP_OK;
+}
+
+typedef struct sparse_job {
+  const double *dmat_t;
+  const double *x;
+  int nov;
+  int skip;
+} sparse_job;
+
+static int sparse_open(const void *job, int device, void **plan) {
+  const sparse_job *j = (const sparse_job *)job;
+  return spd_sparse_plan_create(device, j->dmat_t, j->x, j->nov, j->skip, (spd_sparse_plan **)plan);
+}
+static int sparse_launch(void *plan, unsigned long long lo, unsigned long long hi) {
+  return spd_sparse_plan_launch((spd_sparse_plan *)plan, lo, hi);
+}
+static int sparse_wait(void *plan, double *sum, spd_run_info *info) {
+  return spd_sparse_plan_wait((spd_sparse_plan *)plan, sum, info);
+}
+static void sparse_close(void *plan) { spd_sparse_plan_destroy((spd_sparse_plan *)plan); }
+
+static const sp_job_ops g_sparse_ops = {sparse_open, sparse_launch, sparse_wait, sparse_close};
+
+static double sparse_common(const double *mat, const int *cptrs, const int *rows, const double *cvals,
+                            int nov, int skip, int mode, int gpu_num, sp_stats *stats) {
+  const double t0 = sp_now_ms();
+  if (!mat || !cptrs || !rows || !cvals) { sp_set_error("null argument"); return fail(stats, SP_EINVAL); }
+  if (nov < 1 || nov > 64) { sp_set_error("sparse Ryser supports 1 <= n <= 64 (got %d)", nov); return fail(stats, SP_ELIMIT); }
+  if (gpu_num < 1) gpu_num = 1;
+  if (nov == 1) {
+    if (spd_device_count() <= 0) { sp_set_error("no CUDA device: %s", spd_last_error()); return fail(stats, SP_ENODEV); }
+    return mat[0];
+  }
+  double x[64];
+  double *dmat_t = (double *)malloc((size_t)nov * nov * sizeof(double));
+  if (!dmat_t) { sp_set_error("out of memory"); return fail(stats, SP_ENOMEM); }
+  int rc = sparse_preamble(mat, cptrs, rows, cvals, nov, x, dmat_t);
+  if (rc != SP_OK) { free(dmat_t); return fail(stats, rc); }
+  sparse_job job = {dmat_t, x, nov, skip};
+  const unsigned long long end = 1ull << (nov - 1);
+  while (gpu_num > 1 && (end >> 14) < (unsigned long long)gpu_num) gpu_num--;
+  /* SkipPer's work per index is irregular: give the queue 4x more chunks than SpaRyser */
+  unsigned long long chunks = 0;
+  if (mode == SP_SCHED_DYNAMIC) {
+    chunks = sp_dynamic_chunks(nov, 30, gpu_num);
+    if (skip) { int k = 0; while (k < 2 && end / (chunks * 2) >= (1ull << 22)) { chunks *= 2; ++k; } }
+  }
+  double sum = 0.0;
+  rc = sp_sched_run(&g_sparse_ops, &job, mode, gpu_num, 0, 0ull, end, 14, chunks, &sum, stats);
+  free(dmat_t);
+  if (stats) stats->wall_ms = sp_now_ms() - t0;
+  if (rc != SP_OK) return fail(stats, rc);
+  return sp_nw_factor(nov) * sum;
+}
+
+double sp_sparse_ryser(const double *mat, const int *cptrs, const int *rows, const double *cvals,
+                       int nov, int algo_id, int gpu_num, int use_cpu, int threads, sp_stats *stats) {
+  (void)use_cpu; (void)threads;
+  stats_clear(stats);
+  int mode = SP_SCHED_STATIC;
+  switch (algo_id) {
+    case 1: case 2: case 3: case 4: gpu_num = 1; break;   /* main.cu:108-127 */
+    case 5: break;                                         /* main.cu:128-131 */
+    case 6: mode = SP_SCHED_DYNAMIC; break;                /* main.cu:132-136 */
+    default:
+      sp_set_error("Unknown Algorithm ID");
+      return fail(stats, SP_EALGO);
+  }
+  return sparse_common(mat, cptrs, rows, cvals, nov, 0, mode, gpu_num, stats);
+}
+
+double sp_skipper(const double *mat, const int *rptrs, const int *cols, const int *cptrs,
+                  const int *rows, const double *cvals, int nov, int algo_id, int gpu_num, int use_cpu,
+                  int threads, sp_stats *stats) {
+  (void)rptrs; (void)cols; (void)use_cpu; (void)threads;
+  stats_clear(stats);
+  int mode = SP_SCHED_STATIC;
+  switch (algo_id) {
+    case 7: gpu_num = 1; break;                            /* main.cu:137-141 */
+    case 8: mode = SP_SCHED_DYNAMIC; break;                /* main.cu:142-146 */
+    default:
+      sp_set_error("Unknown Algorithm ID");
+      return fail(stats, SP_EALGO);
+  }
+  return sparse_common(mat, cptrs, rows, cvals, nov, 1, mode, gpu_num, stats);
+}
+
+double sp_sparse_ryser_range(const double *mat, const int *cptrs, const int *rows, const double *cvals,
+                             int nov, int skipper, int device, long long start, long long end,
+                             sp_stats *stats) {
+  const double t0 = sp_now_ms();
+  stats_clear(stats);
+  if (!mat || !cptrs || !rows || !cvals) { sp_set_error("null argument"); return fail(stats, SP_EINVAL); }
+  if (nov < 2 || nov > 64) { sp_set_error("sparse range needs 2 <= n <= 64 (got %d)", nov); return fail(stats, SP_ELIMIT); }
+  if (start < 0 || end < start) { sp_set_error("bad range [%lld, %lld)", start, end); return fail(stats, SP_EINVAL); }
+  double x[64];
+  double *dmat_t = (double *)malloc((size_t)nov * nov * sizeof(double));
+  if (!dmat_t) { sp_set_error("out of memory"); return fail(stats, SP_ENOMEM); }
+  int rc = sparse_preamble(mat, cptrs, rows, cvals, nov, x, dmat_t);
+  if (rc != SP_OK) { free(dmat_t); return fail(stats, rc); }
+  spd_sparse_plan *plan = NULL;
+  rc = spd_sparse_plan_create(device, dmat_t, x, nov, skipper, &plan);
+  free(dmat_t);
+  if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
+  double sum = 0.0;
+  spd_run_info info;
+  rc = spd_sparse_plan_run(plan, (unsigned long long)start, (unsigned long long)end, &sum, &info);
+  spd_sparse_plan_destroy(plan);
+  if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
+  if (stats) {
+    stats->kernel_ms = info.kernel_ms;
+    stats->device_ms[0] = info.kernel_ms;
+    stats->device_partial[0] = sum;
+    stats->device_units[0] = info.units;
+    stats->units = info.units; stats->visited = info.visited;
+    stats->devices = 1; stats->chunks = 1; stats->launches = info.launches;
+    stats->path = info.path; stats->tile_log2 = info.tile_log2;
+    stats->wall_ms = sp_now_ms() - t0;
+  }
+  return sum;
+}
