@@ -15,18 +15,22 @@ LIB     := $(PKG)/libsuperman_b200.so
 CLI     := $(PKG)/perman
 
 GROUPS  := 0 1 2 3 4 5 6 7
-CU_SRCS := sp_device sp_dense sp_sparse
+CU_SRCS := sp_device sp_dense sp_sparse sp_approx
 CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o) $(GROUPS:%=$(BUILD)/sp_sparse_inst_g%.o)
 C_SRCS  := sp_sched sp_api sp_matrix
 C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
 
-all: $(LIB)
+all: $(LIB) $(CLI)
 
 $(BUILD):
 	mkdir -p $(BUILD)
 
 $(BUILD)/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+# the estimators are compared bit for bit with the C oracle: no FMA contraction in this unit
+$(BUILD)/sp_approx.o: $(PKG)/csrc/sp_approx.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 
 $(BUILD)/sp_dense_inst_g%.o: $(PKG)/csrc/sp_dense_inst.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DSPB_GROUP=$* -c $< -o $@
@@ -39,6 +43,9 @@ $(BUILD)/%.o: $(PKG)/host/%.c $(wildcard $(PKG)/host/*.h include/*.h) | $(BUILD)
 
 $(LIB): $(CU_OBJS) $(C_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread -lm
+
+$(CLI): $(PKG)/host/perman_main.c $(LIB) include/superman_b200.h
+	$(CC) -O2 -std=c11 -Wall -Wextra -Iinclude -o $@ $< -L$(PKG) -lsuperman_b200 -lm -Wl,-rpath,'$$ORIGIN'
 
 oracle:
 	$(MAKE) -C oracle

@@ -147,6 +147,44 @@ double sp_sparse_ryser_range(const double *mat, const int *cptrs, const int *row
                              int nov, int skipper, int device, long long start, long long end,
                              sp_stats *stats);
 
+/* ---------------------------------------------------------------------------------------------
+ * Approximations (-a): Rasmussen (-p1 / -p3) and the Sinkhorn-scaled estimator (-p2 / -p4),
+ * main.cu:77-104 (dense), 157-184 (sparse), 250-323 (grid graphs).
+ * trials is -x (number_of_times), scale_intervals -y, scale_times -z.  Exactly `trials` trials
+ * are run and averaged (the reference rounds up to whole 1024-thread blocks, ids 1/2, or gives
+ * the whole budget to the first GPU, ids 3/4 -- SURVEY.md Appendix C); with gpu_num > 1 the trial
+ * indices are split evenly over the devices.  seed == 0 selects the library's fixed default
+ * seed (or the environment variable SP_SEED): runs are reproducible, and a trial's value depends
+ * only on (seed, trial index), not on the device count.
+ * stats->std_error is the standard error of the returned mean, stats->units the trial count.
+ * ------------------------------------------------------------------------------------------- */
+
+/* gpu_perman64_rasmussen_sparse (gpu_approximation_sparse.cu:455; gpu_num = 1) and
+ * gpu_perman64_rasmussen_multigpucpu_chunks_sparse (:497; gpu_num devices) */
+double sp_rasmussen_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
+                           int nov, int nnz, long long trials, int gpu_num,
+                           unsigned long long seed, sp_stats *stats);
+/* gpu_perman64_approximation_sparse (gpu_approximation_sparse.cu:608) and
+ * gpu_perman64_approximation_multigpucpu_chunks_sparse (:663) */
+double sp_scaling_sparse(const int *cptrs, const int *rows, const int *rptrs, const int *cols,
+                         int nov, int nnz, long long trials, int scale_intervals, int scale_times,
+                         int gpu_num, unsigned long long seed, sp_stats *stats);
+/* gpu_perman64_rasmussen (gpu_approximation_dense.cu:373) and
+ * gpu_perman64_rasmussen_multigpucpu_chunks (:411): pattern = entries != 0, nov <= 64 as in the
+ * reference's `long` bit masks is NOT required here (any nov whose pattern fits shared memory) */
+double sp_rasmussen_dense(const double *mat, int nov, long long trials, int gpu_num,
+                          unsigned long long seed, sp_stats *stats);
+/* gpu_perman64_approximation (gpu_approximation_dense.cu:527) and
+ * gpu_perman64_approximation_multigpucpu_chunks (:573): Sinkhorn sums weighted by the entries */
+double sp_scaling_dense(const double *mat, int nov, long long trials, int scale_intervals,
+                        int scale_times, int gpu_num, unsigned long long seed, sp_stats *stats);
+/* One trial's estimate (for parity tests against the oracle): trial index `trial` of the stream
+ * `seed`; scaling == 0 Rasmussen, else scaled with (y, z). */
+double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
+                              int nov, int nnz, int scaling, int scale_intervals, int scale_times,
+                              unsigned long long seed, long long trial, int count, double *values,
+                              sp_stats *stats);
+
 /* (4*(nov&1)-2): the factor every wrapper applies to base + sum (gpu_exact_dense.cu:698). */
 double sp_nw_factor(int nov);
 

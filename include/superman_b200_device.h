@@ -38,6 +38,7 @@ typedef struct spd_run_info {
   int path;                 /* SPD_PATH_* of the dominant kernel */
   int tile_log2;            /* log2 of the per-thread tile (exact register paths), else 0 */
   int reserved;
+  double aux0, aux1;        /* approximations: sum of (estimate*aux1)^2, and the scale aux1 */
 } spd_run_info;
 
 #define SPD_PATH_DENSE_REG      1   /* X in registers, templated on n            */
@@ -92,6 +93,26 @@ int  spd_sparse_plan_run(spd_sparse_plan *plan, unsigned long long lo, unsigned 
                          double *sum, spd_run_info *info);
 int  spd_sparse_plan_launch(spd_sparse_plan *plan, unsigned long long lo, unsigned long long hi);
 int  spd_sparse_plan_wait(spd_sparse_plan *plan, double *sum, spd_run_info *info);
+
+/* ---- Rasmussen / scaling estimators ---------------------------------------------------------- */
+typedef struct spd_approx_plan spd_approx_plan;
+
+/* CRS (rptrs, cols) and CCS (cptrs, rows) of the 0/1 pattern, as gridGraph2compressed /
+ * matrix2compressed produce them.  rvals / cvals (may be NULL) are entry weights used by the
+ * dense scaling twin (gpu_approximation_dense.cu:286-313).  scaling == 0: Rasmussen
+ * (gpu_approximation_sparse.cu:198-290); else the scaled estimator (:292-452) with
+ * scale_intervals (-y) and scale_times (-z).  A run covers the trial indices [lo, hi); *sum is the
+ * sum of the per-trial estimates; a trial's value depends only on (seed, trial index). */
+int  spd_approx_plan_create(int device, const int *rptrs, const int *cols, const int *cptrs,
+                            const int *rows, const double *rvals, const double *cvals, int nov, int nnz,
+                            int scaling, int scale_intervals, int scale_times, unsigned long long seed,
+                            spd_approx_plan **plan);
+void spd_approx_plan_destroy(spd_approx_plan *plan);
+int  spd_approx_plan_run(spd_approx_plan *plan, unsigned long long lo, unsigned long long hi,
+                         double *sum, spd_run_info *info);
+int  spd_approx_plan_launch(spd_approx_plan *plan, unsigned long long lo, unsigned long long hi);
+int  spd_approx_plan_wait(spd_approx_plan *plan, double *sum, spd_run_info *info);
+int  spd_approx_plan_trial(spd_approx_plan *plan, unsigned long long trial, double *value);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,12 @@ _sig("sp_sparse_ryser", C.c_double, [_dp, _ip, _ip, _dp, C.c_int, C.c_int, C.c_i
 _sig("sp_skipper", C.c_double, [_dp, _ip, _ip, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _sp])
 _sig("sp_sparse_ryser_range", C.c_double, [_dp, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, _sp])
 
+_sig("sp_rasmussen_sparse", C.c_double, [_ip, _ip, _ip, _ip, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_ulonglong, _sp])
+_sig("sp_scaling_sparse", C.c_double, [_ip, _ip, _ip, _ip, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, _sp])
+_sig("sp_rasmussen_dense", C.c_double, [_dp, C.c_int, C.c_longlong, C.c_int, C.c_ulonglong, _sp])
+_sig("sp_scaling_dense", C.c_double, [_dp, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, _sp])
+_sig("sp_approx_trial_sparse", C.c_double, [_ip, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, _dp, _sp])
+
 _mp = C.POINTER(SpMatrix)
 _sig("sp_matrix_read", C.c_int, [C.c_char_p, C.c_int, _mp])
 _sig("sp_matrix_from_dense", C.c_int, [_dp, C.c_int, _mp])

@@ -15,6 +15,11 @@ __all__ = [
     "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
     "dense_ryser", "dense_ryser_range", "DenseHandle",
     "sparse_ryser", "skipper", "sparse_ryser_range",
+    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse",
+    "gpu_perman64_rasmussen_sparse", "gpu_perman64_rasmussen_multigpucpu_chunks_sparse",
+    "gpu_perman64_approximation_sparse", "gpu_perman64_approximation_multigpucpu_chunks_sparse",
+    "gpu_perman64_rasmussen", "gpu_perman64_rasmussen_multigpucpu_chunks",
+    "gpu_perman64_approximation", "gpu_perman64_approximation_multigpucpu_chunks",
     "gpu_perman64_xlocal_sparse", "gpu_perman64_xshared_sparse", "gpu_perman64_xshared_coalescing_sparse",
     "gpu_perman64_xshared_coalescing_mshared_sparse", "gpu_perman64_xshared_coalescing_mshared_multigpu_sparse",
     "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_sparse",
@@ -236,6 +241,87 @@ def sparse_ryser_range(mat, cptrs, rows, cvals, start, end, nov=None, skipper=Fa
     st = stats if stats is not None else SpStats()
     v = lib.sp_sparse_ryser_range(_ptr(a), _iptr(cp), _iptr(ro), _ptr(cv), nov, int(skipper), device, start, end, C.byref(st))
     return _check(v, st)
+
+
+def rasmussen_sparse(rptrs, cols, cptrs, rows, nov, nnz, trials, gpu_num=1, seed=0, stats: SpStats | None = None) -> float:
+    rp, co, cp, ro = _iarr(rptrs), _iarr(cols), _iarr(cptrs), _iarr(rows)
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_rasmussen_sparse(_iptr(rp), _iptr(co), _iptr(cp), _iptr(ro), nov, nnz, trials, gpu_num, seed, C.byref(st))
+    return _check(v, st)
+
+
+def scaling_sparse(cptrs, rows, rptrs, cols, nov, nnz, trials, scale_intervals=4, scale_times=5, gpu_num=1, seed=0,
+                   stats: SpStats | None = None) -> float:
+    rp, co, cp, ro = _iarr(rptrs), _iarr(cols), _iarr(cptrs), _iarr(rows)
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_scaling_sparse(_iptr(cp), _iptr(ro), _iptr(rp), _iptr(co), nov, nnz, trials, scale_intervals, scale_times,
+                              gpu_num, seed, C.byref(st))
+    return _check(v, st)
+
+
+def rasmussen_dense(mat, nov, trials, gpu_num=1, seed=0, stats: SpStats | None = None) -> float:
+    a = _dmat(mat, nov)
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_rasmussen_dense(_ptr(a), nov, trials, gpu_num, seed, C.byref(st))
+    return _check(v, st)
+
+
+def scaling_dense(mat, nov, trials, scale_intervals=4, scale_times=5, gpu_num=1, seed=0, stats: SpStats | None = None) -> float:
+    a = _dmat(mat, nov)
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_scaling_dense(_ptr(a), nov, trials, scale_intervals, scale_times, gpu_num, seed, C.byref(st))
+    return _check(v, st)
+
+
+def approx_trials_sparse(rptrs, cols, cptrs, rows, nov, nnz, scaling=False, scale_intervals=4, scale_times=5, seed=1,
+                         first=0, count=1):
+    """Per-trial estimates of trials [first, first+count) (parity tests against the oracle)."""
+    rp, co, cp, ro = _iarr(rptrs), _iarr(cols), _iarr(cptrs), _iarr(rows)
+    out = np.zeros(count, dtype=np.float64)
+    st = SpStats()
+    v = lib.sp_approx_trial_sparse(_iptr(rp), _iptr(co), _iptr(cp), _iptr(ro), nov, nnz, int(scaling), scale_intervals,
+                                   scale_times, seed, first, count, _ptr(out), C.byref(st))
+    _check(v, st)
+    return out
+
+
+# ---- reference wrapper names (gpu_approximation_sparse.cu:455,497,608,663; _dense.cu:373,411,527,573)
+# grid_graph is the reference's unused trailing flag.
+def gpu_perman64_rasmussen_sparse(rptrs, cols, nov, nnz, number_of_times, grid_graph=False, *, cptrs, rows, seed=0):
+    return rasmussen_sparse(rptrs, cols, cptrs, rows, nov, nnz, number_of_times, 1, seed)
+
+
+def gpu_perman64_rasmussen_multigpucpu_chunks_sparse(cptrs, rows, rptrs, cols, nov, nnz, number_of_times, gpu_num,
+                                                     cpu=False, threads=16, grid_graph=False, seed=0):
+    return rasmussen_sparse(rptrs, cols, cptrs, rows, nov, nnz, number_of_times, gpu_num, seed)
+
+
+def gpu_perman64_approximation_sparse(cptrs, rows, rptrs, cols, nov, nnz, number_of_times, scale_intervals, scale_times,
+                                      grid_graph=False, seed=0):
+    return scaling_sparse(cptrs, rows, rptrs, cols, nov, nnz, number_of_times, scale_intervals, scale_times, 1, seed)
+
+
+def gpu_perman64_approximation_multigpucpu_chunks_sparse(cptrs, rows, rptrs, cols, nov, nnz, number_of_times, gpu_num,
+                                                         cpu, scale_intervals, scale_times, threads=16,
+                                                         grid_graph=False, seed=0):
+    return scaling_sparse(cptrs, rows, rptrs, cols, nov, nnz, number_of_times, scale_intervals, scale_times, gpu_num, seed)
+
+
+def gpu_perman64_rasmussen(mat, nov, number_of_times, seed=0):
+    return rasmussen_dense(mat, nov, number_of_times, 1, seed)
+
+
+def gpu_perman64_rasmussen_multigpucpu_chunks(mat, nov, number_of_times, gpu_num, cpu=False, threads=16, seed=0):
+    return rasmussen_dense(mat, nov, number_of_times, gpu_num, seed)
+
+
+def gpu_perman64_approximation(mat, nov, number_of_times, scale_intervals, scale_times, seed=0):
+    return scaling_dense(mat, nov, number_of_times, scale_intervals, scale_times, 1, seed)
+
+
+def gpu_perman64_approximation_multigpucpu_chunks(mat, nov, number_of_times, gpu_num, cpu, scale_intervals, scale_times,
+                                                  threads=16, seed=0):
+    return scaling_dense(mat, nov, number_of_times, scale_intervals, scale_times, gpu_num, seed)
 
 
 # ---- reference wrapper names (gpu_exact_sparse.cu:672,732,792,853,916,995,1123,1192) ------------

@@ -1,0 +1,408 @@
+// Rasmussen and Sinkhorn-scaled permanent estimators on one device, warp-per-trial.
+//
+// Reference paths replaced: kernel_rasmussen_sparse / kernel_approximation_sparse
+// (gpu_approximation_sparse.cu:198-290, 292-452) and their dense twins kernel_rasmussen /
+// kernel_approximation (gpu_approximation_dense.cu:155-229, 231-369), which run one trial per
+// THREAD with the bit masks in local memory, rescan every CRS row at every step and keep the
+// scaling vectors d_r / d_c in global memory at stride nov (2 x 2.7 GB per GPU at nov = 648,
+// gpu_approximation_sparse.cu:742-743).
+//
+// Here one WARP runs one trial; all of a trial's state lives in shared memory:
+//   deg[r]      remaining column count of row r (bytes; maintained incrementally when a column
+//               is removed, instead of recounted from CRS at every step),
+//   rowx/colx   "extracted" bit masks,
+//   d_r, d_c    Sinkhorn scaling vectors (scaling estimator only).
+// The lanes split the rows (minimum-degree search, redux.min on (deg << 16 | row) = first minimum
+// in ascending row order, as the reference's scan), the entries of the chosen row (ballot + rank
+// select of the r-th remaining column) and the columns / rows of a Sinkhorn sweep.  Every branch
+// is warp-uniform.
+// Random numbers: counter-based Philox4x32-10, counter = (trial index, draw/4), key = seed, so a
+// trial's outcome depends only on (seed, trial index) -- reproducible and independent of how the
+// trials are split over devices (the reference seeds XORWOW with time(0)*tid,
+// gpu_approximation_sparse.cu:226,473).
+//
+// Compiled with -fmad=false: the oracle restates the same float / double operations in C and the
+// per-trial values are compared bit for bit.
+#include "sp_internal.cuh"
+#include <string.h>
+#include <new>
+
+namespace spb {
+
+#define APX_WARPS 8
+#define APX_THREADS (APX_WARPS * 32)
+
+struct Philox {
+  uint32_t k0, k1;
+};
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct ApproxArgs {
+  const int* rptrs; const int* cols;   // CRS pattern
+  const int* cptrs; const int* rows;   // CCS pattern
+  const double* rvals; const double* cvals;  // entry weights (dense twins) or nullptr
+  double* partial_sum;                 // per block: sum of estimates
+  double* partial_sq;                  // per block: sum of (estimate * sq_scale)^2
+  unsigned long long trial_lo, trial_hi;
+  unsigned long long seed;
+  double sq_scale;
+  int nov, nnz;
+  int scaling;                         // 0 Rasmussen, 1 scaled
+  int scale_intervals, scale_times;
+};
+
+__device__ __forceinline__ bool bit_test(const unsigned* m, int i) { return (m[i >> 5] >> (i & 31)) & 1u; }
+
+// WEIGHTED: Sinkhorn sums use the entry values in double (dense twin, gpu_approximation_dense.cu:
+// 286-313); otherwise pattern only with float sums (gpu_approximation_sparse.cu:361-396).
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(APX_THREADS)
+approx_kernel(const ApproxArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int nov = a.nov, nnz = a.nnz;
+  const int words = (nov + 31) >> 5;
+  // block-shared pattern
+  int* s_rptrs = reinterpret_cast<int*>(smraw);
+  int* s_cptrs = s_rptrs + (nov + 1);
+  int* s_cols = s_cptrs + (nov + 1);
+  int* s_rows = s_cols + nnz;
+  size_t off = (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
+  off = (off + 15) & ~(size_t)15;
+  // per-warp state
+  const int deg_bytes = (nov + 15) & ~15;
+  const size_t warp_bytes = (size_t)deg_bytes + 2 * (size_t)words * 4 + (a.scaling ? 2 * (size_t)nov * 4 : 0);
+  const size_t warp_stride = (warp_bytes + 15) & ~(size_t)15;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* wbase = smraw + off + wib * warp_stride;
+  unsigned char* deg = wbase;
+  unsigned* rowx = reinterpret_cast<unsigned*>(wbase + deg_bytes);
+  unsigned* colx = rowx + words;
+  float* d_r = reinterpret_cast<float*>(colx + words);
+  float* d_c = d_r + nov;
+  __shared__ double blk_sum[APX_WARPS], blk_sq[APX_WARPS];
+
+  for (int e = threadIdx.x; e <= nov; e += APX_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
+  for (int e = threadIdx.x; e < nnz; e += APX_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
+  __syncthreads();
+
+  const unsigned long long total_warps = (unsigned long long)gridDim.x * APX_WARPS;
+  const unsigned long long wg = (unsigned long long)blockIdx.x * APX_WARPS + wib;
+  double wsum = 0.0, wsq = 0.0;
+  const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+
+  for (unsigned long long trial = a.trial_lo + wg; trial < a.trial_hi; trial += total_warps) {
+    // ---- reset state ----
+    for (int r = lane; r < nov; r += 32) deg[r] = (unsigned char)min(255, s_rptrs[r + 1] - s_rptrs[r]);
+    for (int w = lane; w < words; w += 32) { rowx[w] = 0u; colx[w] = 0u; }
+    if (a.scaling) for (int i = lane; i < nov; i += 32) { d_r[i] = 1.0f; d_c[i] = 1.0f; }
+    __syncwarp();
+    double perm = 1.0;
+    uint32_t rnd[4];
+    bool dead = false;
+    for (int step = 0; step < nov && !dead; ++step) {
+      if ((step & 3) == 0)
+        philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)(step >> 2), 0u, k0, k1, rnd);
+      const uint32_t draw = rnd[step & 3];
+      // ---- minimum-degree remaining row, first in ascending order ----
+      unsigned best = 0xffffffffu;
+      for (int r = lane; r < nov; r += 32)
+        if (!bit_test(rowx, r)) best = min(best, ((unsigned)deg[r] << 16) | (unsigned)r);
+      best = __reduce_min_sync(0xffffffffu, best);
+      const int row = (int)(best & 0xffffu);
+      const int dmin = (int)(best >> 16);
+      if (dmin == 0) { perm = 0.0; dead = true; break; }
+      const int rb = s_rptrs[row], re = s_rptrs[row + 1];
+      int col = -1;
+      if (!a.scaling) {
+        // ---- Rasmussen: perm *= deg; uniform pick of the r-th remaining column ----
+        perm *= (double)dmin;
+        int want = (int)(((uint64_t)draw * (uint64_t)dmin) >> 32);
+        for (int base = rb; base < re && col < 0; base += 32) {
+          const int e = base + lane;
+          const int cc = (e < re) ? s_cols[e] : 0;
+          const bool rem = (e < re) && !bit_test(colx, cc);
+          const unsigned m = __ballot_sync(0xffffffffu, rem);
+          const int cnt = __popc(m);
+          if (want < cnt) {
+            const int src = __fns(m, 0, want + 1);
+            col = __shfl_sync(0xffffffffu, cc, src);
+          } else {
+            want -= cnt;
+          }
+        }
+      } else {
+        // ---- scaled estimator: Sinkhorn sweeps every scale_intervals steps ----
+        if (step % a.scale_intervals == 0) {
+          for (int sweep = 0; sweep < a.scale_times && !dead; ++sweep) {
+            bool zero = false;
+            for (int j = lane; j < nov; j += 32) {
+              if (bit_test(colx, j)) continue;
+              if (WEIGHTED) {
+                double cs = 0.0;
+                for (int t = s_cptrs[j]; t < s_cptrs[j + 1]; ++t) {
+                  const int r = s_rows[t];
+                  if (!bit_test(rowx, r)) cs += (double)d_r[r] * a.cvals[t];
+                }
+                if (cs == 0.0) zero = true; else d_c[j] = (float)(1.0 / cs);
+              } else {
+                float cs = 0.0f;
+                for (int t = s_cptrs[j]; t < s_cptrs[j + 1]; ++t) {
+                  const int r = s_rows[t];
+                  if (!bit_test(rowx, r)) cs += d_r[r];
+                }
+                if (cs == 0.0f) zero = true; else d_c[j] = 1.0f / cs;
+              }
+            }
+            if (__any_sync(0xffffffffu, zero)) { dead = true; break; }
+            __syncwarp();
+            for (int i = lane; i < nov; i += 32) {
+              if (bit_test(rowx, i)) continue;
+              if (WEIGHTED) {
+                double rs = 0.0;
+                for (int t = s_rptrs[i]; t < s_rptrs[i + 1]; ++t) {
+                  const int cc = s_cols[t];
+                  if (!bit_test(colx, cc)) rs += a.rvals[t] * (double)d_c[cc];
+                }
+                if (rs == 0.0) zero = true; else d_r[i] = (float)(1.0 / rs);
+              } else {
+                float rs = 0.0f;
+                for (int t = s_rptrs[i]; t < s_rptrs[i + 1]; ++t) {
+                  const int cc = s_cols[t];
+                  if (!bit_test(colx, cc)) rs += d_c[cc];
+                }
+                if (rs == 0.0f) zero = true; else d_r[i] = 1.0f / rs;
+              }
+            }
+            if (__any_sync(0xffffffffu, zero)) { dead = true; break; }
+            __syncwarp();
+          }
+          if (dead) { perm = 0.0; break; }
+        }
+        // ---- column with probability d_r[row]*d_c[c] / sum (all lanes compute the same) ----
+        const float dr = d_r[row];
+        double tot = 0.0;
+        for (int t = rb; t < re; ++t) {
+          const int cc = s_cols[t];
+          if (!bit_test(colx, cc)) tot += (double)(dr * d_c[cc]);
+        }
+        if (tot == 0.0) { perm = 0.0; dead = true; break; }
+        const double target = ((double)draw + 1.0) * (1.0 / 4294967296.0) * tot;
+        double run = 0.0;
+        for (int t = rb; t < re; ++t) {
+          const int cc = s_cols[t];
+          if (bit_test(colx, cc)) continue;
+          const double s = (double)(dr * d_c[cc]);
+          run += s;
+          if (target <= run) { col = cc; perm /= (s / tot); break; }
+        }
+        if (col < 0) { perm = 0.0; dead = true; break; }   // cannot happen: run reaches tot exactly
+      }
+      // ---- extract row and column; lower the degree of the other rows of that column ----
+      __syncwarp();
+      if (lane == 0) {
+        rowx[row >> 5] |= 1u << (row & 31);
+        colx[col >> 5] |= 1u << (col & 31);
+      }
+      __syncwarp();
+      for (int t = s_cptrs[col] + lane; t < s_cptrs[col + 1]; t += 32) {
+        const int r = s_rows[t];
+        if (!bit_test(rowx, r)) deg[r] -= 1;
+      }
+      __syncwarp();
+    }
+    wsum += perm;
+    const double q = perm * a.sq_scale;
+    wsq += q * q;
+    __syncwarp();
+  }
+  if (lane == 0) { blk_sum[wib] = wsum; blk_sq[wib] = wsq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, q = 0.0;
+    for (int w = 0; w < APX_WARPS; ++w) { s += blk_sum[w]; q += blk_sq[w]; }
+    a.partial_sum[blockIdx.x] = s;
+    a.partial_sq[blockIdx.x] = q;
+  }
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+struct spd_approx_plan {
+  Lane* lanep = nullptr;
+  int nov = 0, nnz = 0;
+  int scaling = 0, y = 4, z = 5;
+  bool weighted = false;
+  unsigned long long seed = 0;
+  double sq_scale = 1.0;
+  int *d_rptrs = nullptr, *d_cols = nullptr, *d_cptrs = nullptr, *d_rows = nullptr;
+  double *d_rvals = nullptr, *d_cvals = nullptr;
+  size_t smem_bytes = 0;
+  int blocks = 0;
+  bool pending = false;
+  spd_run_info info;
+};
+
+extern "C" {
+
+int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const int* cptrs,
+                           const int* rows, const double* rvals, const double* cvals, int nov, int nnz,
+                           int scaling, int scale_intervals, int scale_times, unsigned long long seed,
+                           spd_approx_plan** out) {
+  if (!rptrs || !cols || !cptrs || !rows || !out) { set_error("null argument"); return SPD_EINVAL; }
+  if (nov < 1 || nov > 65535) { set_error("approximation supports 1 <= n <= 65535 (got %d)", nov); return SPD_ELIMIT; }
+  if (nnz < 0) { set_error("negative nnz"); return SPD_EINVAL; }
+  if (scaling && (scale_intervals < 1 || scale_times < 0)) { set_error("bad scaling parameters"); return SPD_EINVAL; }
+  for (int r = 0; r < nov; ++r) {
+    if (rptrs[r + 1] - rptrs[r] > 255 || rptrs[r + 1] < rptrs[r]) {
+      set_error("row %d has %d entries; the estimators keep row degrees in bytes (<= 255)", r, rptrs[r + 1] - rptrs[r]);
+      return SPD_ELIMIT;
+    }
+  }
+  spd_approx_plan* p = new (std::nothrow) spd_approx_plan();
+  if (!p) return SPD_ENOMEM;
+  int rc = lane_acquire(device, &p->lanep);
+  if (rc != SPD_OK) { delete p; return rc; }
+  Lane& L = *p->lanep;
+  auto fail = [&](int code) { lane_release(p->lanep); delete p; return code; };
+  p->nov = nov; p->nnz = nnz; p->scaling = scaling ? 1 : 0;
+  p->y = scale_intervals; p->z = scale_times; p->seed = seed;
+  p->weighted = (rvals != nullptr && cvals != nullptr && scaling);
+  // estimates of a large pattern are ~1e159 (36x36 grid): square them in a scaled domain
+  p->sq_scale = (nov > 64) ? ldexp(1.0, -4 * nov / 5) : 1.0;
+  const int words = (nov + 31) / 32;
+  size_t off = (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
+  off = (off + 15) & ~(size_t)15;
+  const size_t deg_bytes = ((size_t)nov + 15) & ~(size_t)15;
+  size_t warp_bytes = deg_bytes + 2 * (size_t)words * 4 + (scaling ? 2 * (size_t)nov * 4 : 0);
+  warp_bytes = (warp_bytes + 15) & ~(size_t)15;
+  p->smem_bytes = off + APX_WARPS * warp_bytes;
+  if (p->smem_bytes > 227 * 1024) {
+    set_error("pattern too large for shared memory (%zu B needed)", p->smem_bytes);
+    return fail(SPD_ELIMIT);
+  }
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { set_error("%s", cudaGetErrorString(e)); return fail(SPD_ECUDA); }
+  const size_t ib = (size_t)(nov + 1) * sizeof(int), nb = (size_t)(nnz > 0 ? nnz : 1) * sizeof(int);
+  if ((rc = lane_arena_alloc(&L, ib, (void**)&p->d_rptrs)) != SPD_OK) return fail(rc);
+  if ((rc = lane_arena_alloc(&L, ib, (void**)&p->d_cptrs)) != SPD_OK) return fail(rc);
+  if ((rc = lane_arena_alloc(&L, nb, (void**)&p->d_cols)) != SPD_OK) return fail(rc);
+  if ((rc = lane_arena_alloc(&L, nb, (void**)&p->d_rows)) != SPD_OK) return fail(rc);
+  if (p->weighted) {
+    if ((rc = lane_arena_alloc(&L, (size_t)(nnz > 0 ? nnz : 1) * 8, (void**)&p->d_rvals)) != SPD_OK) return fail(rc);
+    if ((rc = lane_arena_alloc(&L, (size_t)(nnz > 0 ? nnz : 1) * 8, (void**)&p->d_cvals)) != SPD_OK) return fail(rc);
+  }
+  if ((e = cudaMemcpyAsync(p->d_rptrs, rptrs, ib, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(p->d_cptrs, cptrs, ib, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+      (nnz > 0 && (e = cudaMemcpyAsync(p->d_cols, cols, (size_t)nnz * 4, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess) ||
+      (nnz > 0 && (e = cudaMemcpyAsync(p->d_rows, rows, (size_t)nnz * 4, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess) ||
+      (p->weighted && nnz > 0 && (e = cudaMemcpyAsync(p->d_rvals, rvals, (size_t)nnz * 8, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess) ||
+      (p->weighted && nnz > 0 && (e = cudaMemcpyAsync(p->d_cvals, cvals, (size_t)nnz * 8, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess) ||
+      (e = cudaStreamSynchronize(L.stream)) != cudaSuccess) {
+    set_error("approx plan upload: %s", cudaGetErrorString(e));
+    return fail(SPD_ECUDA);
+  }
+  if (p->smem_bytes > 48 * 1024) {
+    e = p->weighted ? cudaFuncSetAttribute(approx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes)
+                    : cudaFuncSetAttribute(approx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->smem_bytes, cudaGetErrorString(e)); return fail(SPD_ECUDA); }
+  }
+  int per_sm = 0;
+  e = p->weighted ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<true>, APX_THREADS, p->smem_bytes)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<false>, APX_THREADS, p->smem_bytes);
+  if (e != cudaSuccess || per_sm < 1) { set_error("approx kernel does not fit on an SM: %s", cudaGetErrorString(e)); return fail(SPD_ECUDA); }
+  p->blocks = per_sm * L.sm_count;     // persistent grid: resident blocks x SM count
+  if ((rc = lane_reserve_partials(&L, (size_t)2 * p->blocks + 16)) != SPD_OK) return fail(rc);
+  *out = p;
+  return SPD_OK;
+}
+
+void spd_approx_plan_destroy(spd_approx_plan* p) {
+  if (!p) return;
+  lane_release(p->lanep);
+  delete p;
+}
+
+int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned long long hi) {
+  if (!p) { set_error("null plan"); return SPD_EINVAL; }
+  if (p->pending) { set_error("plan already has a pending run"); return SPD_EINVAL; }
+  if (hi < lo) { set_error("bad trial range"); return SPD_EINVAL; }
+  Lane& L = *p->lanep;
+  SPB_CUDA(cudaSetDevice(L.device));
+  memset(&p->info, 0, sizeof(p->info));
+  p->info.units = hi - lo;
+  p->info.visited = hi - lo;
+  p->info.path = p->scaling ? SPD_PATH_SCALING : SPD_PATH_RASMUSSEN;
+  unsigned long long warps_needed = (hi - lo);
+  int blocks = p->blocks;
+  const unsigned long long need_blocks = (warps_needed + APX_WARPS - 1) / APX_WARPS;
+  if (need_blocks < (unsigned long long)blocks) blocks = (int)(need_blocks ? need_blocks : 1);
+  ApproxArgs a;
+  a.rptrs = p->d_rptrs; a.cols = p->d_cols; a.cptrs = p->d_cptrs; a.rows = p->d_rows;
+  a.rvals = p->d_rvals; a.cvals = p->d_cvals;
+  a.partial_sum = L.d_partials; a.partial_sq = L.d_partials + blocks;
+  a.trial_lo = lo; a.trial_hi = hi; a.seed = p->seed; a.sq_scale = p->sq_scale;
+  a.nov = p->nov; a.nnz = p->nnz; a.scaling = p->scaling;
+  a.scale_intervals = p->y; a.scale_times = p->z;
+  SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
+  if (p->weighted) approx_kernel<true><<<blocks, APX_THREADS, p->smem_bytes, L.stream>>>(a);
+  else approx_kernel<false><<<blocks, APX_THREADS, p->smem_bytes, L.stream>>>(a);
+  SPB_CUDA(cudaGetLastError());
+  int rc;
+  if ((rc = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc;
+  if ((rc = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc;
+  SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+  SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
+  p->info.launches = 3;
+  p->pending = true;
+  return SPD_OK;
+}
+
+int spd_approx_plan_wait(spd_approx_plan* p, double* sum, spd_run_info* info) {
+  if (!p || !p->pending) { set_error("no pending run"); return SPD_EINVAL; }
+  p->pending = false;
+  SPB_CUDA(cudaSetDevice(p->lanep->device));
+  SPB_CUDA(cudaEventSynchronize(p->lanep->ev1));
+  float ms = 0.f;
+  SPB_CUDA(cudaEventElapsedTime(&ms, p->lanep->ev0, p->lanep->ev1));
+  p->info.kernel_ms = ms;
+  p->info.aux0 = p->lanep->h_result[1];   // sum of (estimate * sq_scale)^2
+  p->info.aux1 = p->sq_scale;
+  if (sum) *sum = p->lanep->h_result[0];
+  if (info) *info = p->info;
+  return SPD_OK;
+}
+
+int spd_approx_plan_run(spd_approx_plan* p, unsigned long long lo, unsigned long long hi, double* sum,
+                        spd_run_info* info) {
+  int rc = spd_approx_plan_launch(p, lo, hi);
+  if (rc != SPD_OK) return rc;
+  return spd_approx_plan_wait(p, sum, info);
+}
+
+// One trial on the device, for bit-exact comparison with the oracle (tests only use tiny counts).
+int spd_approx_plan_trial(spd_approx_plan* p, unsigned long long trial, double* value) {
+  double s = 0.0;
+  spd_run_info info;
+  int rc = spd_approx_plan_run(p, trial, trial + 1, &s, &info);
+  if (rc == SPD_OK && value) *value = s;
+  return rc;
+}
+
+}  // extern "C"

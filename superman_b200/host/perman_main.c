@@ -1,0 +1,291 @@
+/* perman -- command-line front end, drop-in for the reference's `perman` (main.cu:325-600).
+ *
+ * Same flags, defaults, algorithm-id tables and stdout lines:
+ *   -f/--file  -b/--binary  -s/--sparse  -r/--preprocessing  -t/--threads  -g/--gpu  -d/--device
+ *   -c/--cpu  -a/--approximation  -p/--perman  -x/--numOfTimes  -y/--scaleIntervals
+ *   -z/--scaleTimes  -i/--grid  -m/--gridm  -n/--gridn
+ * GPU is the default when neither -g nor -c is given (main.cu:482-484).  CPU-only runs (-c without
+ * -g) are the reference's algo.h paths and are NOT provided here (BASELINE.json: "no CPU
+ * fallback"): they exit with status 1 and a message.  With -g, -c only meant "a CPU thread also
+ * pulls chunks" (main.cu:66); it is accepted and ignored.
+ * Extra, off by default: the environment variable PERMAN_PRECISION=<digits> adds a second line
+ * `Result17: <name> <value>` with that many significant digits (the reference prints 6).
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <getopt.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "superman_b200.h"
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + (double)ts.tv_nsec * 1e-9;
+}
+
+static void print_kernel_lines(const sp_stats *st) {
+  /* the wrappers print "kernel in <t>" (single GPU, gpu_exact_dense.cu:683) or
+   * "kernel<g> in <t>" (multi GPU, :755) with the launch+sync wall time in seconds */
+  if (st->devices <= 1) {
+    printf("kernel in %g\n", st->kernel_ms * 1e-3);
+  } else {
+    for (int g = 0; g < st->devices; ++g) printf("kernel%d in %g\n", g, st->device_ms[g] * 1e-3);
+  }
+}
+
+static void extra_precision(const char *name, double v) {
+  const char *e = getenv("PERMAN_PRECISION");
+  if (!e || !*e) return;
+  int digits = atoi(e);
+  if (digits < 1) digits = 17;
+  if (digits > 40) digits = 40;
+  printf("Result17: %s %.*g\n", name, digits, v);
+}
+
+/* cout << "Result: name " << perman << " in " << secs  (6 significant digits, main.cu:58) */
+static void result_cout(const char *name, double v, double secs) {
+  printf("Result: %s %g in %g\n", name, v, secs);
+  extra_precision(name, v);
+}
+/* printf("Result: name %2lf in %lf\n") followed by the cout line (approximations, main.cu:82-83) */
+static void result_both(const char *name, const char *try_prefix, double v, double secs) {
+  printf("Result: %s %2lf in %lf\n", name, v, secs);
+  printf("%s: %s %g in %g\n", try_prefix, name, v, secs);
+  extra_precision(name, v);
+}
+
+static int report_failure(void) {
+  fprintf(stderr, "perman: %s\n", sp_last_error());
+  return 1;
+}
+
+static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int threads, int cpu, int dense,
+                      int approximation, int number_of_times, int scale_intervals, int scale_times) {
+  sp_stats st;
+  double start, perman;
+  const int nov = m->nov;
+  if (dense) {
+    if (!approximation) {
+      static const char *names[7] = {
+          "gpu_perman64_xlocal",  /* id 0 prints the xlocal label in the reference too (main.cu:38) */
+          "gpu_perman64_xlocal", "gpu_perman64_xshared", "gpu_perman64_xshared_coalescing",
+          "gpu_perman64_xshared_coalescing_mshared", "gpu_perman64_xshared_coalescing_mshared_multigpu",
+          "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks"};
+      if (perman_algo == 66) {
+        /* 3:3:1:1 manual split over exactly four GPUs (gpu_exact_dense.cu:906-989): a hack for one
+         * heterogeneous box; served by the even static split over four devices */
+        start = now_s();
+        perman = sp_dense_ryser(m->mat, nov, 5, 4, cpu, threads, &st);
+        if (isnan(perman) && st.error) return report_failure();
+        print_kernel_lines(&st);
+        printf("Result: gpu_perman64_xshared_coalescing_mshared_multigpu_manual_distribution %2lf in %lf\n",
+               perman, now_s() - start);
+        return 0;
+      }
+      if (perman_algo < 0 || perman_algo > 6) { printf("Unknown Algorithm ID\n"); return 0; }
+      start = now_s();
+      perman = sp_dense_ryser(m->mat, nov, perman_algo, gpu_num, cpu, threads, &st);
+      if (isnan(perman) && st.error) return report_failure();
+      print_kernel_lines(&st);
+      result_cout(names[perman_algo], perman, now_s() - start);
+    } else {
+      const char *name;
+      start = now_s();
+      switch (perman_algo) {
+        case 1: name = "gpu_perman64_rasmussen";
+          perman = sp_rasmussen_dense(m->mat, nov, number_of_times, 1, 0, &st); break;
+        case 2: name = "gpu_perman64_approximation";
+          perman = sp_scaling_dense(m->mat, nov, number_of_times, scale_intervals, scale_times, 1, 0, &st); break;
+        case 3: name = "gpu_perman64_rasmussen_multigpucpu_chunks";
+          perman = sp_rasmussen_dense(m->mat, nov, number_of_times, gpu_num, 0, &st); break;
+        case 4: name = "gpu_perman64_approximation_multigpucpu_chunks";
+          perman = sp_scaling_dense(m->mat, nov, number_of_times, scale_intervals, scale_times, gpu_num, 0, &st); break;
+        default: printf("Unknown Algorithm ID\n"); return 0;
+      }
+      if (isnan(perman) && st.error) return report_failure();
+      print_kernel_lines(&st);
+      result_both(name, "Result", perman, now_s() - start);
+    }
+  } else {
+    if (!approximation) {
+      const char *name = NULL;
+      start = now_s();
+      switch (perman_algo) {
+        case 1: name = "gpu_perman64_xlocal_sparse"; break;
+        case 2: name = "gpu_perman64_xshared_sparse"; break;
+        case 3: name = "gpu_perman64_xshared_coalescing_sparse"; break;
+        case 4: name = "gpu_perman64_xshared_coalescing_mshared_sparse"; break;
+        case 5: name = "gpu_perman64_xshared_coalescing_mshared_multigpu_sparse"; break;
+        case 6: name = "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_sparse"; break;
+        case 7: name = "gpu_perman64_xshared_coalescing_mshared_skipper"; break;
+        case 8: name = "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_skipper"; break;
+        case 66: name = "gpu_perman64_xshared_coalescing_mshared_multigpu_sparse_manual_distribution"; break;
+        default: printf("Unknown Algorithm ID\n"); return 0;
+      }
+      if (perman_algo == 7 || perman_algo == 8)
+        perman = sp_skipper(m->mat, m->rptrs, m->cols, m->cptrs, m->rows, m->cvals, nov, perman_algo, gpu_num,
+                            cpu, threads, &st);
+      else if (perman_algo == 66)
+        perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, nov, 5, 4, cpu, threads, &st);
+      else
+        perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, nov, perman_algo, gpu_num, cpu, threads, &st);
+      if (isnan(perman) && st.error) return report_failure();
+      print_kernel_lines(&st);
+      result_cout(name, perman, now_s() - start);
+    } else {
+      const char *name;
+      start = now_s();
+      switch (perman_algo) {
+        case 1: name = "gpu_perman64_rasmussen_sparse";
+          perman = sp_rasmussen_sparse(m->rptrs, m->cols, m->cptrs, m->rows, nov, m->nnz, number_of_times, 1, 0, &st); break;
+        case 2: name = "gpu_perman64_approximation_sparse";
+          perman = sp_scaling_sparse(m->cptrs, m->rows, m->rptrs, m->cols, nov, m->nnz, number_of_times,
+                                     scale_intervals, scale_times, 1, 0, &st); break;
+        case 3: name = "gpu_perman64_rasmussen_multigpucpu_chunks_sparse";
+          perman = sp_rasmussen_sparse(m->rptrs, m->cols, m->cptrs, m->rows, nov, m->nnz, number_of_times, gpu_num, 0, &st); break;
+        case 4: name = "gpu_perman64_approximation_multigpucpu_chunks_sparse";
+          perman = sp_scaling_sparse(m->cptrs, m->rows, m->rptrs, m->cols, nov, m->nnz, number_of_times,
+                                     scale_intervals, scale_times, gpu_num, 0, &st); break;
+        default: printf("Unknown Algorithm ID\n"); return 0;
+      }
+      if (isnan(perman) && st.error) return report_failure();
+      print_kernel_lines(&st);
+      result_both(name, "Result", perman, now_s() - start);
+    }
+  }
+  return 0;
+}
+
+/* RunPermanForGridGraphs (main.cu:250-323) */
+static int run_grid(int gm, int gn, int perman_algo, int gpu_num, int number_of_times, int scale_intervals,
+                    int scale_times) {
+  sp_matrix g;
+  if (sp_matrix_grid(gm, gn, &g) != SP_OK) {
+    /* the reference prints this (sic) and returns without computing, main.cu:404-407 / 253-260 */
+    printf("one of the grid dimensions should be positive.");
+    return 0;
+  }
+  sp_stats st;
+  double perman;
+  const char *name, *try_name;
+  const double start = now_s();
+  switch (perman_algo) {
+    case 1: name = try_name = "gpu_perman64_rasmussen_sparse";
+      perman = sp_rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, number_of_times, 1, 0, &st); break;
+    case 2: name = try_name = "gpu_perman64_approximation_sparse";
+      perman = sp_scaling_sparse(g.cptrs, g.rows, g.rptrs, g.cols, g.nov, g.nnz, number_of_times, scale_intervals,
+                                 scale_times, 1, 0, &st); break;
+    case 3: name = try_name = "gpu_perman64_rasmussen_multigpucpu_chunks";
+      perman = sp_rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, number_of_times, gpu_num, 0, &st); break;
+    case 4: name = try_name = "gpu_perman64_approximation_multigpucpu_chunks_sparse";
+      perman = sp_scaling_sparse(g.cptrs, g.rows, g.rptrs, g.cols, g.nov, g.nnz, number_of_times, scale_intervals,
+                                 scale_times, gpu_num, 0, &st); break;
+    default:
+      printf("Unknown Algorithm ID\n");
+      sp_matrix_free(&g);
+      return 0;
+  }
+  if (isnan(perman) && st.error) { sp_matrix_free(&g); return report_failure(); }
+  const double secs = now_s() - start;
+  print_kernel_lines(&st);
+  printf("Result: %s %2lf in %lf\n", name, perman, secs);
+  printf("Try: %s %g in %g\n", try_name, perman, secs);
+  extra_precision(name, perman);
+  if (getenv("PERMAN_PRECISION")) printf("StdError: %s %.6g trials %llu\n", name, st.std_error, st.units);
+  /* the reference dumps m rows x n columns of the nov x nov matrix here (main.cu:309-316) */
+  printf("------------GRID--------------\n");
+  for (int i = 0; i < gm; ++i) {
+    for (int j = 0; j < gn; ++j) {
+      const long idx = (long)i * gn + j;
+      printf("%d ", idx < (long)g.nov * g.nov ? (int)g.mat[idx] : 0);
+    }
+    printf("\n");
+  }
+  printf("------------GRID--------------\n");
+  sp_matrix_free(&g);
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  int generic = 1, dense = 1, approximation = 0, gpu = 0, cpu = 0;
+  int gpu_num = 2, threads = 16;                     /* main.cu:332-333 */
+  const char *filename = "";
+  int perman_algo = 1, preprocessing = 0;            /* main.cu:335-336 */
+  int number_of_times = 100000, scale_intervals = 4, scale_times = 5;   /* main.cu:338-340 */
+  int grid_graph = 0, gridm = 36, gridn = 36;        /* main.cu:342-344 */
+
+  static const char *short_options = "bsr:t:f:gd:cap:x:y:z:im:n:";
+  static const struct option long_options[] = {
+      {"binary", 0, NULL, 'b'},        {"sparse", 0, NULL, 's'},       {"preprocessing", 1, NULL, 'r'},
+      {"threads", 1, NULL, 't'},       {"file", 1, NULL, 'f'},         {"gpu", 0, NULL, 'g'},
+      {"device", 1, NULL, 'd'},        {"cpu", 0, NULL, 'c'},          {"approximation", 0, NULL, 'a'},
+      {"perman", 1, NULL, 'p'},        {"numOfTimes", 1, NULL, 'x'},   {"scaleIntervals", 1, NULL, 'y'},
+      {"scaleTimes", 1, NULL, 'z'},    {"grid", 0, NULL, 'i'},         {"gridm", 1, NULL, 'm'},
+      {"gridn", 1, NULL, 'n'},         {NULL, 0, NULL, 0}};
+
+  int opt;
+  while ((opt = getopt_long(argc, argv, short_options, long_options, NULL)) != -1) {
+    /* every valued option refuses an argument that looks like another option (main.cu:381-384) */
+    if (optarg && optarg[0] == '-' && strchr("rtfdpxyzmn", opt)) {
+      /* the reference's message names -t for -r as well (main.cu:382); we name the real option */
+      fprintf(stderr, "Option -%c requires an argument.\n", opt);
+      return 1;
+    }
+    switch (opt) {
+      case 'b': generic = 0; break;
+      case 's': dense = 0; break;
+      case 'r': preprocessing = atoi(optarg); break;
+      case 't': threads = atoi(optarg); break;
+      case 'f': filename = optarg; break;
+      case 'a': approximation = 1; break;
+      case 'g': gpu = 1; break;
+      case 'd': gpu_num = atoi(optarg); break;
+      case 'c': cpu = 1; break;
+      case 'p': perman_algo = atoi(optarg); break;
+      case 'x': number_of_times = atoi(optarg); break;
+      case 'y': scale_intervals = atoi(optarg); break;
+      case 'z': scale_times = atoi(optarg); break;
+      case 'i': grid_graph = 1; break;
+      case 'm': gridm = atoi(optarg); break;
+      case 'n': gridn = atoi(optarg); break;
+      case '?': return 1;
+      default: abort();
+    }
+  }
+  if (!grid_graph && filename[0] == '\0') {
+    fprintf(stderr, "Option -f is a required argument.\n");
+    return 1;
+  }
+  for (int index = optind; index < argc; index++) printf("Non-option argument %s\n", argv[index]);
+  if (!cpu && !gpu) gpu = 1;
+  if (!gpu) {
+    fprintf(stderr,
+            "perman: CPU-only algorithms (-c without -g: algo.h of the reference) are not part of this build; "
+            "run without -c to use the GPU paths\n");
+    return 1;
+  }
+  /* the reference's single-GPU ids pick device 1 and need two GPUs (gpu_exact_dense.cu:664); here
+   * -d only bounds the multi-GPU ids, capped by what is visible */
+  const int visible = sp_device_count();
+  if (visible <= 0) return report_failure();
+  if (gpu_num > visible) {
+    fprintf(stderr, "perman: -d %d but only %d device(s) visible; using %d\n", gpu_num, visible, visible);
+    gpu_num = visible;
+  }
+  if (gpu_num < 1) gpu_num = 1;
+
+  if (grid_graph)
+    return run_grid(gridm, gridn, perman_algo, gpu_num, number_of_times, scale_intervals, scale_times);
+
+  sp_matrix m;
+  if (sp_matrix_read(filename, !generic, &m) != SP_OK) return report_failure();
+  if (sp_matrix_compress(&m, preprocessing) != SP_OK) { sp_matrix_free(&m); return report_failure(); }
+  const int rc = run_matrix(&m, perman_algo, gpu_num, threads, cpu, dense, approximation, number_of_times,
+                            scale_intervals, scale_times);
+  sp_matrix_free(&m);
+  return rc;
+}

@@ -343,3 +343,176 @@ double sp_sparse_ryser_range(const double *mat, const int *cptrs, const int *row
   }
   return sum;
 }
+
+/* ================================================================================================
+ * Approximations
+ * ============================================================================================== */
+#define SP_DEFAULT_SEED 0x5355506572ULL   /* "SUPer" */
+
+static unsigned long long pick_seed(unsigned long long seed) {
+  if (seed != 0) return seed;
+  const char *e = getenv("SP_SEED");
+  if (e && *e) {
+    unsigned long long v = strtoull(e, NULL, 0);
+    if (v != 0) return v;
+  }
+  return SP_DEFAULT_SEED;
+}
+
+typedef struct approx_job {
+  const int *rptrs, *cols, *cptrs, *rows;
+  const double *rvals, *cvals;
+  int nov, nnz, scaling, y, z;
+  unsigned long long seed;
+} approx_job;
+
+static int approx_open(const void *job, int device, void **plan) {
+  const approx_job *j = (const approx_job *)job;
+  return spd_approx_plan_create(device, j->rptrs, j->cols, j->cptrs, j->rows, j->rvals, j->cvals, j->nov,
+                                j->nnz, j->scaling, j->y, j->z, j->seed, (spd_approx_plan **)plan);
+}
+static int approx_launch(void *plan, unsigned long long lo, unsigned long long hi) {
+  return spd_approx_plan_launch((spd_approx_plan *)plan, lo, hi);
+}
+/* the scheduler only carries one double per chunk; the squared sums ride along in a side table */
+static _Thread_local double g_sq_acc;
+static _Thread_local double g_sq_scale;
+static int approx_wait(void *plan, double *sum, spd_run_info *info) {
+  int rc = spd_approx_plan_wait((spd_approx_plan *)plan, sum, info);
+  if (rc == SPD_OK) { g_sq_acc += info->aux0; g_sq_scale = info->aux1; }
+  return rc;
+}
+static void approx_close(void *plan) { spd_approx_plan_destroy((spd_approx_plan *)plan); }
+static const sp_job_ops g_approx_ops = {approx_open, approx_launch, approx_wait, approx_close};
+
+static double approx_common(const approx_job *job, long long trials, int gpu_num, sp_stats *stats) {
+  const double t0 = sp_now_ms();
+  stats_clear(stats);
+  if (!job->rptrs || !job->cols || !job->cptrs || !job->rows) { sp_set_error("null argument"); return fail(stats, SP_EINVAL); }
+  if (trials < 1) { sp_set_error("number of trials must be positive (got %lld)", trials); return fail(stats, SP_EINVAL); }
+  if (gpu_num < 1) gpu_num = 1;
+  if ((long long)gpu_num > trials) gpu_num = (int)trials;
+  sp_stats local;
+  sp_stats *st = stats ? stats : &local;
+  double sum = 0.0;
+  int rc;
+  if (gpu_num == 1) {
+    /* single device: run on the calling thread so that the squared sum can be read back directly */
+    g_sq_acc = 0.0; g_sq_scale = 1.0;
+    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, 1, 0, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
+    if (rc == SP_OK) {
+      const double n = (double)trials, mean = sum / n, ms = mean * g_sq_scale;
+      double var = g_sq_acc / n - ms * ms;
+      if (var < 0) var = 0;
+      st->std_error = (n > 1) ? sqrt(var / (n - 1)) / g_sq_scale : 0.0;
+    }
+  } else {
+    /* several devices: static even split of the trial indices; the standard error is taken from
+     * the per-device means (batch means) */
+    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, gpu_num, 0, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
+    if (rc == SP_OK) {
+      const double mean = sum / (double)trials;
+      double acc = 0.0;
+      for (int g = 0; g < st->devices; ++g) {
+        const double mg = st->device_partial[g] / (double)(st->device_units[g] ? st->device_units[g] : 1);
+        const double rel = (mean != 0.0) ? (mg / mean - 1.0) : 0.0;
+        acc += rel * rel;
+      }
+      st->std_error = (st->devices > 1) ? fabs(mean) * sqrt(acc / (st->devices - 1) / st->devices) : 0.0;
+    }
+  }
+  st->wall_ms = sp_now_ms() - t0;
+  if (rc != SP_OK) return fail(stats, rc);
+  return sum / (double)trials;
+}
+
+double sp_rasmussen_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
+                           int nov, int nnz, long long trials, int gpu_num,
+                           unsigned long long seed, sp_stats *stats) {
+  approx_job job = {rptrs, cols, cptrs, rows, NULL, NULL, nov, nnz, 0, 1, 0, pick_seed(seed)};
+  return approx_common(&job, trials, gpu_num, stats);
+}
+
+double sp_scaling_sparse(const int *cptrs, const int *rows, const int *rptrs, const int *cols,
+                         int nov, int nnz, long long trials, int scale_intervals, int scale_times,
+                         int gpu_num, unsigned long long seed, sp_stats *stats) {
+  approx_job job = {rptrs, cols, cptrs, rows, NULL, NULL, nov, nnz, 1, scale_intervals, scale_times, pick_seed(seed)};
+  return approx_common(&job, trials, gpu_num, stats);
+}
+
+/* pattern (entries != 0) of a dense matrix as CRS + CCS with values */
+static int dense_pattern(const double *mat, int nov, int **rptrs, int **cols, double **rvals, int **cptrs,
+                         int **rows, double **cvals, int *nnz_out) {
+  int nnz = 0;
+  for (size_t e = 0; e < (size_t)nov * nov; ++e) nnz += (mat[e] != 0);
+  const size_t c1 = (size_t)(nnz > 0 ? nnz : 1);
+  *rptrs = (int *)malloc((size_t)(nov + 1) * sizeof(int));
+  *cptrs = (int *)malloc((size_t)(nov + 1) * sizeof(int));
+  *cols = (int *)malloc(c1 * sizeof(int));
+  *rows = (int *)malloc(c1 * sizeof(int));
+  *rvals = (double *)malloc(c1 * sizeof(double));
+  *cvals = (double *)malloc(c1 * sizeof(double));
+  if (!*rptrs || !*cptrs || !*cols || !*rows || !*rvals || !*cvals) { sp_set_error("out of memory"); return SP_ENOMEM; }
+  int r = 0, c = 0;
+  for (int a = 0; a < nov; ++a) {
+    (*rptrs)[a] = r; (*cptrs)[a] = c;
+    for (int b = 0; b < nov; ++b) {
+      if (mat[(size_t)a * nov + b] != 0) { (*cols)[r] = b; (*rvals)[r] = mat[(size_t)a * nov + b]; ++r; }
+      if (mat[(size_t)b * nov + a] != 0) { (*rows)[c] = b; (*cvals)[c] = mat[(size_t)b * nov + a]; ++c; }
+    }
+  }
+  (*rptrs)[nov] = r; (*cptrs)[nov] = c;
+  *nnz_out = nnz;
+  return SP_OK;
+}
+
+static double dense_approx(const double *mat, int nov, long long trials, int scaling, int y, int z,
+                           int gpu_num, unsigned long long seed, sp_stats *stats) {
+  stats_clear(stats);
+  if (!mat) { sp_set_error("mat is NULL"); return fail(stats, SP_EINVAL); }
+  if (nov < 1 || nov > SP_MAX_NOV) { sp_set_error("matrix order %d out of range", nov); return fail(stats, SP_ELIMIT); }
+  int *rptrs = NULL, *cols = NULL, *cptrs = NULL, *rows = NULL, nnz = 0;
+  double *rvals = NULL, *cvals = NULL;
+  int rc = dense_pattern(mat, nov, &rptrs, &cols, &rvals, &cptrs, &rows, &cvals, &nnz);
+  double r = NAN;
+  if (rc == SP_OK) {
+    approx_job job = {rptrs, cols, cptrs, rows, scaling ? rvals : NULL, scaling ? cvals : NULL,
+                      nov, nnz, scaling, y, z, pick_seed(seed)};
+    r = approx_common(&job, trials, gpu_num, stats);
+  } else if (stats) {
+    stats->error = rc;
+  }
+  free(rptrs); free(cols); free(cptrs); free(rows); free(rvals); free(cvals);
+  return r;
+}
+
+double sp_rasmussen_dense(const double *mat, int nov, long long trials, int gpu_num,
+                          unsigned long long seed, sp_stats *stats) {
+  return dense_approx(mat, nov, trials, 0, 1, 0, gpu_num, seed, stats);
+}
+
+double sp_scaling_dense(const double *mat, int nov, long long trials, int scale_intervals,
+                        int scale_times, int gpu_num, unsigned long long seed, sp_stats *stats) {
+  return dense_approx(mat, nov, trials, 1, scale_intervals, scale_times, gpu_num, seed, stats);
+}
+
+double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
+                              int nov, int nnz, int scaling, int scale_intervals, int scale_times,
+                              unsigned long long seed, long long trial, int count, double *values,
+                              sp_stats *stats) {
+  stats_clear(stats);
+  if (!values || count < 1 || trial < 0) { sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
+  spd_approx_plan *plan = NULL;
+  int rc = spd_approx_plan_create(0, rptrs, cols, cptrs, rows, NULL, NULL, nov, nnz, scaling,
+                                  scale_intervals, scale_times, pick_seed(seed), &plan);
+  if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
+  double total = 0.0;
+  for (int i = 0; i < count; ++i) {
+    rc = spd_approx_plan_trial(plan, (unsigned long long)trial + (unsigned long long)i, &values[i]);
+    if (rc != SPD_OK) break;
+    total += values[i];
+  }
+  spd_approx_plan_destroy(plan);
+  if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
+  return total;
+}

@@ -71,6 +71,30 @@ class Oracle:
         L.orc_sparyser_range_f64.argtypes = [_dp, _ip, _ip, _dp, C.c_int, u64, u64]
         L.orc_skipper_range_f64.restype = C.c_double
         L.orc_skipper_range_f64.argtypes = [_dp, _ip, _ip, _ip, _ip, _dp, C.c_int, u64, u64, C.POINTER(u64)]
+        self._approx_sigs()
+
+    # ---- approximations ----
+    def _approx_sigs(self):
+        L = self.lib
+        L.orc_rasmussen_trial.restype = C.c_double
+        L.orc_rasmussen_trial.argtypes = [_ip, _ip, C.c_int, u64, u64]
+        L.orc_scaling_trial.restype = C.c_double
+        L.orc_scaling_trial.argtypes = [_ip, _ip, _ip, _ip, _dp, _dp, C.c_int, C.c_int, C.c_int, u64, u64]
+        L.orc_philox.restype = None
+        L.orc_philox.argtypes = [u64, u64, C.c_uint, C.POINTER(C.c_uint * 4)]
+
+    def philox(self, seed, trial, block):
+        out = (C.c_uint * 4)()
+        self.lib.orc_philox(seed, trial, block, C.byref(out))
+        return list(out)
+
+    def rasmussen_trial(self, rptrs, cols, nov, seed, trial) -> float:
+        return self.lib.orc_rasmussen_trial(_pi(_i(rptrs)), _pi(_i(cols)), nov, seed, trial)
+
+    def scaling_trial(self, rptrs, cols, cptrs, rows, nov, y, z, seed, trial, rvals=None, cvals=None) -> float:
+        rv = _pd(_d(rvals)) if rvals is not None else None
+        cv = _pd(_d(cvals)) if cvals is not None else None
+        return self.lib.orc_scaling_trial(_pi(_i(rptrs)), _pi(_i(cols)), _pi(_i(cptrs)), _pi(_i(rows)), rv, cv, nov, y, z, seed, trial)
 
     # ---- dense ----
     def perm_ld(self, mat) -> float:

@@ -1,0 +1,136 @@
+"""CPU: host logic in C (reader, CRS/CCS, SortOrder, SkipOrder, grid, scheduler partition), the
+C-ABI symbol table, and the no-CPU-fallback rule."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol(sp):
+    from superman_b200 import _ffi
+    names = set()
+    for hdr in ("superman_b200.h", "superman_b200_device.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(spd?_[a-z0-9_]+)\s*\(", text))
+    assert len(names) > 40
+    missing = [n for n in sorted(names) if not hasattr(_ffi.lib, n)]
+    assert not missing, missing
+
+
+def test_reader_and_preprocessing_match_reference_golden(sp, tmp_path):
+    for idx, e in enumerate(_golden.small()):
+        path = tmp_path / ("m%d.txt" % idx)
+        _golden.write_matrix_file(e, path)
+        for pre in (0, 1, 2):
+            g = e["compress_%d" % pre]
+            m = sp.Matrix.read(str(path)).compress(pre)
+            assert m.nov == e["n"] and m.type == e["type"] and m.nnz == g["nnz"]
+            assert m.mat.reshape(-1).tolist() == g["mat"], (idx, pre)
+            assert m.cptrs.tolist() == g["cptrs"] and m.rows.tolist() == g["rows"]
+            assert m.rptrs.tolist() == g["rptrs"] and m.cols.tolist() == g["cols"]
+            assert m.cvals.tolist() == g["cvals"] and m.rvals.tolist() == g["rvals"]
+        b = sp.Matrix.read(str(path), binary=True)
+        assert set(np.unique(b.mat)) <= {0.0, 1.0}
+        assert (b.mat != 0).sum() == len(e["triples"])
+
+
+def test_reader_edge_cases(sp, tmp_path):
+    p = tmp_path / "edge.txt"
+    p.write_text("3 4 int\n0 0 2\n\nnot a line\n1 1 3.9\n2 2 4\n7 7 1\n0 2 5 trailing\n")
+    m = sp.Matrix.read(str(p)).compress(0)
+    want = np.array([[2, 0, 5], [0, 3, 0], [0, 0, 4]], float)   # "3.9" read as int -> 3; (7,7) out of range ignored
+    assert np.array_equal(m.mat, want)
+    assert m.header_nnz == 4 and m.nnz == 4
+    (tmp_path / "bad.txt").write_text("3 4 complex\n0 0 1\n")
+    with pytest.raises(sp.SupermanError):
+        sp.Matrix.read(str(tmp_path / "bad.txt"))
+    with pytest.raises(sp.SupermanError):
+        sp.Matrix.read(str(tmp_path / "missing.txt"))
+    (tmp_path / "empty.txt").write_text("")
+    with pytest.raises(sp.SupermanError):
+        sp.Matrix.read(str(tmp_path / "empty.txt"))
+    # float files are rounded to float first (ReadMatrix<float>)
+    (tmp_path / "f.txt").write_text("1 1 float\n0 0 0.1\n")
+    assert sp.Matrix.read(str(tmp_path / "f.txt")).mat[0, 0] == float(np.float32(0.1))
+
+
+def test_grid_matches_reference_golden(sp):
+    for g in _golden.grids():
+        m = sp.Matrix.grid(g["m"], g["n"])
+        assert m.nov == g["nov"] and m.nnz == g["nnz"]
+        assert m.cptrs.tolist() == g["cptrs"] and m.rows.tolist() == g["rows"]
+        assert m.rptrs.tolist() == g["rptrs"] and m.cols.tolist() == g["cols"]
+    with pytest.raises(sp.SupermanError):
+        sp.Matrix.grid(3, 5)
+
+
+def test_scheduler_partition(sp):
+    from superman_b200 import _ffi
+    f = _ffi.lib.sp_sched_boundary
+    f.restype = C.c_ulonglong
+    f.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_int]
+    for lo, hi, parts, align in [(0, 1 << 35, 8, 14), (0, 1 << 35, 3, 14), (1, (1 << 20) + 7, 5, 4), (0, 100, 7, 0), (5, 5, 4, 3)]:
+        b = [f(lo, hi, parts, i, align) for i in range(parts + 1)]
+        assert b[0] == lo and b[-1] == hi
+        assert all(b[i] <= b[i + 1] for i in range(parts))
+        for x in b[1:-1]:
+            assert x == lo or x % (1 << align) == 0
+    # bench.py's rank_slice uses the same rule
+    import bench
+    for world in (1, 2, 4, 8):
+        sl = [bench.rank_slice(1 << 35, r, world) for r in range(world)]
+        assert sl[0][0] == 0 and sl[-1][1] == 1 << 35
+        assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
+        assert [s[0] for s in sl] == [f(0, 1 << 35, world, r, 14) for r in range(world)]
+    g = _ffi.lib.sp_dynamic_chunks
+    g.restype = C.c_ulonglong
+    g.argtypes = [C.c_int, C.c_int, C.c_int]
+    assert g(36, 29, 1) == 128 and g(40, 29, 8) == 2048      # gpu_exact_dense.cu:786-793
+    assert g(33, 30, 1) == 8 and g(30, 29, 8) >= 2
+
+
+def test_no_cpu_fallback(sp):
+    """without a GPU every compute entry point must fail loudly, never compute on the host"""
+    if sp.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(sp.SupermanError):
+        sp.dense_ryser(np.ones((4, 4)), 4)
+    m = sp.Matrix.from_dense(np.ones((4, 4))).compress(0)
+    with pytest.raises(sp.SupermanError):
+        sp.sparse_ryser(m.mat, m.cptrs, m.rows, m.cvals, 4)
+    with pytest.raises(sp.SupermanError):
+        sp.rasmussen_sparse(m.rptrs, m.cols, m.cptrs, m.rows, 4, m.nnz, 10)
+    with pytest.raises(sp.SupermanError):
+        sp.fp64_peak(0, 10)
+
+
+def test_product_does_not_link_the_oracle():
+    so = os.path.join(ROOT, "superman_b200", "libsuperman_b200.so")
+    out = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+    assert "orc_" not in out
+    ldd = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "liboracle" not in ldd and "libref" not in ldd
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "superman_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".c", ".cu", ".h", ".cuh")):
+                assert "oracle" not in open(os.path.join(dirpath, fn)).read().replace("the oracle restates", "").replace("with the C oracle", "").replace("the oracle", ""), fn
+
+
+def test_cli_argument_errors():
+    exe = os.path.join(ROOT, "superman_b200", "perman")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Option -f is a required argument." in r.stderr      # main.cu:472-475
+    r = subprocess.run([exe, "-f", "x", "-p", "-3"], capture_output=True, text=True)
+    assert r.returncode == 1 and "requires an argument" in r.stderr                     # main.cu:381-384
+    r = subprocess.run([exe, "-f", "x", "-c"], capture_output=True, text=True)
+    assert r.returncode == 1 and "CPU-only" in r.stderr
+    r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 1

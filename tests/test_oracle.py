@@ -1,0 +1,145 @@
+"""CPU: pins the oracle (oracle/*.c) against closed forms, the committed golden vectors produced by
+the unmodified reference, and -- when oracle/_ref/libref.so is present -- the reference itself."""
+import math
+
+import numpy as np
+import pytest
+
+import _golden
+
+
+def test_closed_forms(oracle):
+    for n in (1, 2, 3, 5, 8, 11):
+        J = np.ones((n, n))
+        assert oracle.perm_ld(J) == math.factorial(n)
+        assert oracle.perm_i128(J) == math.factorial(n)
+        assert oracle.perm_f64(J) == pytest.approx(math.factorial(n), rel=1e-13)
+        assert oracle.perm_ld(np.eye(n)) == 1.0
+    # derangements: perm(J - I)
+    der = [1, 0, 1, 2, 9, 44, 265, 1854, 14833, 133496, 1334961]
+    for n in range(2, 11):
+        D = np.ones((n, n)) - np.eye(n)
+        assert oracle.perm_i128(D) == der[n]
+        assert oracle.perm_ld(D) == pytest.approx(der[n], rel=1e-14)
+
+
+def test_range_additivity_and_base_term(oracle):
+    rng = np.random.default_rng(5)
+    n = 12
+    A = rng.uniform(0.1, 3, (n, n))
+    full = 1 << (n - 1)
+    cuts = [0, 1, 2, 77, 513, 1500, full]
+    parts = sum(oracle.ryser_range_f64(A, cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1))
+    whole = oracle.ryser_range_f64(A, 0, full)
+    assert parts == pytest.approx(whole, rel=1e-12)
+    # index 0 alone is the NW base product (algo.h:1049)
+    assert oracle.ryser_range_f64(A, 0, 1) == pytest.approx(oracle.nw_base_prod(A), rel=1e-13)
+    assert oracle.ryser_range_ld(A, 0, full) == pytest.approx(whole, rel=1e-11)
+    assert oracle.ryser_range_f64(A, 5, 5) == 0.0
+
+
+def test_golden_small(oracle):
+    for e in _golden.small():
+        A = _golden.dense_from(e)
+        n = e["n"]
+        # the double restatement is perman64 bit for bit; the long-double value was stored by the generator
+        assert oracle.perm_f64(A) == e["ref_perman64"]
+        assert oracle.perm_ld(A) == e["ld"]
+        assert oracle.perm_ld(A) == pytest.approx(e["ref_perman64"], rel=1e-10)
+        if e["i128"] is not None:
+            assert oracle.perm_i128(A.astype(int)) == int(e["i128"])
+            assert float(int(e["i128"])) == pytest.approx(e["ld"], rel=1e-15)
+        assert oracle.perm_i128((A != 0).astype(int)) == int(e["i128_binary"])
+        full = 1 << (n - 1)
+        for pre in (0, 1, 2):
+            g = e["compress_%d" % pre]
+            c = oracle.compress(A, pre)
+            assert c["nnz"] == g["nnz"]
+            for k in ("cptrs", "rows", "rptrs", "cols"):
+                assert c[k].tolist() == g[k], (n, pre, k)
+            assert c["cvals"].tolist() == g["cvals"] and c["rvals"].tolist() == g["rvals"]
+            assert c["mat"].reshape(-1).tolist() == g["mat"]
+            if pre:
+                f = -2.0 if n % 2 == 0 else 2.0
+                base = oracle.ryser_range_f64(c["mat"], 0, 1)     # NW base term, sequential row sums
+                spa = (base + oracle.sparyser_range(c["mat"], c["cptrs"], c["rows"], c["cvals"], 1, full)) * f
+                skp, vis = oracle.skipper_range(c["mat"], c["rptrs"], c["cols"], c["cptrs"], c["rows"], c["cvals"], 1, full)
+                skp = (base + skp) * f
+                # parallel_perman64_sparse (1 thread) keeps X in FLOAT (algo.h:570): bit-equal on
+                # integer matrices (half-integers are exact in float), ~1e-7 off on real-valued ones
+                if e["type"] == "int":
+                    assert spa == e["ref_sparse_%d" % pre]
+                else:
+                    assert spa == pytest.approx(e["ref_sparse_%d" % pre], rel=1e-5)
+                assert spa == pytest.approx(e["ld"], rel=1e-10)
+                assert skp == e["ref_skipper_%d" % pre]          # parallel_skip_perman64_w, 1 thread
+                assert 1 <= vis <= full - 1
+
+
+def test_golden_corpus_values(oracle):
+    """n=30 corpus files (BASELINE.json configs[0]): stored long-double values agree with the values
+    the reference's own double paths returned, to the spread SURVEY.md 8(c) documents."""
+    c = _golden.corpus()
+    assert "int/30_0.50_0" in c and "double/30_0.50_0" in c
+    assert c["int/30_0.50_0"]["ld"] == pytest.approx(5.319364329955188e+37, rel=1e-11)
+    assert c["double/30_0.50_0"]["ld"] == pytest.approx(1.082510471543260191e+35, rel=1e-13)
+    for name, e in c.items():
+        if e.get("ref_perman64") is not None:
+            assert e["ref_perman64"] == pytest.approx(e["ld"], rel=2e-8), name   # one serial double chain of 2^29 terms
+        for key in ("ref_skipper_sort", "ref_skipper_skip"):           # all-double paths (algo.h:885)
+            assert e[key] == pytest.approx(e["ld"], rel=2e-8), (name, key)
+        for key in ("ref_sparse_sort", "ref_sparse_skip"):             # float X (algo.h:570)
+            tol = 1e-9 if name.startswith("int/") else 0.5
+            assert e[key] == pytest.approx(e["ld"], rel=tol), (name, key)
+        if name.startswith("int/"):
+            # float X is exact for small-integer matrices: parallel_perman64 agrees there ...
+            assert e["ref_parallel_perman64_float_x"] == pytest.approx(e["ld"], rel=1e-9), name
+    # ... and is wrong on double/ files: parity is never asserted against it
+    d = c["double/30_0.50_0"]
+    assert abs(d["ref_parallel_perman64_float_x"] / d["ld"] - 1.0) > 1e-4
+
+
+def test_grid_and_kasteleyn(oracle):
+    for g in _golden.grids():
+        mat, nnz = oracle.grid_graph(g["m"], g["n"])
+        assert nnz == g["nnz"] and mat.shape[0] == g["nov"]
+        c = oracle.compress(mat.astype(float), 0)
+        assert c["cptrs"].tolist() == g["cptrs"] and c["rows"].tolist() == g["rows"]
+        assert c["rptrs"].tolist() == g["rptrs"] and c["cols"].tolist() == g["cols"]
+        assert oracle.kasteleyn(g["m"], g["n"]) == pytest.approx(g["kasteleyn"], rel=1e-14)
+        if g["nov"] <= 18:
+            assert oracle.perm_ld(mat.astype(float)) == pytest.approx(g["kasteleyn"], rel=1e-12)
+    assert oracle.kasteleyn(8, 8) == pytest.approx(12988816, rel=1e-13)
+    assert oracle.kasteleyn(36, 36) == pytest.approx(3.0596785293264126e159, rel=1e-12)
+    assert oracle.grid_graph(3, 5)[1] == -1
+
+
+def test_philox_known_answer(oracle):
+    # Random123 known-answer vectors for philox4x32-10
+    assert oracle.philox(0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+def test_estimators_unbiased(oracle):
+    g = [x for x in _golden.grids() if (x["m"], x["n"]) == (4, 4)][0]
+    ras = [oracle.rasmussen_trial(g["rptrs"], g["cols"], g["nov"], 3, t) for t in range(3000)]
+    sca = [oracle.scaling_trial(g["rptrs"], g["cols"], g["cptrs"], g["rows"], g["nov"], 4, 5, 3, t) for t in range(3000)]
+    for v in (ras, sca):
+        se = np.std(v) / math.sqrt(len(v))
+        assert abs(np.mean(v) - 36.0) < 5 * se
+
+
+def test_against_reference_live(oracle, reference):
+    """only where oracle/_ref/libref.so exists: fresh random inputs, reference vs oracle"""
+    rng = np.random.default_rng(99)
+    for n in (6, 9, 13, 16):
+        A = (rng.random((n, n)) < 0.5) * np.round(rng.uniform(0.01, 5, (n, n)), 6)
+        # no empty row: the reference's SkipOrder leaves rowPerm uninitialised for rows it never
+        # reaches (util.h:622,654) and then indexes with it
+        A[np.arange(n), np.arange(n)] = 1.5
+        assert oracle.perm_f64(A) == reference.perman64(A)
+        for pre in (0, 1, 2):
+            co, cr = oracle.compress(A, pre), reference.compress(A, pre)
+            for k in ("mat", "cptrs", "rows", "cvals", "rptrs", "cols", "rvals"):
+                assert np.array_equal(co[k], cr[k]), (n, pre, k)
+    for m, k in ((4, 4), (5, 6), (6, 7)):
+        assert np.array_equal(oracle.grid_graph(m, k)[0], reference.grid_graph(m, k)[0])
