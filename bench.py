@@ -6,7 +6,7 @@
 
 One "step" is one complete permanent of the seeded synthetic 36x36 density-0.50 double matrix
 (BASELINE.json configs[3]; 2^35 Gray indices).  With N ranks the index space is cut into N
-contiguous, 2^14-aligned slices, one per rank / GPU; there is no data-path collective -- each rank
+contiguous, 2^16-aligned slices, one per rank / GPU; there is no data-path collective -- each rank
 leaves one double and rank 0 adds them in rank order (strong scaling of one permanent, as the
 north star asks: "time-to-permanent ... at 1/2/4/8 B200").
 
@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 N_DENSE = 36
 DENSITY = 0.50
-ALIGN_LOG2 = 14
+ALIGN_LOG2 = 16
 
 
 def synthetic_matrix(n: int, density: float, instance: int = 0):

@@ -58,20 +58,31 @@ struct RegLayout {
   static constexpr int TOTAL = LOWR + N * LB;
 };
 
-// Tiles [tile_first, tile_first + n_tiles) of 2^c indices each; thread t of the grid owns tile
-// tile_first + t.  partials[blockIdx.x] receives the block's signed sum.  Index 0 (the NW base
-// term that the reference adds on the host, gpu_exact_dense.cu:653,691) is an ordinary tile
-// start here, so a launch over [0, 2^(n-1)) yields the complete sum.
-// Requires B + 1 <= c <= N - 1 and N - 1 > B.
+// Work layout: a "group" is SPB-THREADS (=128) consecutive tiles of 2^c indices, aligned to
+// 128 tiles; thread t of a block owns tile t of each of the block's `groups_per_block` consecutive
+// groups.  Inside a group the Gray codes of the 128 tile starts agree in every bit >= c+7, so the
+// block computes that common part of X once (X_blk, shared memory) and a thread only adds its own
+// 8 columns c-1 .. c+6 (masked by its Gray bits): the explicit X start (cf. gpu_exact_dense.cu:
+// 363-371) costs 8n FMAs per tile instead of (n-c)n.  That makes SHORT tiles affordable, and short
+// tiles are what keeps the result accurate: X is updated in place 2^c times per tile and its
+// rounding drift grows with the length of that chain (measured on double/30_0.20_0: 3e-11
+// relative error at c=13, 1e-12 at c=8; the reference's chains are 2^13..2^17 long).
+//
+// partials[blockIdx.x] receives the block's signed sum.  Index 0 (the NW base term that the
+// reference adds on the host, gpu_exact_dense.cu:653,691) is an ordinary tile start here, so a
+// launch over [0, 2^(n-1)) yields the complete sum.
+// Requires B + 1 <= c, c + 7 <= N - 1, group_first * 128 tiles aligned (it is a group index).
 template <int N, int B, int THREADS, int MINBLOCKS>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 ryser_reg_kernel(const double* __restrict__ mat_t,   // mat_t[k*N + j] = A[j][k]
                  const double* __restrict__ xbase,   // NW start vector (gpu_exact_dense.cu:647-654)
-                 double* __restrict__ partials, unsigned long long tile_first,
-                 unsigned long long n_tiles, int c) {
+                 double* __restrict__ partials, unsigned long long group_first,
+                 unsigned long long n_groups, int groups_per_block, int c) {
+  static_assert(THREADS == 128, "a group is 128 tiles: 7 thread-specific Gray bits");
   using L = RegLayout<N, B>;
   constexpr int NP = L::NP, LB = L::LB, NB = 1 << B;
   __shared__ __align__(16) double sm[L::TOTAL];
+  __shared__ __align__(16) double x_blk[NP];
   __shared__ double warp_part[THREADS / 32];
   for (int e = threadIdx.x; e < N * N; e += THREADS) {
     const int k = e / N, j = e % N;
@@ -79,72 +90,89 @@ ryser_reg_kernel(const double* __restrict__ mat_t,   // mat_t[k*N + j] = A[j][k]
     sm[L::COLT + k * NP + j] = v;
     if (k < B) sm[L::LOWR + j * LB + k] = v;
   }
-  __syncthreads();
   const uint32_t sm_colT = (uint32_t)__cvta_generic_to_shared(sm + L::COLT);
   const uint32_t sm_lowR = (uint32_t)__cvta_generic_to_shared(sm + L::LOWR);
 
-  const unsigned long long t = (unsigned long long)blockIdx.x * THREADS + threadIdx.x;
-  const bool active = t < n_tiles;
-  const unsigned long long s = (tile_first + (active ? t : 0ull)) << c;   // first index of the tile
-  const unsigned long long g = s ^ (s >> 1);                              // Gray code at the tile start
-  double x[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) x[j] = xbase[j];
-  // explicit X at the tile start (cf. gpu_exact_dense.cu:363-371).  Bits below c-1 of g are
-  // zero; every lane reads the same column (broadcast) and masks it with its own Gray bit.
-  for (int k = c - 1; k < N - 1; ++k) {
-    const double f = (double)((g >> k) & 1ull);
-    const double* col = sm + L::COLT + k * NP;
-#pragma unroll
-    for (int j = 0; j < N; ++j) x[j] = fma(f, col[j], x[j]);
-  }
-
   double acc = 0.0;
-  const int nblk = 1 << (c - B);
-  unsigned long long i0 = s;
+  const unsigned long long g0 = (unsigned long long)blockIdx.x * (unsigned)groups_per_block;
 #pragma unroll 1
-  for (int blk = 0; blk < nblk; ++blk, i0 += (unsigned long long)NB) {
-    // high column flipped at the block start: k = ctz(i0) = B + ctz(blk), same for all threads.
-    // Gray bit k after the flip is 1 ^ bit(k+1) of i0 -> add (+1) when that bit is clear.
-    // blk == 0 is the tile start, where X is already explicit: weight 0 leaves it unchanged.
-    const int k = (blk != 0) ? (B + __ffs(blk) - 1) : B;
-    const double sg = (blk != 0) ? (((i0 >> (k + 1)) & 1ull) ? -1.0 : 1.0) : 0.0;
-    // column B-1 flips in the middle of the block; its direction is bit B of i0
-    const double sg_top = (blk & 1) ? -1.0 : 1.0;
-    const uint32_t hi_addr = sm_colT + (uint32_t)(k * NP * 8);
-
-    double P[NB];
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      double m[LB];
-#pragma unroll
-      for (int q = 0; q < LB; q += 2) lds_f64x2(sm_lowR + (uint32_t)((j * LB + q) * 8), m[q], m[q + 1]);
-      double d;
-      lds_f64(hi_addr + (uint32_t)(j * 8), d);
-      double v = fma(sg, d, x[j]);
-      P[0] = (j == 0) ? v : P[0] * v;
-#pragma unroll
-      for (int u = 1; u < NB; ++u) {
-        const int K = ctz_c(u);
-        if (K == B - 1) {
-          v = fma(sg_top, m[K], v);
-        } else if (((u >> (K + 1)) & 1) == 0) {
-          v += m[K];
-        } else {
-          v -= m[K];
-        }
-        P[u] = (j == 0) ? v : P[u] * v;
-      }
-      x[j] = v;
+  for (int gi = 0; gi < groups_per_block; ++gi) {
+    const unsigned long long grp = g0 + gi;
+    if (grp >= n_groups) break;                                            // block-uniform
+    const unsigned long long tile0 = (group_first + grp) * THREADS;        // first tile of the group
+    __syncthreads();                                                       // x_blk free / sm staged
+    if (threadIdx.x < N) {
+      // common part: Gray bits >= c+7 of the group's tile starts
+      const unsigned long long s0 = tile0 << c;
+      const unsigned long long gc = s0 ^ (s0 >> 1);
+      double v = xbase[threadIdx.x];
+      for (int k = c + 7; k < N - 1; ++k)
+        if ((gc >> k) & 1ull) v += sm[L::COLT + k * NP + threadIdx.x];
+      x_blk[threadIdx.x] = v;
     }
-    // term sign (-1)^i: block start is even
-    double blk_sum = 0.0;
+    __syncthreads();
+    const unsigned long long s = (tile0 + threadIdx.x) << c;               // first index of my tile
+    const unsigned long long g = s ^ (s >> 1);                             // Gray code at the tile start
+    double x[N];
 #pragma unroll
-    for (int u = 0; u < NB; u += 2) blk_sum += (P[u] - P[u + 1]);
-    acc += blk_sum;
+    for (int j = 0; j < N; ++j) x[j] = x_blk[j];
+    // my own bits c-1 .. c+6: every lane reads the same column (broadcast) and masks it
+#pragma unroll 1
+    for (int k = c - 1; k < c + 7; ++k) {
+      const double f = (double)((g >> k) & 1ull);
+      const double* col = sm + L::COLT + k * NP;
+#pragma unroll
+      for (int j = 0; j < N; ++j) x[j] = fma(f, col[j], x[j]);
+    }
+
+    double tile_acc = 0.0;
+    const int nblk = 1 << (c - B);
+    unsigned long long i0 = s;
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk, i0 += (unsigned long long)NB) {
+      // high column flipped at the block start: k = ctz(i0) = B + ctz(blk), same for all threads.
+      // Gray bit k after the flip is 1 ^ bit(k+1) of i0 -> add (+1) when that bit is clear.
+      // blk == 0 is the tile start, where X is already explicit: weight 0 leaves it unchanged.
+      const int k = (blk != 0) ? (B + __ffs(blk) - 1) : B;
+      const double sg = (blk != 0) ? (((i0 >> (k + 1)) & 1ull) ? -1.0 : 1.0) : 0.0;
+      // column B-1 flips in the middle of the block; its direction is bit B of i0
+      const double sg_top = (blk & 1) ? -1.0 : 1.0;
+      const uint32_t hi_addr = sm_colT + (uint32_t)(k * NP * 8);
+
+      double P[NB];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double m[LB];
+#pragma unroll
+        for (int q = 0; q < LB; q += 2) lds_f64x2(sm_lowR + (uint32_t)((j * LB + q) * 8), m[q], m[q + 1]);
+        double d;
+        lds_f64(hi_addr + (uint32_t)(j * 8), d);
+        double v = fma(sg, d, x[j]);
+        P[0] = (j == 0) ? v : P[0] * v;
+#pragma unroll
+        for (int u = 1; u < NB; ++u) {
+          const int K = ctz_c(u);
+          if (K == B - 1) {
+            v = fma(sg_top, m[K], v);
+          } else if (((u >> (K + 1)) & 1) == 0) {
+            v += m[K];
+          } else {
+            v -= m[K];
+          }
+          P[u] = (j == 0) ? v : P[u] * v;
+        }
+        x[j] = v;
+      }
+      // term sign (-1)^i: block start is even
+      double blk_sum = 0.0;
+#pragma unroll
+      for (int u = 0; u < NB; u += 2) blk_sum += (P[u] - P[u + 1]);
+      tile_acc += blk_sum;
+    }
+    acc += tile_acc;
   }
 
-  acc = warp_sum(active ? acc : 0.0);
+  acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -94,16 +94,16 @@ ryser_smem_kernel(const double* __restrict__ mat_t, const double* __restrict__ x
 
 static int reg_launch(int n, int B, cudaStream_t st, const double* mat_t, const double* xbase,
                       double* partials, unsigned long long tile_first, unsigned long long n_tiles,
-                      int c, unsigned* blocks_out) {
+                      int gpb, int c, unsigned* blocks_out) {
   switch (n % SPB_NGROUPS) {
-    case 0: return spb_reg_launch_g0(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
-    case 1: return spb_reg_launch_g1(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
-    case 2: return spb_reg_launch_g2(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
-    case 3: return spb_reg_launch_g3(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
-    case 4: return spb_reg_launch_g4(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
-    case 5: return spb_reg_launch_g5(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
-    case 6: return spb_reg_launch_g6(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
-    default: return spb_reg_launch_g7(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+    case 0: return spb_reg_launch_g0(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
+    case 1: return spb_reg_launch_g1(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
+    case 2: return spb_reg_launch_g2(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
+    case 3: return spb_reg_launch_g3(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
+    case 4: return spb_reg_launch_g4(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
+    case 5: return spb_reg_launch_g5(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
+    case 6: return spb_reg_launch_g6(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
+    default: return spb_reg_launch_g7(n, B, st, mat_t, xbase, partials, tile_first, n_tiles, gpb, c, blocks_out);
   }
 }
 
@@ -183,33 +183,42 @@ static int dense_enqueue(spd_dense_plan* p, unsigned long long lo, unsigned long
   const bool reg_ok = (n >= SPB_REG_NMIN && n <= SPB_REG_NMAX && env_int("SP_DENSE_FORCE_SMEM", 0) == 0);
   unsigned long long body_lo = lo, body_hi = lo;   // empty body by default
   int c = 0;
-  if (reg_ok && len >= (1ull << (B + 1))) {
-    // tile = 2^c indices per thread: large enough to amortise the explicit X start (n-c+1 column
-    // adds), small enough that a launch has >= 2^tiles_log2 tiles to balance over the SMs.
-    const int tiles_log2 = env_int("SP_DENSE_TILES_LOG2", 22);
+  if (reg_ok && len >= (1ull << (B + 1 + 7))) {
+    // tile = 2^c indices per thread, group = 128 tiles.  Short tiles keep X's rounding drift small
+    // (ryser_reg.cuh); c = 9 costs < 1 % for the explicit X starts.  Small ranges use shorter tiles
+    // so that there are still enough groups to fill the SMs.
     c = env_int("SP_DENSE_TILE_LOG2", 0);
     if (c <= 0) {
-      c = ilog2_ull(len) - tiles_log2;
-      if (c > 14) c = 14;
+      c = ilog2_ull(len) - 7 - 12;
+      if (c > 9) c = 9;
     }
     if (c < B + 1) c = B + 1;
-    if (c > n - 1) c = n - 1;
-    const unsigned long long T = 1ull << c;
-    body_lo = (lo + T - 1) & ~(T - 1);
-    body_hi = hi & ~(T - 1);
-    if (body_hi <= body_lo) { body_lo = body_hi = lo; }
+    if (c > n - 8) c = n - 8;
+    if (c >= B + 1) {
+      const unsigned long long G = 1ull << (c + 7);
+      body_lo = (lo + G - 1) & ~(G - 1);
+      body_hi = hi & ~(G - 1);
+      if (body_hi <= body_lo) { body_lo = body_hi = lo; }
+    }
   }
 
   int rc;
   if (body_hi > body_lo) {
     p->info.path = SPD_PATH_DENSE_REG;
     p->info.tile_log2 = c;
-    unsigned long long tile = body_lo >> c;
-    unsigned long long tiles_left = (body_hi - body_lo) >> c;
-    const unsigned long long max_tiles = 1ull << 27;   // <= 2^20 blocks (8 MiB of partials) per launch
-    while (tiles_left) {
-      const unsigned long long nt = tiles_left < max_tiles ? tiles_left : max_tiles;
-      const size_t blocks = (size_t)((nt + SPB_REG_THREADS - 1) / SPB_REG_THREADS);
+    unsigned long long group = body_lo >> (c + 7);
+    unsigned long long groups_left = (body_hi - body_lo) >> (c + 7);
+    // groups per block: aim at ~16 waves of resident blocks, at most 16 groups (2^20 indices at c=9)
+    int gpb = env_int("SP_DENSE_GROUPS_PER_BLOCK", 0);
+    if (gpb <= 0) {
+      const unsigned long long want_blocks = (unsigned long long)L.sm_count * 4ull * 16ull;
+      unsigned long long g = groups_left / want_blocks;
+      gpb = g < 1 ? 1 : (g > 16 ? 16 : (int)g);
+    }
+    const unsigned long long max_groups = (1ull << 20) * (unsigned)gpb;   // <= 2^20 blocks per launch
+    while (groups_left) {
+      const unsigned long long ng = groups_left < max_groups ? groups_left : max_groups;
+      const size_t blocks = (size_t)((ng + (unsigned)gpb - 1) / (unsigned)gpb);
       if (pcount + blocks > (1u << 21)) {   // flush what we have
         rc = launch_reduce(L, L.d_partials, pcount, L.d_result, 0, !first_reduce);
         if (rc != SPD_OK) return rc;
@@ -218,11 +227,11 @@ static int dense_enqueue(spd_dense_plan* p, unsigned long long lo, unsigned long
       rc = lane_reserve_partials(&L, pcount + blocks);
       if (rc != SPD_OK) return rc;
       unsigned nb = 0;
-      rc = reg_launch(n, B, L.stream, p->d_mat_t, p->d_xbase, L.d_partials + pcount, tile, nt, c, &nb);
+      rc = reg_launch(n, B, L.stream, p->d_mat_t, p->d_xbase, L.d_partials + pcount, group, ng, gpb, c, &nb);
       if (rc != SPD_OK) { set_error("no register kernel for n=%d B=%d", n, B); return rc; }
       SPB_CUDA(cudaGetLastError());
       pcount += nb; ++launches;
-      tile += nt; tiles_left -= nt;
+      group += ng; groups_left -= ng;
     }
     rc = enqueue_smem(p, lo, body_lo, &pcount, &launches);
     if (rc != SPD_OK) return rc;

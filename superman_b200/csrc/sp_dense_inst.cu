@@ -13,12 +13,12 @@ namespace spb {
 
 template <int N, int B, int MB>
 static int launch_one(cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
-                      unsigned long long tile_first, unsigned long long n_tiles, int c,
+                      unsigned long long group_first, unsigned long long n_groups, int gpb, int c,
                       unsigned* blocks_out) {
-  const unsigned long long blocks = (n_tiles + SPB_REG_THREADS - 1) / SPB_REG_THREADS;
+  const unsigned long long blocks = (n_groups + (unsigned)gpb - 1) / (unsigned)gpb;
   if (blocks == 0 || blocks > 0x7fffffffull) return SPD_EINVAL;
   ryser_reg_kernel<N, B, SPB_REG_THREADS, MB>
-      <<<(unsigned)blocks, SPB_REG_THREADS, 0, st>>>(mat_t, xbase, partials, tile_first, n_tiles, c);
+      <<<(unsigned)blocks, SPB_REG_THREADS, 0, st>>>(mat_t, xbase, partials, group_first, n_groups, gpb, c);
   *blocks_out = (unsigned)blocks;
   return SPD_OK;
 }
@@ -27,16 +27,16 @@ static int launch_one(cudaStream_t st, const double* mat_t, const double* xbase,
 // registers per thread, 3 blocks 168 (ptxas -v: zero spills for every entry below).
 template <int N, int B>
 static int launch_nb(cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
-                     unsigned long long tile_first, unsigned long long n_tiles, int c,
+                     unsigned long long group_first, unsigned long long n_groups, int gpb, int c,
                      unsigned* blocks_out) {
   constexpr int MB = (B == 4) ? (N <= 36 ? 4 : 3) : (N <= 42 ? 4 : 3);
-  return launch_one<N, B, MB>(st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out);
+  return launch_one<N, B, MB>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out);
 }
 
 #define SPB_CASE(N)                                                                          \
   case N:                                                                                    \
-    if (B == 3) return launch_nb<N, 3>(st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out); \
-    if (B == 4) return launch_nb<N, 4>(st, mat_t, xbase, partials, tile_first, n_tiles, c, blocks_out); \
+    if (B == 3) return launch_nb<N, 3>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out); \
+    if (B == 4) return launch_nb<N, 4>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out); \
     return SPD_ELIMIT;
 
 #define SPB_GLUE2(a, b) a##b
@@ -44,24 +44,24 @@ static int launch_nb(cudaStream_t st, const double* mat_t, const double* xbase, 
 
 extern "C" int SPB_GLUE(spb_reg_launch_g, SPB_GROUP)(
     int n, int B, cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
-    unsigned long long tile_first, unsigned long long n_tiles, int c, unsigned* blocks_out) {
+    unsigned long long group_first, unsigned long long n_groups, int gpb, int c, unsigned* blocks_out) {
   switch (n) {
 #if SPB_GROUP == 0
-    SPB_CASE(8) SPB_CASE(16) SPB_CASE(24) SPB_CASE(32) SPB_CASE(40) SPB_CASE(48)
+    SPB_CASE(16) SPB_CASE(24) SPB_CASE(32) SPB_CASE(40) SPB_CASE(48)
 #elif SPB_GROUP == 1
-    SPB_CASE(9) SPB_CASE(17) SPB_CASE(25) SPB_CASE(33) SPB_CASE(41)
+    SPB_CASE(17) SPB_CASE(25) SPB_CASE(33) SPB_CASE(41)
 #elif SPB_GROUP == 2
-    SPB_CASE(10) SPB_CASE(18) SPB_CASE(26) SPB_CASE(34) SPB_CASE(42)
+    SPB_CASE(18) SPB_CASE(26) SPB_CASE(34) SPB_CASE(42)
 #elif SPB_GROUP == 3
-    SPB_CASE(11) SPB_CASE(19) SPB_CASE(27) SPB_CASE(35) SPB_CASE(43)
+    SPB_CASE(19) SPB_CASE(27) SPB_CASE(35) SPB_CASE(43)
 #elif SPB_GROUP == 4
-    SPB_CASE(12) SPB_CASE(20) SPB_CASE(28) SPB_CASE(36) SPB_CASE(44)
+    SPB_CASE(20) SPB_CASE(28) SPB_CASE(36) SPB_CASE(44)
 #elif SPB_GROUP == 5
     SPB_CASE(13) SPB_CASE(21) SPB_CASE(29) SPB_CASE(37) SPB_CASE(45)
 #elif SPB_GROUP == 6
     SPB_CASE(14) SPB_CASE(22) SPB_CASE(30) SPB_CASE(38) SPB_CASE(46)
 #elif SPB_GROUP == 7
-    SPB_CASE(7) SPB_CASE(15) SPB_CASE(23) SPB_CASE(31) SPB_CASE(39) SPB_CASE(47)
+    SPB_CASE(15) SPB_CASE(23) SPB_CASE(31) SPB_CASE(39) SPB_CASE(47)
 #endif
     default:
       return SPD_ELIMIT;

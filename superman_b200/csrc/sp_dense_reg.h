@@ -4,14 +4,15 @@
 
 #define SPB_REG_THREADS 128
 #define SPB_NGROUPS 8
-#define SPB_REG_NMIN 7
+#define SPB_REG_NMIN 13
 #define SPB_REG_NMAX 48
+#define SPB_SPARSE_NMIN 7
 
 extern "C" {
 #define SPB_DECL(g)                                                                               \
   int spb_reg_launch_g##g(int n, int B, cudaStream_t st, const double* mat_t, const double* xbase, \
-                          double* partials, unsigned long long tile_first,                        \
-                          unsigned long long n_tiles, int c, unsigned* blocks_out);
+                          double* partials, unsigned long long group_first,                       \
+                          unsigned long long n_groups, int gpb, int c, unsigned* blocks_out);
 SPB_DECL(0) SPB_DECL(1) SPB_DECL(2) SPB_DECL(3) SPB_DECL(4) SPB_DECL(5) SPB_DECL(6) SPB_DECL(7)
 #undef SPB_DECL
 }

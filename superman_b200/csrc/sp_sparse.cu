@@ -70,7 +70,7 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
   unsigned long long smem_indices = len;   // indices evaluated by the dense-semantics ragged kernel
   bool have_visited = false;
 
-  const bool reg_ok = (n >= SPB_REG_NMIN && n <= SPB_REG_NMAX && env_int("SP_SPARSE_FORCE_SMEM", 0) == 0);
+  const bool reg_ok = (n >= SPB_SPARSE_NMIN && n <= SPB_REG_NMAX && env_int("SP_SPARSE_FORCE_SMEM", 0) == 0);
   int rc;
   unsigned long long body_lo = lo, body_hi = lo;
   int c = 0, B = 3;

@@ -121,12 +121,12 @@ double sp_dense_ryser(const double *mat, int nov, int algo_id, int gpu_num, int 
   nw_preamble(mat, nov, x, mat_t);
   dense_job job = {mat_t, x, nov};
   const unsigned long long end = 1ull << (nov - 1);
-  /* never more devices than 2^14-index tiles */
-  while (gpu_num > 1 && (end >> 14) < (unsigned long long)gpu_num) gpu_num--;
+  /* never more devices than 2^16-index tile groups (the kernel's alignment unit) */
+  while (gpu_num > 1 && (end >> 16) < (unsigned long long)gpu_num) gpu_num--;
   const unsigned long long chunks = (mode == SP_SCHED_DYNAMIC) ? sp_dynamic_chunks(nov, 29, gpu_num) : 0;
   double sum = 0.0;
   /* index 0 (the base term p = prod x, gpu_exact_dense.cu:653) is part of device 0's range */
-  int rc = sp_sched_run(&g_dense_ops, &job, mode, gpu_num, 0, 0ull, end, 14, chunks, &sum, stats);
+  int rc = sp_sched_run(&g_dense_ops, &job, mode, gpu_num, 0, 0ull, end, 16, chunks, &sum, stats);
   free(mat_t);
   if (stats) stats->wall_ms = sp_now_ms() - t0;
   if (rc != SP_OK) return fail(stats, rc);

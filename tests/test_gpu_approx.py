@@ -1,0 +1,127 @@
+"""GPU tests of the Rasmussen / scaling estimators: every trial bit-equal to the oracle's
+restatement (same Philox stream), means inside the confidence interval of the exact value."""
+import math
+
+import numpy as np
+import pytest
+
+import _golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid(sp, m, n):
+    return sp.Matrix.grid(m, n)
+
+
+@pytest.mark.parametrize("dims", [(2, 2), (4, 4), (3, 4), (6, 6), (5, 8), (8, 8)])
+def test_trials_bitwise_equal_to_oracle(sp, oracle, dims):
+    g = _grid(sp, *dims)
+    seed = 1234567
+    got = sp.approx_trials_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, scaling=False, seed=seed, first=5, count=40)
+    for i, v in enumerate(got):
+        assert v == oracle.rasmussen_trial(g.rptrs, g.cols, g.nov, seed, 5 + i)
+    got = sp.approx_trials_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, scaling=True, scale_intervals=4,
+                                  scale_times=5, seed=seed, first=0, count=40)
+    for i, v in enumerate(got):
+        assert v == oracle.scaling_trial(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, 4, 5, seed, i)
+    got = sp.approx_trials_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, scaling=True, scale_intervals=1,
+                                  scale_times=2, seed=seed, first=100, count=10)
+    for i, v in enumerate(got):
+        assert v == oracle.scaling_trial(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, 1, 2, seed, 100 + i)
+
+
+def test_random_sparse_patterns_bitwise(sp, oracle):
+    rng = np.random.default_rng(9)
+    for n in (9, 33, 70):
+        pat = rng.random((n, n)) < min(0.5, 6.0 / n)
+        pat[np.arange(n), rng.permutation(n)] = True
+        m = sp.Matrix.from_dense(pat.astype(float)).compress(0)
+        r = sp.approx_trials_sparse(m.rptrs, m.cols, m.cptrs, m.rows, n, m.nnz, scaling=False, seed=5, first=0, count=24)
+        s = sp.approx_trials_sparse(m.rptrs, m.cols, m.cptrs, m.rows, n, m.nnz, scaling=True, seed=5, first=0, count=24)
+        for t in range(24):
+            assert r[t] == oracle.rasmussen_trial(m.rptrs, m.cols, n, 5, t)
+            assert s[t] == oracle.scaling_trial(m.rptrs, m.cols, m.cptrs, m.rows, n, 4, 5, 5, t)
+
+
+def test_mean_is_sum_of_trials_and_split_invariant(sp, oracle):
+    g = _grid(sp, 6, 6)
+    N = 3000
+    st = sp._ffi.SpStats()
+    mean = sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, N, 1, seed=42, stats=st)
+    assert st.units == N
+    ref = sum(oracle.rasmussen_trial(g.rptrs, g.cols, g.nov, 42, t) for t in range(N)) / N
+    assert mean == pytest.approx(ref, rel=1e-12)          # same trials, different summation order
+    assert st.std_error > 0 and abs(mean - 6728.0) < 6 * st.std_error
+    again = sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, N, 1, seed=42)
+    assert again == mean                                  # reproducible
+    other = sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, N, 1, seed=43)
+    assert other != mean
+
+
+@pytest.mark.parametrize("dims,exact", [((4, 4), 36.0), ((6, 6), 6728.0), ((8, 8), 12988816.0)])
+def test_confidence_interval(sp, dims, exact):
+    g = _grid(sp, *dims)
+    for scaled in (False, True):
+        st = sp._ffi.SpStats()
+        if scaled:
+            v = sp.scaling_sparse(g.cptrs, g.rows, g.rptrs, g.cols, g.nov, g.nnz, 40000, 4, 5, 1, seed=7, stats=st)
+        else:
+            v = sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, 40000, 1, seed=7, stats=st)
+        assert st.units == 40000 and st.std_error > 0
+        assert abs(v - exact) < 5 * st.std_error, (dims, scaled, v, st.std_error)
+        assert st.std_error < 0.2 * exact
+
+
+def test_config5_grid_36x36(sp, oracle):
+    """BASELINE.json configs[4]: -a -i -m36 -n36 -x100000 -y4 -z5 ; exact value by Kasteleyn"""
+    g = _grid(sp, 36, 36)
+    assert (g.nov, g.nnz) == (648, 2520)
+    exact = oracle.kasteleyn(36, 36)
+    st = sp._ffi.SpStats()
+    v = sp.scaling_sparse(g.cptrs, g.rows, g.rptrs, g.cols, g.nov, g.nnz, 100000, 4, 5, 1, seed=0, stats=st)
+    # On a 648-row pattern almost every trial of either estimator runs into an empty row (the
+    # oracle's restatement of the reference kernels does the same: 0 survivors in 200 trials), so
+    # 10^5 trials typically return 0 and a survivor carries ~1e159/p_survive: the estimator is
+    # unbiased but far too heavy-tailed for a CI at this size ("hard parts").  What can
+    # be asserted at full size: the trial count, finiteness, per-trial parity with the oracle, and
+    # that any non-zero mean is not below the exact value's order of magnitude.
+    assert st.units == 100000 and math.isfinite(v) and v >= 0
+    if v > 0:
+        assert math.log10(v) > math.log10(exact) - 6
+    r = sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, 100000, 1, seed=0, stats=st)
+    assert math.isfinite(r) and r >= 0
+    # per-trial parity on the full-size pattern
+    got = sp.approx_trials_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, scaling=True, seed=3, first=0, count=3)
+    for t in range(3):
+        assert got[t] == oracle.scaling_trial(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, 4, 5, 3, t)
+    got = sp.approx_trials_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, scaling=False, seed=3, first=0, count=6)
+    for t in range(6):
+        assert got[t] == oracle.rasmussen_trial(g.rptrs, g.cols, g.nov, 3, t)
+
+
+def test_dense_twins(sp, oracle):
+    rng = np.random.default_rng(15)
+    n = 12
+    pat = rng.random((n, n)) < 0.6
+    pat[np.arange(n), np.arange(n)] = True
+    B = pat.astype(float)
+    exact = oracle.perm_ld(B)
+    st = sp._ffi.SpStats()
+    v = sp.rasmussen_dense(B, n, 60000, 1, seed=1, stats=st)
+    assert abs(v - exact) < 5 * st.std_error
+    v = sp.scaling_dense(B, n, 60000, 4, 5, 1, seed=1, stats=st)
+    assert abs(v - exact) < 5 * st.std_error
+    # reference-named wrappers
+    assert sp.gpu_perman64_rasmussen(B, n, 1000, seed=2) == sp.rasmussen_dense(B, n, 1000, 1, seed=2)
+    assert sp.gpu_perman64_approximation(B, n, 1000, 4, 5, seed=2) == sp.scaling_dense(B, n, 1000, 4, 5, 1, seed=2)
+
+
+def test_dead_ends_and_errors(sp):
+    # a pattern with an empty row: every trial is 0
+    pat = np.ones((5, 5)); pat[2, :] = 0
+    m = sp.Matrix.from_dense(pat).compress(0)
+    assert sp.rasmussen_sparse(m.rptrs, m.cols, m.cptrs, m.rows, 5, m.nnz, 500, 1, seed=1) == 0.0
+    assert sp.scaling_sparse(m.cptrs, m.rows, m.rptrs, m.cols, 5, m.nnz, 500, 4, 5, 1, seed=1) == 0.0
+    with pytest.raises(sp.SupermanError):
+        sp.rasmussen_sparse(m.rptrs, m.cols, m.cptrs, m.rows, 5, m.nnz, 0, 1)

@@ -1,0 +1,110 @@
+"""GPU: the `perman` executable end to end -- flags, id dispatch, output lines (main.cu)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "superman_b200", "perman")
+
+
+def run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([EXE, *args], capture_output=True, text=True, env=e, timeout=600)
+    return r
+
+
+def result_of(out, key="Result17"):
+    m = re.search(r"^%s: (\S+) (\S+)" % key, out, flags=re.M)
+    assert m, out
+    return m.group(1), float(m.group(2))
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mats")
+    out = []
+    for idx, e in enumerate(_golden.small()):
+        p = d / ("m%d.txt" % idx)
+        _golden.write_matrix_file(e, p)
+        out.append((str(p), e))
+    return out
+
+
+def test_dense_ids_and_result_line(files):
+    path, e = files[7]          # n = 18 int
+    names = {0: "gpu_perman64_xlocal", 1: "gpu_perman64_xlocal", 2: "gpu_perman64_xshared",
+             3: "gpu_perman64_xshared_coalescing", 4: "gpu_perman64_xshared_coalescing_mshared",
+             5: "gpu_perman64_xshared_coalescing_mshared_multigpu",
+             6: "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks"}
+    for algo, name in names.items():
+        r = run("-f", path, "-p", str(algo), "-d", "1", env={"PERMAN_PRECISION": "17"})
+        assert r.returncode == 0, r.stderr
+        # Result: <name> <6 significant digits> in <seconds>   (main.cu:58)
+        m = re.search(r"^Result: (\S+) (\S+) in (\S+)$", r.stdout, flags=re.M)
+        assert m and m.group(1) == name
+        assert m.group(2) == "%g" % e["ld"]
+        assert "kernel" in r.stdout
+        assert result_of(r.stdout)[1] == pytest.approx(e["ld"], rel=1e-9)
+    r = run("-f", path, "-p", "9")
+    assert r.returncode == 0 and "Unknown Algorithm ID" in r.stdout     # main.cu:75
+    r = run("-f", path, "-g", "-c", "-p", "4", env={"PERMAN_PRECISION": "17"})   # -c with -g is accepted (main.cu:66)
+    assert result_of(r.stdout)[1] == pytest.approx(e["ld"], rel=1e-9)
+    r = run("-f", path, "extra_arg", "-p", "4")
+    assert "Non-option argument extra_arg" in r.stdout                  # main.cu:477-480
+
+
+def test_default_algo_and_binary_flag(files):
+    path, e = files[3]          # n = 12 int
+    r = run("--file", path, env={"PERMAN_PRECISION": "17"})             # defaults: -p1, GPU (main.cu:335,482)
+    name, v = result_of(r.stdout)
+    assert name == "gpu_perman64_xlocal" and v == pytest.approx(e["ld"], rel=1e-9)
+    r = run("-f", path, "-b", "-p", "4", env={"PERMAN_PRECISION": "17"})
+    assert round(result_of(r.stdout)[1]) == int(e["i128_binary"])
+
+
+def test_sparse_ids_with_preprocessing(files):
+    for path, e in files[5:9]:
+        for pre in ("0", "1", "2"):
+            for algo, name in ((4, "gpu_perman64_xshared_coalescing_mshared_sparse"),
+                               (6, "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_sparse"),
+                               (7, "gpu_perman64_xshared_coalescing_mshared_skipper"),
+                               (8, "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks_skipper")):
+                r = run("-f", path, "-s", "-r", pre, "-p", str(algo), "-d", "1", env={"PERMAN_PRECISION": "17"})
+                assert r.returncode == 0, r.stderr
+                got_name, v = result_of(r.stdout)
+                assert got_name == name
+                assert v == pytest.approx(e["ld"], rel=1e-9), (path, pre, algo)
+
+
+def test_grid_approximations():
+    for algo, name in ((1, "gpu_perman64_rasmussen_sparse"), (2, "gpu_perman64_approximation_sparse"),
+                       (3, "gpu_perman64_rasmussen_multigpucpu_chunks"),
+                       (4, "gpu_perman64_approximation_multigpucpu_chunks_sparse")):
+        r = run("-a", "-i", "-m", "6", "-n", "6", "-x", "20000", "-y", "4", "-z", "5", "-p", str(algo), "-d", "1",
+                env={"PERMAN_PRECISION": "17"})
+        assert r.returncode == 0, r.stderr
+        assert re.search(r"^Result: %s \S+ in \S+$" % name, r.stdout, flags=re.M)
+        assert re.search(r"^Try: \S+ \S+ in \S+$", r.stdout, flags=re.M)      # main.cu:267
+        assert "------------GRID--------------" in r.stdout                   # main.cu:309
+        v = result_of(r.stdout)[1]
+        se = float(re.search(r"^StdError: \S+ (\S+)", r.stdout, flags=re.M).group(1))
+        assert abs(v - 6728.0) < 6 * se
+    r = run("-a", "-i", "-m", "3", "-n", "5", "-p", "1")
+    assert "one of the grid dimensions should be positive." in r.stdout       # main.cu:405 (sic)
+
+
+def test_dense_approximation_on_file(files):
+    path, e = files[3]
+    for algo, name in ((1, "gpu_perman64_rasmussen"), (2, "gpu_perman64_approximation")):
+        r = run("-f", path, "-b", "-a", "-p", str(algo), "-x", "50000", env={"PERMAN_PRECISION": "17"})
+        assert r.returncode == 0, r.stderr
+        got_name, v = result_of(r.stdout)
+        assert got_name == name
+        assert v == pytest.approx(float(e["i128_binary"]), rel=0.25)

@@ -89,7 +89,7 @@ def test_scheduler_partition(sp):
         sl = [bench.rank_slice(1 << 35, r, world) for r in range(world)]
         assert sl[0][0] == 0 and sl[-1][1] == 1 << 35
         assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
-        assert [s[0] for s in sl] == [f(0, 1 << 35, world, r, 14) for r in range(world)]
+        assert [s[0] for s in sl] == [f(0, 1 << 35, world, r, bench.ALIGN_LOG2) for r in range(world)]
     g = _ffi.lib.sp_dynamic_chunks
     g.restype = C.c_ulonglong
     g.argtypes = [C.c_int, C.c_int, C.c_int]
