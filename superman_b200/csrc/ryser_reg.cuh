@@ -84,11 +84,12 @@ ryser_reg_kernel(const double* __restrict__ mat_t,   // mat_t[k*N + j] = A[j][k]
   __shared__ __align__(16) double sm[L::TOTAL];
   __shared__ __align__(16) double x_blk[NP];
   __shared__ double warp_part[THREADS / 32];
-  for (int e = threadIdx.x; e < N * N; e += THREADS) {
-    const int k = e / N, j = e % N;
-    const double v = mat_t[e];
-    sm[L::COLT + k * NP + j] = v;
-    if (k < B) sm[L::LOWR + j * LB + k] = v;
+  // staging: consecutive threads write consecutive shared-memory words in both images (no bank
+  // conflicts); the low-column image is gathered from global memory instead
+  for (int e = threadIdx.x; e < N * N; e += THREADS) sm[L::COLT + (e / N) * NP + (e % N)] = mat_t[e];
+  for (int e = threadIdx.x; e < N * LB; e += THREADS) {
+    const int j = e / LB, k = e % LB;
+    sm[L::LOWR + e] = (k < B) ? mat_t[k * N + j] : 0.0;
   }
   const uint32_t sm_colT = (uint32_t)__cvta_generic_to_shared(sm + L::COLT);
   const uint32_t sm_lowR = (uint32_t)__cvta_generic_to_shared(sm + L::LOWR);
@@ -125,16 +126,17 @@ ryser_reg_kernel(const double* __restrict__ mat_t,   // mat_t[k*N + j] = A[j][k]
       for (int j = 0; j < N; ++j) x[j] = fma(f, col[j], x[j]);
     }
 
-    double tile_acc = 0.0;
     const int nblk = 1 << (c - B);
-    unsigned long long i0 = s;
+    const int tile_odd = threadIdx.x & 1;        // bit c of the tile's first index (tile0 is even)
 #pragma unroll 1
-    for (int blk = 0; blk < nblk; ++blk, i0 += (unsigned long long)NB) {
-      // high column flipped at the block start: k = ctz(i0) = B + ctz(blk), same for all threads.
-      // Gray bit k after the flip is 1 ^ bit(k+1) of i0 -> add (+1) when that bit is clear.
+    for (int blk = 0; blk < nblk; ++blk) {
+      // high column flipped at the block start i0 = s + blk*2^B: k = ctz(i0) = B + ctz(blk), the
+      // same for all threads.  Gray bit k after the flip is 1 ^ bit(k+1) of i0 -> add (+1) when
+      // that bit is clear; bit k+1 of i0 is a bit of blk, or the tile's parity when k+1 == c.
       // blk == 0 is the tile start, where X is already explicit: weight 0 leaves it unchanged.
       const int k = (blk != 0) ? (B + __ffs(blk) - 1) : B;
-      const double sg = (blk != 0) ? (((i0 >> (k + 1)) & 1ull) ? -1.0 : 1.0) : 0.0;
+      const int up = (k + 1 < c) ? ((blk >> (k + 1 - B)) & 1) : tile_odd;
+      const double sg = (blk != 0) ? (up ? -1.0 : 1.0) : 0.0;
       // column B-1 flips in the middle of the block; its direction is bit B of i0
       const double sg_top = (blk & 1) ? -1.0 : 1.0;
       const uint32_t hi_addr = sm_colT + (uint32_t)(k * NP * 8);
@@ -167,9 +169,8 @@ ryser_reg_kernel(const double* __restrict__ mat_t,   // mat_t[k*N + j] = A[j][k]
       double blk_sum = 0.0;
 #pragma unroll
       for (int u = 0; u < NB; u += 2) blk_sum += (P[u] - P[u + 1]);
-      tile_acc += blk_sum;
+      acc += blk_sum;
     }
-    acc += tile_acc;
   }
 
   acc = warp_sum(acc);

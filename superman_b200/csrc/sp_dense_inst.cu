@@ -29,7 +29,8 @@ template <int N, int B>
 static int launch_nb(cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
                      unsigned long long group_first, unsigned long long n_groups, int gpb, int c,
                      unsigned* blocks_out) {
-  constexpr int MB = (B == 4) ? (N <= 36 ? 4 : 3) : (N <= 42 ? 4 : 3);
+  // from the ptxas -v survey of every (N, B, MB): the largest occupancy with zero spill bytes
+  constexpr int MB = (B == 4) ? ((N <= 39 && N != 33) ? 4 : 3) : (N <= 43 ? 4 : 3);
   return launch_one<N, B, MB>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out);
 }
 

@@ -49,11 +49,12 @@ sparse_reg_kernel(const SparseArgs a) {
   __shared__ double warp_part[WARPS];
   __shared__ unsigned long long warp_vis[WARPS];
   __shared__ unsigned long long queue[WARPS][64];
-  for (int e = threadIdx.x; e < N * N; e += THREADS) {
-    const int k = e / N, j = e % N;
-    const double v = a.mat_t[e];
-    sm[L::COLT + k * NP + j] = v;
-    if (k < B) sm[L::LOWR + j * LB + k] = v;
+  // staging: consecutive threads write consecutive shared-memory words in both images (no bank
+  // conflicts); the low-column image is gathered from global memory instead
+  for (int e = threadIdx.x; e < N * N; e += THREADS) sm[L::COLT + (e / N) * NP + (e % N)] = a.mat_t[e];
+  for (int e = threadIdx.x; e < N * LB; e += THREADS) {
+    const int j = e / LB, k = e % LB;
+    sm[L::LOWR + e] = (k < B) ? a.mat_t[k * N + j] : 0.0;
   }
   __syncthreads();
   const uint32_t sm_colT = (uint32_t)__cvta_generic_to_shared(sm + L::COLT);
