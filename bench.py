@@ -231,8 +231,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # rank 0 must print exactly one line: keep NCCL's version banner off stdout
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL prints it at VERSION level and above, i.e. also at WARN)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     import superman_b200 as sp
