@@ -185,6 +185,16 @@ double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptr
                               unsigned long long seed, long long trial, int count, double *values,
                               sp_stats *stats);
 
+/* ---------------------------------------------------------------------------------------------
+ * The reference's Python / MATLAB shim on the GPU engine (interface_connector.c:61-231,
+ * matlab_calculate_return.h:4,12,20): same names and arguments; see superman_b200/host/sp_connector.c
+ * for the algorithm numbering and the two defects fixed.  `connect()` is exported as sp_connect().
+ * ------------------------------------------------------------------------------------------- */
+void   sp_connect(void);
+double read_calculate_return(char *filename, int algorithm, int nt, int x, int y, int z);
+double matlab_calculate_return_int(int *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz);
+double matlab_calculate_return_double(double *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz);
+
 /* (4*(nov&1)-2): the factor every wrapper applies to base + sum (gpu_exact_dense.cu:698). */
 double sp_nw_factor(int nov);
 

@@ -20,6 +20,7 @@ def test_cabi_exports_every_declared_symbol(sp):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(spd?_[a-z0-9_]+)\s*\(", text))
+        names |= set(re.findall(r"\b(read_calculate_return|matlab_calculate_return_[a-z]+)\s*\(", text))
     assert len(names) > 40
     missing = [n for n in sorted(names) if not hasattr(_ffi.lib, n)]
     assert not missing, missing

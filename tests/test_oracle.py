@@ -89,8 +89,12 @@ def test_golden_corpus_values(oracle):
         for key in ("ref_skipper_sort", "ref_skipper_skip"):           # all-double paths (algo.h:885)
             assert e[key] == pytest.approx(e["ld"], rel=2e-8), (name, key)
         for key in ("ref_sparse_sort", "ref_sparse_skip"):             # float X (algo.h:570)
-            tol = 1e-9 if name.startswith("int/") else 0.5
-            assert e[key] == pytest.approx(e["ld"], rel=tol), (name, key)
+            # exact on integer files; on double/ files the float X makes the reference's own result
+            # meaningless (78 % off on double/32_0.50_0): recorded, never asserted against
+            if name.startswith("int/"):
+                assert e[key] == pytest.approx(e["ld"], rel=1e-9), (name, key)
+            else:
+                assert math.isfinite(e[key]), (name, key)
         if name.startswith("int/"):
             # float X is exact for small-integer matrices: parallel_perman64 agrees there ...
             assert e["ref_parallel_perman64_float_x"] == pytest.approx(e["ld"], rel=1e-9), name
