@@ -329,7 +329,10 @@ def main():
     achieved = per_launch_units * (2 * n + 1) / per_launch_s
     roofline = {
         "bound": "fp64_issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s (thread-level FP64)",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one ryser_reg_kernel<36,4,128,4> launch over 2^35
+        # indices (ncu --set full, profiles/r01_ncu_dense.txt): 87 296 B read + 0 B written
+        "traffic": 87296 if (n == 36 and world == 1) else None,
         "algorithmic": f"{2 * n + 1} FP64 instr per Gray index x {per_launch_units} indices per launch (SURVEY 8(d)); "
                        f"executed count is {2 * n} (the 1.0*x0 multiply is elided)",
         "peak_source": "measured in this run: spd_fp64_peak_instr_per_s (8 independent DFMA chains/thread, best of 3); "

@@ -117,7 +117,8 @@ approx_kernel(const ApproxArgs a) {
     for (int step = 0; step < nov && !dead; ++step) {
       if ((step & 3) == 0)
         philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)(step >> 2), 0u, k0, k1, rnd);
-      const uint32_t draw = rnd[step & 3];
+      const int rw = step & 3;   // select, not index: keeps the four words in registers
+      const uint32_t draw = (rw == 0) ? rnd[0] : (rw == 1) ? rnd[1] : (rw == 2) ? rnd[2] : rnd[3];
       // ---- minimum-degree remaining row, first in ascending order ----
       unsigned best = 0xffffffffu;
       for (int r = lane; r < nov; r += 32)

@@ -128,21 +128,33 @@ sparse_reg_kernel(const SparseArgs a) {
       // Rows are handled in groups of G: one uniform branch per group instead of one per row, so
       // the G rows of a group are straight-line code whose chains interleave.  Hg = H rounded up
       // to a whole group (a cold row treated as hot just adds zeros).
-      // cold groups: one update, one multiply per row and block
-      double q0 = 1.0, q1 = 1.0;
-#pragma unroll
-      for (int j0 = 0; j0 < N; j0 += G) {
-        if (j0 >= Hg) {
-#pragma unroll
-          for (int j = j0; j < j0 + G && j < N; ++j) {
-            double d;
-            lds_f64(hi_addr + (uint32_t)(j * 8), d);
-            x[j] = fma(sg, d, x[j]);
-            if (j & 1) q1 *= x[j]; else q0 *= x[j];
-          }
-        }
+      // cold groups: one update, one multiply per row and block.  The cold rows are the contiguous
+      // range [Hg, N): a single uniform jump into an unrolled sequence (switch with fall-through)
+      // gives the scheduler ONE basic block for all of them, so the independent updates and the
+      // four product chains overlap instead of waiting on each other group by group.
+      double q0 = 1.0, q1 = 1.0, q2 = 1.0, q3 = 1.0;
+#define SPB_COLD_GROUP(gidx)                                                   \
+  case gidx:                                                                   \
+    if constexpr (G * (gidx) < N) {                                            \
+      _Pragma("unroll") for (int j = G * (gidx); j < G * (gidx) + G && j < N; ++j) { \
+        double d;                                                              \
+        lds_f64(hi_addr + (uint32_t)(j * 8), d);                               \
+        x[j] = fma(sg, d, x[j]);                                               \
+        if ((j & 3) == 0) q0 *= x[j];                                          \
+        else if ((j & 3) == 1) q1 *= x[j];                                     \
+        else if ((j & 3) == 2) q2 *= x[j];                                     \
+        else q3 *= x[j];                                                       \
+      }                                                                        \
+    }                                                                          \
+    [[fallthrough]];
+      switch (Hg / G) {
+        SPB_COLD_GROUP(0) SPB_COLD_GROUP(1) SPB_COLD_GROUP(2) SPB_COLD_GROUP(3)
+        SPB_COLD_GROUP(4) SPB_COLD_GROUP(5) SPB_COLD_GROUP(6) SPB_COLD_GROUP(7)
+        SPB_COLD_GROUP(8) SPB_COLD_GROUP(9) SPB_COLD_GROUP(10) SPB_COLD_GROUP(11)
+        default: break;
       }
-      const double Q = q0 * q1;
+#undef SPB_COLD_GROUP
+      const double Q = (q0 * q1) * (q2 * q3);
       const bool skip_blk = SKIP && __all_sync(0xffffffffu, !active || Q == 0.0);
       if (skip_blk) {
         // whole warp: the block contributes exact zeros; apply its net effect on the hot rows
