@@ -193,7 +193,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "gray_code_iterations_per_second", "value": value, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dense Ryser n={N_DENSE} density {DENSITY} FP64 (seeded synthetic, seed {1000 * N_DENSE})",
+        "config": {"workload": f"dense Ryser n={N_DENSE} density {DENSITY} FP64, one full permanent (2^{N_DENSE - 1} Gray indices) per step, "
+                               f"seeded synthetic matrix (seed {1000 * N_DENSE}); BASELINE.json configs[3]",
                    "sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

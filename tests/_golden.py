@@ -47,3 +47,7 @@ def corpus():
     out = dict(_load("corpus.json") or {})
     out.update(_load("corpus_big.json") or {})
     return out
+
+
+def real():
+    return _load("real.json") or {}

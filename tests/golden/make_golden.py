@@ -106,7 +106,25 @@ def grids():
     return out
 
 
+def real():
+    """the reference's real/ matrices that are small enough for the exact paths: inputs, and the
+    long-double permanent where it finishes in minutes (ibm32, n = 32)"""
+    out = {}
+    for name, want_ld in (("real/ibm32.mtxzero", True), ("real/cage5_c2.mtxzero", False)):
+        A, hdr_nnz, typ = R.read_matrix(os.path.join(REF, name))
+        e = {"n": int(A.shape[0]), "type": typ, "header_nnz": hdr_nnz, "triples": triples(A, typ)}
+        e["ld"] = O.perm_ld(A) if want_ld else None
+        for pre, key in ((1, "sort"), (2, "skip")):
+            e["colcount_" + key] = np.diff(R.compress(A, pre)["cptrs"]).tolist()
+        out[name] = e
+        print(name, e["n"], e["ld"], flush=True)
+    return out
+
+
 if __name__ == "__main__":
+    if "--real" in sys.argv:
+        json.dump(real(), open(os.path.join(HERE, "real.json"), "w"))
+        sys.exit(0)
     json.dump(small(), open(os.path.join(HERE, "small.json"), "w"))
     json.dump(grids(), open(os.path.join(HERE, "grid.json"), "w"))
     json.dump(corpus(), open(os.path.join(HERE, "corpus_big.json" if BIG else "corpus.json"), "w"))
