@@ -16,7 +16,7 @@ CLI     := $(PKG)/perman
 
 GROUPS  := 0 1 2 3 4 5 6 7
 CU_SRCS := sp_device sp_dense sp_sparse sp_approx
-CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o) $(GROUPS:%=$(BUILD)/sp_sparse_inst_g%.o)
+CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(BUILD)/sp_level_inst_b3s0.o $(BUILD)/sp_level_inst_b3s1.o $(BUILD)/sp_level_inst_b4s0.o $(BUILD)/sp_level_inst_b4s1.o $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o) $(GROUPS:%=$(BUILD)/sp_sparse_inst_g%.o)
 C_SRCS  := sp_sched sp_api sp_matrix sp_connector
 C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
 
@@ -31,6 +31,10 @@ $(BUILD)/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h incl
 # the estimators are compared bit for bit with the C oracle: no FMA contraction in this unit
 $(BUILD)/sp_approx.o: $(PKG)/csrc/sp_approx.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+
+$(BUILD)/sp_level_inst_b3s0.o $(BUILD)/sp_level_inst_b3s1.o $(BUILD)/sp_level_inst_b4s0.o $(BUILD)/sp_level_inst_b4s1.o: \
+$(BUILD)/sp_level_inst_b%.o: $(PKG)/csrc/sp_level_inst.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DSPB_LV_B=$(word 1,$(subst s, ,$*)) -DSPB_LV_SKIP=$(word 2,$(subst s, ,$*)) -c $< -o $@
 
 $(BUILD)/sp_dense_inst_g%.o: $(PKG)/csrc/sp_dense_inst.cu $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DSPB_GROUP=$* -c $< -o $@

@@ -1,0 +1,267 @@
+// LevelRyser: SpaRyser / SkipPer kernel for sparse matrices, sm_100a.
+//
+// Same tile / block decomposition as ryser_reg.cuh (a thread owns a tile of 2^c Gray indices and
+// walks it in aligned blocks of 2^B), but the work per index follows the STRUCTURE of the matrix:
+// a row whose lowest non-zero column is L ("level" L) can only change when a column >= L flips.
+//
+//   hot rows (level < B): X in registers, in B*S fixed slots, S per level (the host packs the rows
+//     into slots; free slots hold the neutral row x = 1, entries 0).  A level-L slot takes only
+//     2^(B-L) distinct values inside a block, so it costs 2^(B-L) updates and multiplies into its
+//     level's 2^(B-L) running products PL[L][.] instead of 2^B of each; the 2^B terms of a block are
+//     recombined as  term_u = PL[0][u] * PL[1][u>>1] * ... * PL[B-1][u>>(B-1)] * Q.
+//     Everything here is compile-time structured: straight-line code, no runtime branch.
+//   cold rows (level >= B): X in shared memory (X[row][thread], conflict-free), sorted by level.
+//     Their product Q is kept as suffix products SP[i] = prod(rows of level >= B+i): the block that
+//     flips high column k only touches the rows of level <= k, refreshes SP[k-B .. 0] and reuses
+//     SP[k-B+1].  Half of the blocks flip column B, a quarter column B+1, ...: the expected number
+//     of cold rows touched per block is small.
+//
+// SkipPer (SKIP = true): terms with a zero cold row are exact zeros (Q == 0).  Tiles whose
+// tile-constant rows (level >= c) contain a zero are dropped by a warp-wide filter (ballot +
+// shared-memory queue compaction, full warps only); blocks with Q == 0 in every lane skip the hot
+// work (__all_sync) and apply only its net effect.  All control flow is warp-uniform.
+//
+// Replaces kernel_xshared_coalescing_mshared_sparse / _skipper (gpu_exact_sparse.cu:455-670).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ryser_reg.cuh"
+
+namespace spb {
+
+struct LevelArgs {
+  // packed device image (doubles unless noted), see sp_sparse.cu: level_pack()
+  const double* colT_hot;    // [(n-1) * HSP]   colT_hot[k*HSP + s]  = D[slot s][k]
+  const double* lowR;        // [HS * LB]       lowR[s*LB + q]       = D[slot s][q], q < B
+  const double* dcold;       // [(n-1) * NCP]   dcold[k*NCP + jc]    = D[cold row jc][k]
+  const double* xb_hot;      // [HS]
+  const double* xb_cold;     // [NC]
+  const int* cold_start;     // [n - B + 2]     first cold row of level >= B+i
+  double* partials;
+  unsigned long long* visited;
+  unsigned long long tile_first, n_tiles;
+  int n, NC, NCP, HSP;
+  int c;
+  int tiles_per_warp;
+};
+
+template <int B, int S>
+struct LevelLayout {
+  static constexpr int HS = B * S;
+  static constexpr int HSP = HS + (HS & 1);
+  static constexpr int LB = B + (B & 1);
+};
+
+// dynamic shared memory (doubles):  colT_hot | lowR | dcold | xb_hot | xb_cold | Xc[NC][T] | SP[c-B+1][T]
+// then ints: cold_start
+template <int B, int S, int THREADS, int MINBLOCKS, bool SKIP>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+level_reg_kernel(const LevelArgs a) {
+  using LL = LevelLayout<B, S>;
+  constexpr int HS = LL::HS, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
+  extern __shared__ __align__(16) double dsm[];
+  const int n = a.n, NC = a.NC, NCP = a.NCP, c = a.c;
+  const int nseg = c - B;                       // SP[0 .. nseg]
+  double* s_colT = dsm;
+  double* s_lowR = s_colT + (size_t)(n - 1) * HSP;
+  double* s_dcold = s_lowR + HS * LB;
+  double* s_xbh = s_dcold + (size_t)(n - 1) * NCP;
+  double* s_xbc = s_xbh + HSP;
+  double* s_X = s_xbc + NCP;                    // [NC][THREADS]
+  double* s_SP = s_X + (size_t)NC * THREADS;    // [nseg + 1][THREADS]
+  int* s_cs = reinterpret_cast<int*>(s_SP + (size_t)(nseg + 1) * THREADS);
+  __shared__ double warp_part[WARPS];
+  __shared__ unsigned long long warp_vis[WARPS];
+  __shared__ unsigned long long queue[WARPS][64];
+
+  for (int e = threadIdx.x; e < (n - 1) * HSP; e += THREADS) s_colT[e] = a.colT_hot[e];
+  for (int e = threadIdx.x; e < HS * LB; e += THREADS) s_lowR[e] = a.lowR[e];
+  for (int e = threadIdx.x; e < (n - 1) * NCP; e += THREADS) s_dcold[e] = a.dcold[e];
+  for (int e = threadIdx.x; e < HS; e += THREADS) s_xbh[e] = a.xb_hot[e];
+  for (int e = threadIdx.x; e < NC; e += THREADS) s_xbc[e] = a.xb_cold[e];
+  for (int e = threadIdx.x; e < n - B + 2; e += THREADS) s_cs[e] = a.cold_start[e];
+  __syncthreads();
+
+  const uint32_t sm_colT = (uint32_t)__cvta_generic_to_shared(s_colT);
+  const uint32_t sm_lowR = (uint32_t)__cvta_generic_to_shared(s_lowR);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* myX = s_X + threadIdx.x;
+  double* mySP = s_SP + threadIdx.x;
+  const int tc_first = s_cs[nseg];              // cold rows >= this index are constant over a tile
+
+  const unsigned long long wg = (unsigned long long)blockIdx.x * WARPS + wib;
+  unsigned long long cand = wg * (unsigned long long)a.tiles_per_warp;
+  unsigned long long cand_hi = cand + (unsigned long long)a.tiles_per_warp;
+  if (cand_hi > a.n_tiles) cand_hi = a.n_tiles;
+
+  double acc = 0.0;
+  unsigned long long vis = 0;
+  int q = 0;
+  for (;;) {
+    // ---- refill: test 32 candidate tiles per trip until a full warp of survivors is queued ----
+    while (q < 32 && cand < cand_hi) {
+      const unsigned long long t = cand + lane;
+      bool alive = t < cand_hi;
+      if (SKIP && tc_first < NC) {
+        const unsigned long long s = (a.tile_first + (alive ? t : cand)) << c;
+        const unsigned long long g = s ^ (s >> 1);
+        for (int jc = tc_first; jc < NC; ++jc) {
+          double xr = s_xbc[jc];
+          for (int k = c; k < n - 1; ++k)
+            xr = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], xr);
+          alive = alive && (xr != 0.0);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, alive);
+      if (alive) queue[wib][q + __popc(m & ((1u << lane) - 1u))] = t;
+      q += __popc(m);
+      cand += 32;
+    }
+    __syncwarp();
+    if (q == 0) break;
+    const int take = q < 32 ? q : 32;
+    const bool active = lane < take;
+    const unsigned long long my_tile = queue[wib][active ? lane : 0];
+    __syncwarp();
+    if (lane + 32 < q) queue[wib][lane] = queue[wib][lane + 32];
+    q -= take;
+    __syncwarp();
+
+    // ---- explicit X at the tile start (cf. gpu_exact_sparse.cu:497-503) -------------------------
+    const unsigned long long s = (a.tile_first + my_tile) << c;
+    const unsigned long long g = s ^ (s >> 1);
+    double xh[HS];
+#pragma unroll
+    for (int i = 0; i < HS; ++i) xh[i] = s_xbh[i];
+    for (int k = c - 1; k < n - 1; ++k) {
+      const double f = (double)((g >> k) & 1ull);
+      const double* col = s_colT + k * HSP;
+#pragma unroll
+      for (int i = 0; i < HS; ++i) xh[i] = fma(f, col[i], xh[i]);
+    }
+    {
+      // cold rows, from the last (highest level) to the first, building the suffix products
+      double run = 1.0;
+      int seg = n - B;                           // segment of the row being visited
+      for (int jc = NC - 1; jc >= 0; --jc) {
+        while (jc < s_cs[seg]) {                 // crossed into a lower segment: close the upper ones
+          if (seg <= nseg) mySP[seg * THREADS] = run;
+          --seg;
+        }
+        double x = s_xbc[jc];
+        for (int k = c - 1; k < n - 1; ++k)
+          x = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], x);
+        myX[jc * THREADS] = x;
+        run *= x;
+      }
+      for (; seg >= 0; --seg)
+        if (seg <= nseg) mySP[seg * THREADS] = run;
+    }
+
+    double tile_acc = 0.0;
+    unsigned long long tile_vis = 0;
+    const int nblk = 1 << (c - B);
+    const int tile_odd = (int)((a.tile_first + my_tile) & 1ull);
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int z = (blk != 0) ? (__ffs(blk) - 1) : 0;     // k - B
+      const int k = B + z;
+      const int up = (k + 1 < c) ? ((blk >> (z + 1)) & 1) : tile_odd;
+      const double sg = (blk != 0) ? (up ? -1.0 : 1.0) : 0.0;
+      const double sg_top = (blk & 1) ? -1.0 : 1.0;
+
+      // ---- cold rows of level <= k: update, refresh SP[z .. 0] ----
+      double Q;
+      if (blk != 0) {
+        double run = mySP[(z + 1) * THREADS];
+        const double* dk = s_dcold + k * NCP;
+        for (int seg = z; seg >= 0; --seg) {
+          const int lo = s_cs[seg];
+          for (int jc = s_cs[seg + 1] - 1; jc >= lo; --jc) {
+            const double x = fma(sg, dk[jc], myX[jc * THREADS]);
+            myX[jc * THREADS] = x;
+            run *= x;
+          }
+          mySP[seg * THREADS] = run;
+        }
+        Q = run;
+      } else {
+        Q = mySP[0];
+      }
+
+      const uint32_t hi_addr = sm_colT + (uint32_t)(k * HSP * 8);
+      const bool skip_blk = SKIP && __all_sync(0xffffffffu, !active || Q == 0.0);
+      if (skip_blk) {
+        // exact zeros: only the block's net effect on the hot slots (high column + column B-1)
+#pragma unroll
+        for (int i = 0; i < HS; ++i) {
+          double d, mt;
+          lds_f64(hi_addr + (uint32_t)(i * 8), d);
+          lds_f64(sm_lowR + (uint32_t)((i * LB + (B - 1)) * 8), mt);
+          xh[i] = fma(sg_top, mt, fma(sg, d, xh[i]));
+        }
+      } else {
+        // ---- hot slots: level L = slot / S takes 2^(B-L) values ----
+        double PL[2 * NB];                       // PL[L][w] at PL[(NB >> L) + w] ... packed below
+        // layout: level L occupies indices [off(L), off(L) + 2^(B-L)), off(L) = 2*NB - 2*(NB >> L)
+#pragma unroll
+        for (int i = 0; i < HS; ++i) {
+          constexpr int dummy = 0; (void)dummy;
+          const int L = i / S;                   // compile-time after unrolling
+          const int off = 2 * NB - 2 * (NB >> L);
+          const int cnt = NB >> L;
+          double m[LB];
+#pragma unroll
+          for (int qq = 0; qq < LB; qq += 2) lds_f64x2(sm_lowR + (uint32_t)((i * LB + qq) * 8), m[qq], m[qq + 1]);
+          double d;
+          lds_f64(hi_addr + (uint32_t)(i * 8), d);
+          double v = fma(sg, d, xh[i]);
+          const bool first = (i % S) == 0;       // first slot of its level initialises the products
+          PL[off] = first ? v : PL[off] * v;
+#pragma unroll
+          for (int w = 1; w < cnt; ++w) {
+            const int u = w << L;
+            const int K = ctz_c(u);
+            if (K == B - 1) v = fma(sg_top, m[K], v);
+            else if (((u >> (K + 1)) & 1) == 0) v += m[K];
+            else v -= m[K];
+            PL[off + w] = first ? v : PL[off + w] * v;
+          }
+          xh[i] = v;
+        }
+        // ---- recombine: T_L[w] = PL[L][w] * T_{L+1}[w >> 1], T_B = Q ----
+#pragma unroll
+        for (int L = B - 1; L >= 0; --L) {
+          const int off = 2 * NB - 2 * (NB >> L);
+          const int offu = 2 * NB - 2 * (NB >> (L + 1));
+          const int cnt = NB >> L;
+#pragma unroll
+          for (int w = 0; w < cnt; ++w) PL[off + w] *= (L == B - 1) ? Q : PL[offu + (w >> 1)];
+        }
+        double blk_sum = 0.0;
+#pragma unroll
+        for (int u = 0; u < NB; u += 2) blk_sum += (PL[u] - PL[u + 1]);    // off(0) = 0
+        tile_acc += blk_sum;
+        tile_vis += 1;
+      }
+    }
+    if (active) { acc += tile_acc; vis += tile_vis; }
+    __syncwarp();
+  }
+
+  acc = warp_sum(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vis += __shfl_down_sync(0xffffffffu, vis, o);
+  if (lane == 0) { warp_part[wib] = acc; warp_vis[wib] = vis; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    unsigned long long cnt = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { v += warp_part[w]; cnt += warp_vis[w]; }
+    a.partials[blockIdx.x] = v;
+    a.visited[blockIdx.x] = cnt;
+  }
+}
+
+}  // namespace spb

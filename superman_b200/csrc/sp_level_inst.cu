@@ -1,0 +1,44 @@
+// Instantiations of the LevelRyser kernel (level_reg.cuh); compiled four times with
+// -DSPB_LV_B={3,4} -DSPB_LV_SKIP={0,1}.
+#include "sp_internal.cuh"
+#include "level_reg.cuh"
+#include "sp_dense_reg.h"
+
+#if !defined(SPB_LV_B) || !defined(SPB_LV_SKIP)
+#error "compile with -DSPB_LV_B=<3|4> -DSPB_LV_SKIP=<0|1>"
+#endif
+
+namespace spb {
+
+template <int B, int S, bool SKIP>
+static int launch_level(cudaStream_t st, const LevelArgs& a, unsigned blocks, size_t smem) {
+  // registers: X of the hot slots 2*B*S, level products 2*(2^(B+1)-2): 128 registers up to 16 slots
+  constexpr int MB = (B * S <= 16) ? 4 : 3;
+  auto kern = level_reg_kernel<B, S, SPB_REG_THREADS, MB, SKIP>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return SPD_ECUDA; }
+  }
+  kern<<<blocks, SPB_REG_THREADS, smem, st>>>(a);
+  return SPD_OK;
+}
+
+#define SPB_GLUE3(a, b, c, d) a##b##c##d
+#define SPB_GLUE(a, b, c, d) SPB_GLUE3(a, b, c, d)
+
+extern "C" int SPB_GLUE(spb_level_launch_b, SPB_LV_B, _s, SPB_LV_SKIP)(int S, cudaStream_t st, const LevelArgs* a,
+                                                                      unsigned blocks, size_t smem) {
+  constexpr int B = SPB_LV_B;
+  constexpr bool SKIP = SPB_LV_SKIP != 0;
+  switch (S) {
+    case 1: return launch_level<B, 1, SKIP>(st, *a, blocks, smem);
+    case 2: return launch_level<B, 2, SKIP>(st, *a, blocks, smem);
+    case 3: return launch_level<B, 3, SKIP>(st, *a, blocks, smem);
+    case 4: return launch_level<B, 4, SKIP>(st, *a, blocks, smem);
+    case 6: return launch_level<B, 6, SKIP>(st, *a, blocks, smem);
+    case 8: return launch_level<B, 8, SKIP>(st, *a, blocks, smem);
+    default: return SPD_ELIMIT;
+  }
+}
+
+}  // namespace spb

@@ -7,6 +7,7 @@
 // vector; it orders the rows hot-first (see sparse_reg.cuh) once, at creation.
 #include "sp_internal.cuh"
 #include "sparse_reg.cuh"
+#include "level_reg.cuh"
 #include "sp_dense_reg.h"
 #include <stdlib.h>
 #include <string.h>
@@ -21,7 +22,20 @@ SPB_DECL(0) SPB_DECL(1) SPB_DECL(2) SPB_DECL(3) SPB_DECL(4) SPB_DECL(5) SPB_DECL
 #undef SPB_DECL
 }
 
+extern "C" {
+int spb_level_launch_b3_s0(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+int spb_level_launch_b3_s1(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+int spb_level_launch_b4_s0(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+int spb_level_launch_b4_s1(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+}
+
 using namespace spb;
+
+static int level_launch(int B, int S, int skip, cudaStream_t st, const LevelArgs* a, unsigned blocks, size_t smem) {
+  if (B == 3) return skip ? spb_level_launch_b3_s1(S, st, a, blocks, smem) : spb_level_launch_b3_s0(S, st, a, blocks, smem);
+  if (B == 4) return skip ? spb_level_launch_b4_s1(S, st, a, blocks, smem) : spb_level_launch_b4_s0(S, st, a, blocks, smem);
+  return SPD_ELIMIT;
+}
 
 static int sparse_launch(int n, int B, int skip, cudaStream_t st, const SparseArgs* a, unsigned blocks) {
   switch (n % SPB_NGROUPS) {
@@ -43,12 +57,90 @@ struct spd_sparse_plan {
   double* d_mat_t = nullptr;   // row-ordered, mat_t[k*n + j]
   double* d_xbase = nullptr;
   std::vector<int> level;      // sorted ascending: level[j] of the row now at position j
+  // LevelRyser image (level_reg.cuh); lvB == 0 when the matrix does not fit its slots
+  int lvB = 0, lvS = 0, NC = 0, NCP = 0, HSP = 0;
+  double lv_cost = 1e300, hc_cost = 1e300;
+  double *d_colT_hot = nullptr, *d_lowR = nullptr, *d_dcold = nullptr, *d_xb_hot = nullptr, *d_xb_cold = nullptr;
+  int* d_cold_start = nullptr;
   bool pending = false;
   spd_run_info info;
 };
 
 static int count_level_below(const spd_sparse_plan* p, int bound) {
   return (int)(std::lower_bound(p->level.begin(), p->level.end(), bound) - p->level.begin());
+}
+
+
+// FP64-instruction cost per Gray index of the two sparse engines (used to pick one per matrix)
+static double hotcold_cost(const spd_sparse_plan* p, int B) {
+  const int n = p->n;
+  int H = count_level_below(p, B);
+  H = ((H + 3) / 4) * 4;
+  if (H > n) H = n;
+  return 2.0 * H + (2.0 * (n - H) + 8.0) / (double)(1 << B);
+}
+
+// Packs the rows into the LevelRyser layout for (B, S): S register slots per level < B, the other
+// rows cold, sorted by level.  lvl[] / dmat_t / xbase are in the ORIGINAL row order.  Returns
+// false when some level has more rows than the slots at or below it can take.
+static bool level_pack(int n, int B, int S, const std::vector<int>& lvl, const double* dmat_t,
+                       const double* xbase, std::vector<double>& colT_hot, std::vector<double>& lowR,
+                       std::vector<double>& dcold, std::vector<double>& xb_hot, std::vector<double>& xb_cold,
+                       std::vector<int>& cold_start, int* NC_out, double* cost_out) {
+  const int HS = B * S, HSP = HS + (HS & 1), LB = B + (B & 1);
+  std::vector<int> slot_row(HS, -1);
+  std::vector<int> order(n);
+  for (int j = 0; j < n; ++j) order[j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lvl[a] < lvl[b]; });
+  // hot rows by ascending level: own level's slots first, then any free slot of a lower level
+  std::vector<int> cold;
+  for (int idx = 0; idx < n; ++idx) {
+    const int j = order[idx];
+    if (lvl[j] >= B) { cold.push_back(j); continue; }
+    int placed = -1;
+    for (int L = lvl[j]; L >= 0 && placed < 0; --L)
+      for (int t = 0; t < S; ++t)
+        if (slot_row[L * S + t] < 0) { placed = L * S + t; break; }
+    if (placed < 0) return false;
+    slot_row[placed] = j;
+  }
+  const int NC = (int)cold.size(), NCP = NC + (NC & 1) + ((NC == 0) ? 2 : 0);
+  colT_hot.assign((size_t)(n - 1) * HSP, 0.0);
+  lowR.assign((size_t)HS * LB, 0.0);
+  dcold.assign((size_t)(n - 1) * NCP, 0.0);
+  xb_hot.assign(HSP, 1.0);
+  xb_cold.assign(NCP, 1.0);
+  for (int sl = 0; sl < HS; ++sl) {
+    const int j = slot_row[sl];
+    if (j < 0) continue;                          // neutral slot: x = 1, all entries 0
+    xb_hot[sl] = xbase[j];
+    for (int k = 0; k < n - 1; ++k) colT_hot[(size_t)k * HSP + sl] = dmat_t[(size_t)k * n + j];
+    for (int q = 0; q < B; ++q) lowR[(size_t)sl * LB + q] = dmat_t[(size_t)q * n + j];
+  }
+  cold_start.assign(n - B + 2, NC);
+  for (int jc = NC - 1; jc >= 0; --jc) {
+    const int j = cold[jc];
+    xb_cold[jc] = xbase[j];
+    for (int k = 0; k < n - 1; ++k) dcold[(size_t)k * NCP + jc] = dmat_t[(size_t)k * n + j];
+  }
+  // cold_start[i] = first cold row with level >= B+i  (levels run up to n = "never touched")
+  {
+    int jc = 0;
+    for (int i = 0; i <= n - B; ++i) {
+      while (jc < NC && lvl[cold[jc]] < B + i) ++jc;
+      cold_start[i] = jc;
+    }
+    cold_start[n - B + 1] = NC;
+  }
+  // cost per index: hot slots + recombination + expected cold refresh (x3: it runs from shared memory)
+  double hot = 0.0;
+  for (int L = 0; L < B; ++L) hot += (double)S * 2.0 * (double)(1 << (B - L));
+  double coldc = 0.0, w = 0.5;
+  for (int z = 0; z < 16 && B + z <= n; ++z, w *= 0.5) coldc += w * 3.0 * (double)cold_start[(z + 1 <= n - B + 1) ? z + 1 : n - B + 1];
+  const double per_block = hot + (double)((2 << B) - 2) + (double)(1 << B) + coldc;
+  *cost_out = per_block / (double)(1 << B);
+  *NC_out = NC;
+  return true;
 }
 
 static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned long long hi) {
@@ -70,7 +162,8 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
   unsigned long long smem_indices = len;   // indices evaluated by the dense-semantics ragged kernel
   bool have_visited = false;
 
-  const bool reg_ok = (n >= SPB_SPARSE_NMIN && n <= SPB_REG_NMAX && env_int("SP_SPARSE_FORCE_SMEM", 0) == 0);
+  const bool use_level = p->lvB != 0;
+  const bool reg_ok = (use_level || (n >= SPB_SPARSE_NMIN && n <= SPB_REG_NMAX)) && env_int("SP_SPARSE_FORCE_SMEM", 0) == 0;
   int rc;
   unsigned long long body_lo = lo, body_hi = lo;
   int c = 0, B = 3;
@@ -85,6 +178,7 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
     }
     const int forced = env_int("SP_SPARSE_LOWCOLS", 0);
     if (forced == 3 || forced == 4) B = forced;
+    if (use_level) B = p->lvB;
     const int tiles_log2 = env_int("SP_SPARSE_TILES_LOG2", 21);
     c = env_int("SP_SPARSE_TILE_LOG2", 0);
     if (c <= 0) {
@@ -119,12 +213,28 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
       if (nt > tiles_left) nt = tiles_left;
       if ((rc = lane_reserve_partials(&L, (size_t)blocks + 4096)) != SPD_OK) return rc;
       if ((rc = lane_reserve_aux(&L, (size_t)blocks)) != SPD_OK) return rc;
-      SparseArgs a;
-      a.mat_t = p->d_mat_t; a.xbase = p->d_xbase;
-      a.partials = L.d_partials; a.visited = L.d_aux;
-      a.tile_first = tile; a.n_tiles = nt; a.c = c; a.H = H; a.TC = TC; a.tiles_per_warp = tiles_per_warp;
-      rc = sparse_launch(n, B, p->skip, L.stream, &a, (unsigned)blocks);
-      if (rc != SPD_OK) { set_error("no sparse register kernel for n=%d B=%d", n, B); return rc; }
+      if (use_level) {
+        LevelArgs la;
+        la.colT_hot = p->d_colT_hot; la.lowR = p->d_lowR; la.dcold = p->d_dcold;
+        la.xb_hot = p->d_xb_hot; la.xb_cold = p->d_xb_cold; la.cold_start = p->d_cold_start;
+        la.partials = L.d_partials; la.visited = L.d_aux;
+        la.tile_first = tile; la.n_tiles = nt;
+        la.n = n; la.NC = p->NC; la.NCP = p->NCP; la.HSP = p->HSP; la.c = c; la.tiles_per_warp = tiles_per_warp;
+        const int HS = p->lvB * p->lvS, LBv = p->lvB + (p->lvB & 1);
+        const size_t dbl = (size_t)(n - 1) * p->HSP + (size_t)HS * LBv + (size_t)(n - 1) * p->NCP + p->HSP + p->NCP +
+                           (size_t)p->NC * SPB_REG_THREADS + (size_t)(c - B + 1) * SPB_REG_THREADS;
+        const size_t smem = dbl * sizeof(double) + (size_t)(n - B + 2) * sizeof(int);
+        if (smem > 220 * 1024) { set_error("level engine needs %zu B of shared memory", smem); return SPD_ELIMIT; }
+        rc = level_launch(p->lvB, p->lvS, p->skip, L.stream, &la, (unsigned)blocks, smem);
+        if (rc != SPD_OK) { if (rc == SPD_ELIMIT) set_error("no level kernel for B=%d S=%d", p->lvB, p->lvS); return rc; }
+      } else {
+        SparseArgs a;
+        a.mat_t = p->d_mat_t; a.xbase = p->d_xbase;
+        a.partials = L.d_partials; a.visited = L.d_aux;
+        a.tile_first = tile; a.n_tiles = nt; a.c = c; a.H = H; a.TC = TC; a.tiles_per_warp = tiles_per_warp;
+        rc = sparse_launch(n, B, p->skip, L.stream, &a, (unsigned)blocks);
+        if (rc != SPD_OK) { set_error("no sparse register kernel for n=%d B=%d", n, B); return rc; }
+      }
       SPB_CUDA(cudaGetLastError());
       ++launches;
       // fold this launch's per-block sums into result slots 0 (value) and 1 (visited blocks)
@@ -205,6 +315,57 @@ int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase
   if ((rc = smem_kernel_prepare(nov)) != SPD_OK) return fail(rc);
   if ((rc = lane_reserve_partials(&L, (1u << 20) + 8192)) != SPD_OK) return fail(rc);
   if ((rc = lane_reserve_aux(&L, 1u << 20)) != SPD_OK) return fail(rc);
+
+  // ---- choose the engine: LevelRyser (B, S) with the lowest cost, if the matrix fits its slots ----
+  p->hc_cost = std::min(hotcold_cost(p, 3), hotcold_cost(p, 4)) * 1.45;   // measured: ~68 % of the pipe
+  const int engine = env_int("SP_SPARSE_ENGINE", 0);                       // 0 auto, 1 hot/cold, 2 level
+  if (engine != 1 && n >= 6) {
+    static const int s_opts[6] = {1, 2, 3, 4, 6, 8};
+    std::vector<double> bh, bl, bd, bxh, bxc;
+    std::vector<int> bcs;
+    const int forceB = env_int("SP_SPARSE_LOWCOLS", 0), forceS = env_int("SP_LEVEL_SLOTS", 0);
+    for (int B = 3; B <= 4; ++B) {
+      if (B + 2 > n - 1) continue;
+      if (forceB && forceB != B) continue;
+      for (int si = 0; si < 6; ++si) {
+        if (forceS && forceS != s_opts[si]) continue;
+        std::vector<double> h, l, d, xh, xc;
+        std::vector<int> cs;
+        int NC = 0;
+        double cost = 0;
+        if (!level_pack(n, B, s_opts[si], lvl, dmat_t, xbase, h, l, d, xh, xc, cs, &NC, &cost)) continue;
+        cost *= 1.15;
+        if (cost < p->lv_cost) {
+          p->lv_cost = cost; p->lvB = B; p->lvS = s_opts[si]; p->NC = NC;
+          bh.swap(h); bl.swap(l); bd.swap(d); bxh.swap(xh); bxc.swap(xc); bcs.swap(cs);
+        }
+        break;   // a larger S for the same B only costs more
+      }
+    }
+    if (p->lvB && (engine == 2 || p->lv_cost < p->hc_cost || n > SPB_REG_NMAX)) {
+      const int HS = p->lvB * p->lvS;
+      p->HSP = HS + (HS & 1);
+      p->NCP = (int)bxc.size();
+      auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+        int r = lane_arena_alloc(&L, bytes ? bytes : 8, dst);
+        if (r != SPD_OK) return r;
+        if (bytes && cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, L.stream) != cudaSuccess) {
+          set_error("level image upload failed");
+          return SPD_ECUDA;
+        }
+        return SPD_OK;
+      };
+      if ((rc = up(bh.data(), bh.size() * 8, (void**)&p->d_colT_hot)) != SPD_OK) return fail(rc);
+      if ((rc = up(bl.data(), bl.size() * 8, (void**)&p->d_lowR)) != SPD_OK) return fail(rc);
+      if ((rc = up(bd.data(), bd.size() * 8, (void**)&p->d_dcold)) != SPD_OK) return fail(rc);
+      if ((rc = up(bxh.data(), bxh.size() * 8, (void**)&p->d_xb_hot)) != SPD_OK) return fail(rc);
+      if ((rc = up(bxc.data(), bxc.size() * 8, (void**)&p->d_xb_cold)) != SPD_OK) return fail(rc);
+      if ((rc = up(bcs.data(), bcs.size() * 4, (void**)&p->d_cold_start)) != SPD_OK) return fail(rc);
+      if (cudaStreamSynchronize(L.stream) != cudaSuccess) { set_error("level image upload failed"); return fail(SPD_ECUDA); }
+    } else {
+      p->lvB = 0;
+    }
+  }
   *out = p;
   return SPD_OK;
 }
