@@ -119,3 +119,33 @@ def test_errors(sp):
     bad_rows = m.rows.copy(); bad_rows[0] = 99
     with pytest.raises(sp.SupermanError):
         sp.sparse_ryser(m.mat, m.cptrs, bad_rows, m.cvals, 5, 4)
+
+
+def test_reference_real_matrices(sp):
+    """the reference's real/ inputs that the exact paths can handle: ibm32 (n = 32, 0/1) against the
+    long-double oracle value -- an exact integer -- and cage5_c2 (n = 37, real-valued): the dense,
+    SpaRyser+SortOrder and SkipPer+SkipOrder paths walk different Gray sequences over differently
+    permuted matrices and must agree"""
+    r = _golden.real()
+    if not r:
+        pytest.skip("tests/golden/real.json not generated")
+    e = r["real/ibm32.mtxzero"]
+    A = _golden.dense_from(e)
+    n = e["n"]
+    assert e["ld"] == round(e["ld"])
+    m1 = sp.Matrix.from_dense(A).compress(1)
+    m2 = sp.Matrix.from_dense(A).compress(2)
+    assert np.diff(m1.cptrs).tolist() == e["colcount_sort"] and np.diff(m2.cptrs).tolist() == e["colcount_skip"]
+    assert round(sp.dense_ryser(A, n, 4)) == e["ld"]
+    assert round(sp.sparse_ryser(m1.mat, m1.cptrs, m1.rows, m1.cvals, n, 4)) == e["ld"]
+    st = sp._ffi.SpStats()
+    assert round(sp.skipper(m2.mat, m2.rptrs, m2.cols, m2.cptrs, m2.rows, m2.cvals, n, 7, stats=st)) == e["ld"]
+    assert st.visited < st.units
+    e = r["real/cage5_c2.mtxzero"]
+    A = _golden.dense_from(e)
+    n = e["n"]
+    d = sp.dense_ryser(A, n, 4)
+    m1 = sp.Matrix.from_dense(A).compress(1)
+    m2 = sp.Matrix.from_dense(A).compress(2)
+    assert sp.sparse_ryser(m1.mat, m1.cptrs, m1.rows, m1.cvals, n, 4) == pytest.approx(d, rel=REL)
+    assert sp.skipper(m2.mat, m2.rptrs, m2.cols, m2.cptrs, m2.rows, m2.cvals, n, 7) == pytest.approx(d, rel=REL)
