@@ -76,7 +76,9 @@ typedef struct sp_matrix {
 
 /* Header sniff + ReadMatrix<T> (main.cu:494-498, util.h:343-358): `nov nnz {int|float|double}`
  * then `i j val` lines, 0-based; unparsable lines are skipped; binary != 0 is the -b flag (every
- * listed entry becomes 1). */
+ * listed entry becomes 1).  A file whose first line is a `%%MatrixMarket matrix coordinate ...`
+ * banner is read as MatrixMarket instead (1-based, real / integer / pattern, general / symmetric:
+ * the revised front-end's format, revised_perman/read_matrix.hpp:11-157). */
 int  sp_matrix_read(const char *path, int binary, sp_matrix *out);
 int  sp_matrix_from_dense(const double *mat, int nov, sp_matrix *out);
 /* matrix2compressed (preprocessing 0, util.h:522-551), _sortOrder (1, util.h:553-619; rewrites

@@ -24,13 +24,13 @@ static int launch_one(cudaStream_t st, const double* mat_t, const double* xbase,
 }
 
 // Registers: X is 2N, the 2^B running products 2^(B+1); 4 blocks of 128 threads per SM leave 128
-// registers per thread, 3 blocks 168 (ptxas -v: zero spills for every entry below).
+// registers per thread, 3 blocks 168, 2 blocks 255 (ptxas -v: zero spills for every entry below).
 template <int N, int B>
 static int launch_nb(cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
                      unsigned long long group_first, unsigned long long n_groups, int gpb, int c,
                      unsigned* blocks_out) {
   // from the ptxas -v survey of every (N, B, MB): the largest occupancy with zero spill bytes
-  constexpr int MB = (B == 4) ? ((N <= 39 && N != 33) ? 4 : 3) : (N <= 43 ? 4 : 3);
+  constexpr int MB = (N > 54) ? 2 : (B == 4) ? ((N <= 39 && N != 33) ? 4 : 3) : (N <= 43 ? 4 : 3);
   return launch_one<N, B, MB>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out);
 }
 
@@ -48,21 +48,21 @@ extern "C" int SPB_GLUE(spb_reg_launch_g, SPB_GROUP)(
     unsigned long long group_first, unsigned long long n_groups, int gpb, int c, unsigned* blocks_out) {
   switch (n) {
 #if SPB_GROUP == 0
-    SPB_CASE(16) SPB_CASE(24) SPB_CASE(32) SPB_CASE(40) SPB_CASE(48)
+    SPB_CASE(16) SPB_CASE(24) SPB_CASE(32) SPB_CASE(40) SPB_CASE(48) SPB_CASE(56) SPB_CASE(64)
 #elif SPB_GROUP == 1
-    SPB_CASE(17) SPB_CASE(25) SPB_CASE(33) SPB_CASE(41)
+    SPB_CASE(17) SPB_CASE(25) SPB_CASE(33) SPB_CASE(41) SPB_CASE(49) SPB_CASE(57)
 #elif SPB_GROUP == 2
-    SPB_CASE(18) SPB_CASE(26) SPB_CASE(34) SPB_CASE(42)
+    SPB_CASE(18) SPB_CASE(26) SPB_CASE(34) SPB_CASE(42) SPB_CASE(50) SPB_CASE(58)
 #elif SPB_GROUP == 3
-    SPB_CASE(19) SPB_CASE(27) SPB_CASE(35) SPB_CASE(43)
+    SPB_CASE(19) SPB_CASE(27) SPB_CASE(35) SPB_CASE(43) SPB_CASE(51) SPB_CASE(59)
 #elif SPB_GROUP == 4
-    SPB_CASE(20) SPB_CASE(28) SPB_CASE(36) SPB_CASE(44)
+    SPB_CASE(20) SPB_CASE(28) SPB_CASE(36) SPB_CASE(44) SPB_CASE(52) SPB_CASE(60)
 #elif SPB_GROUP == 5
-    SPB_CASE(13) SPB_CASE(21) SPB_CASE(29) SPB_CASE(37) SPB_CASE(45)
+    SPB_CASE(13) SPB_CASE(21) SPB_CASE(29) SPB_CASE(37) SPB_CASE(45) SPB_CASE(53) SPB_CASE(61)
 #elif SPB_GROUP == 6
-    SPB_CASE(14) SPB_CASE(22) SPB_CASE(30) SPB_CASE(38) SPB_CASE(46)
+    SPB_CASE(14) SPB_CASE(22) SPB_CASE(30) SPB_CASE(38) SPB_CASE(46) SPB_CASE(54) SPB_CASE(62)
 #elif SPB_GROUP == 7
-    SPB_CASE(15) SPB_CASE(23) SPB_CASE(31) SPB_CASE(39) SPB_CASE(47)
+    SPB_CASE(15) SPB_CASE(23) SPB_CASE(31) SPB_CASE(39) SPB_CASE(47) SPB_CASE(55) SPB_CASE(63)
 #endif
     default:
       return SPD_ELIMIT;

@@ -5,8 +5,9 @@
 #define SPB_REG_THREADS 128
 #define SPB_NGROUPS 8
 #define SPB_REG_NMIN 13
-#define SPB_REG_NMAX 48
+#define SPB_REG_NMAX 64
 #define SPB_SPARSE_NMIN 7
+#define SPB_SPARSE_NMAX 48
 
 extern "C" {
 #define SPB_DECL(g)                                                                               \

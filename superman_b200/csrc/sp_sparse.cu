@@ -163,7 +163,7 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
   bool have_visited = false;
 
   const bool use_level = p->lvB != 0;
-  const bool reg_ok = (use_level || (n >= SPB_SPARSE_NMIN && n <= SPB_REG_NMAX)) && env_int("SP_SPARSE_FORCE_SMEM", 0) == 0;
+  const bool reg_ok = (use_level || (n >= SPB_SPARSE_NMIN && n <= SPB_SPARSE_NMAX)) && env_int("SP_SPARSE_FORCE_SMEM", 0) == 0;
   int rc;
   unsigned long long body_lo = lo, body_hi = lo;
   int c = 0, B = 3;
@@ -342,7 +342,7 @@ int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase
         break;   // a larger S for the same B only costs more
       }
     }
-    if (p->lvB && (engine == 2 || p->lv_cost < p->hc_cost || n > SPB_REG_NMAX)) {
+    if (p->lvB && (engine == 2 || p->lv_cost < p->hc_cost || n > SPB_SPARSE_NMAX)) {
       const int HS = p->lvB * p->lvS;
       p->HSP = HS + (HS & 1);
       p->NCP = (int)bxc.size();

@@ -77,6 +77,68 @@ static int parse_triple(const char *line, int type, int *i, int *j, double *val)
   return 1;
 }
 
+/* MatrixMarket coordinate files (the revised front-end's reader,
+ * revised_perman/read_matrix.hpp:11-157 + mmio banner): `%%MatrixMarket matrix coordinate
+ * {real|integer|pattern} {general|symmetric}`, comment lines starting with %, `rows cols entries`,
+ * then 1-based `i j [val]` lines; `pattern` files and the -b flag give 1 for every listed entry;
+ * `symmetric` files mirror the off-diagonal entries.  The matrix must be square. */
+static int read_mtx(FILE *f, const char *path, const char *banner, int binary, sp_matrix *out) {
+  char obj[32] = "", fmt[32] = "", field[32] = "", sym[32] = "";
+  if (sscanf(banner, "%%%%MatrixMarket %31s %31s %31s %31s", obj, fmt, field, sym) < 4) {
+    sp_set_error("%s: malformed MatrixMarket banner", path);
+    return SP_EIO;
+  }
+  for (char *p = field; *p; ++p) *p = (char)tolower((unsigned char)*p);
+  for (char *p = sym; *p; ++p) *p = (char)tolower((unsigned char)*p);
+  for (char *p = fmt; *p; ++p) *p = (char)tolower((unsigned char)*p);
+  if (strcmp(fmt, "coordinate") != 0) { sp_set_error("%s: only coordinate MatrixMarket files are supported", path); return SP_EIO; }
+  const int pattern = strcmp(field, "pattern") == 0;
+  const int integer = strcmp(field, "integer") == 0;
+  if (!pattern && !integer && strcmp(field, "real") != 0 && strcmp(field, "double") != 0) {
+    sp_set_error("%s: unsupported MatrixMarket field `%s`", path, field);
+    return SP_EIO;
+  }
+  const int symmetric = strcmp(sym, "symmetric") == 0;
+  if (!symmetric && strcmp(sym, "general") != 0) { sp_set_error("%s: unsupported MatrixMarket symmetry `%s`", path, sym); return SP_EIO; }
+  char *line = NULL;
+  size_t cap = 0;
+  int rc = SP_OK, rows = 0, cols = 0, entries = 0, have_size = 0;
+  while (getline(&line, &cap, f) >= 0) {
+    const char *p = line;
+    while (*p == ' ' || *p == '\t') ++p;
+    if (*p == '%' || *p == '\n' || *p == '\r' || *p == '\0') continue;
+    if (!have_size) {
+      if (sscanf(p, "%d %d %d", &rows, &cols, &entries) < 3) { sp_set_error("%s: missing size line", path); rc = SP_EIO; break; }
+      if (rows != cols) { sp_set_error("%s: matrix is %d x %d, the permanent needs a square matrix", path, rows, cols); rc = SP_EINVAL; break; }
+      if ((rc = alloc_dense(out, rows)) != SP_OK) break;
+      out->type = (pattern || integer) ? SP_TYPE_INT : SP_TYPE_DOUBLE;
+      out->header_nnz = entries;
+      have_size = 1;
+      continue;
+    }
+    char *end;
+    long i = strtol(p, &end, 10);
+    if (end == p) continue;
+    p = end;
+    long j = strtol(p, &end, 10);
+    if (end == p) continue;
+    double v = 1.0;
+    if (!pattern) {
+      p = end;
+      v = strtod(p, &end);
+      if (end == p) continue;
+    }
+    if (binary || pattern) v = 1.0;
+    --i; --j;
+    if (i < 0 || j < 0 || i >= rows || j >= rows) continue;
+    out->mat[(size_t)i * rows + j] = v;
+    if (symmetric && i != j) out->mat[(size_t)j * rows + i] = v;
+  }
+  free(line);
+  if (rc == SP_OK && !have_size) { sp_set_error("%s: missing size line", path); rc = SP_EIO; }
+  return rc;
+}
+
 int sp_matrix_read(const char *path, int binary, sp_matrix *out) {
   if (!path || !out) { sp_set_error("null argument"); return SP_EINVAL; }
   matrix_zero(out);
@@ -88,6 +150,10 @@ int sp_matrix_read(const char *path, int binary, sp_matrix *out) {
   if (getline(&line, &cap, f) < 0) {
     sp_set_error("%s: empty file", path);
     rc = SP_EIO;
+    goto done;
+  }
+  if (strncmp(line, "%%MatrixMarket", 14) == 0) {
+    rc = read_mtx(f, path, line, binary, out);
     goto done;
   }
   int nov = 0, nnz = 0;

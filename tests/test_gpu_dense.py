@@ -137,16 +137,23 @@ def test_errors(sp):
         sp.dense_ryser(np.ones((22, 22)), 22, 5, gpu_num=64)     # more devices than the box has
 
 
-def test_large_n_shared_memory_path(sp, oracle):
-    """n > 48 runs the shared-memory-X kernel with > 48 KiB of dynamic shared memory (the reference
-    cannot launch there): check a leading range against the oracle"""
+def test_large_n_paths(sp, oracle, monkeypatch):
+    """49 <= n <= 64: register kernel at 2-3 blocks/SM, and the shared-memory-X kernel with > 48 KiB of
+    dynamic shared memory (the reference cannot launch there): leading ranges
+    against the oracle"""
     rng = np.random.default_rng(6)
-    for n in (52, 64):
+    for n in (49, 52, 57, 64):
         A = _rand(rng, n, 0.3, "dbl")
         lo, hi = 3, 3 + (1 << 18)
-        got = sp.dense_ryser_range(A, lo, hi, n)
         want = oracle.ryser_range_ld(A, lo, hi)
+        got = sp.dense_ryser_range(A, lo, hi, n)                  # ragged head + register body + tail
         assert got == pytest.approx(want, rel=1e-9, abs=1e-14 * _scale(A))
+        lo2, hi2 = 1 << 20, (1 << 20) + (1 << 19)
+        want2 = oracle.ryser_range_ld(A, lo2, hi2)
+        assert sp.dense_ryser_range(A, lo2, hi2, n) == pytest.approx(want2, rel=1e-9, abs=1e-14 * _scale(A))
+        monkeypatch.setenv("SP_DENSE_FORCE_SMEM", "1")
+        assert sp.dense_ryser_range(A, lo, hi, n) == pytest.approx(want, rel=1e-9, abs=1e-14 * _scale(A))
+        monkeypatch.delenv("SP_DENSE_FORCE_SMEM")
 
 
 # ---- BASELINE.json full sizes: size-independent properties ------------------------------------------

@@ -63,6 +63,32 @@ def test_reader_edge_cases(sp, tmp_path):
     assert sp.Matrix.read(str(tmp_path / "f.txt")).mat[0, 0] == float(np.float32(0.1))
 
 
+def test_matrix_market_reader(sp, tmp_path):
+    p = tmp_path / "g.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate real general\n% a comment\n3 3 4\n1 1 2.5\n2 3 -1\n3 2 4\n1 3 0.5\n")
+    m = sp.Matrix.read(str(p)).compress(0)
+    assert np.array_equal(m.mat, np.array([[2.5, 0, 0.5], [0, 0, -1], [0, 4, 0]]))
+    assert m.type == "double" and m.header_nnz == 4 and m.nnz == 3          # CRS/CCS keep entries > 0 (util.h:537)
+    b = sp.Matrix.read(str(p), binary=True)
+    assert np.array_equal(b.mat, np.array([[1, 0, 1], [0, 0, 1], [0, 1, 0]], float))
+    p = tmp_path / "s.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate pattern symmetric\n4 4 4\n1 1\n2 1\n4 3\n3 3\n")
+    m = sp.Matrix.read(str(p))
+    want = np.zeros((4, 4)); want[0, 0] = want[1, 0] = want[0, 1] = want[3, 2] = want[2, 3] = want[2, 2] = 1
+    assert np.array_equal(m.mat, want) and m.type == "int"
+    p = tmp_path / "i.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate integer general\n2 2 2\n1 2 3\n2 1 4\n")
+    assert np.array_equal(sp.Matrix.read(str(p)).mat, np.array([[0, 3], [4, 0]], float))
+    for bad in ("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n",
+                "%%MatrixMarket matrix coordinate complex general\n2 2 1\n1 1 1 0\n",
+                "%%MatrixMarket matrix coordinate real general\n2 3 1\n1 1 1\n",
+                "%%MatrixMarket matrix coordinate real general\n"):
+        q = tmp_path / "bad.mtx"
+        q.write_text(bad)
+        with pytest.raises(sp.SupermanError):
+            sp.Matrix.read(str(q))
+
+
 def test_grid_matches_reference_golden(sp):
     for g in _golden.grids():
         m = sp.Matrix.grid(g["m"], g["n"])
