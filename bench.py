@@ -204,6 +204,61 @@ def run_reference_arm(args):
     return 0
 
 
+def run_in_process_multi_gpu(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: the library's own static multi-GPU split
+    (sp_dense_ryser id 5 = the reference's -p5 -dN: one host thread per device, rank-order host sum)."""
+    import torch
+    import superman_b200 as sp
+    from superman_b200._ffi import SpStats
+    n = args.n
+    mat = synthetic_matrix(n, DENSITY)
+    total = 1 << (n - 1)
+    if sp.device_count() < args.gpus:
+        print(f"bench.py: --gpus {args.gpus} but {sp.device_count()} device(s) visible", file=sys.stderr)
+        return 2
+    peak = sp.fp64_peak(0, 200)
+    st = SpStats()
+    for _ in range(args.warmup):
+        sp.dense_ryser(mat, n, 5, gpu_num=args.gpus, stats=st)
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    torch.cuda.synchronize()
+    t0w, t0 = time.time(), time.perf_counter()
+    dev_ms, launches, perm = 0.0, 0, 0.0
+    for _ in range(args.steps):
+        perm = sp.dense_ryser(mat, n, 5, gpu_num=args.gpus, stats=st)
+        dev_ms += st.kernel_ms            # max over devices of their CUDA-event times
+        launches += st.launches
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t1w = time.time()
+    time.sleep(0.2)
+    sampler.stop()
+    units = args.steps * total
+    value = units / (dev_ms * 1e-3)
+    achieved = (total / args.gpus) * (2 * n + 1) / ((dev_ms / args.steps) * 1e-3)
+    line = {
+        "metric": "gray_code_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense Ryser n={n} density {DENSITY} FP64, one full permanent (2^{n - 1} Gray indices) per step, "
+                               f"seeded synthetic matrix (seed {1000 * n}); BASELINE.json configs[3]",
+                   "partition": f"in-process static split over {args.gpus} devices (sp_dense_ryser id 5 = -p5 -d{args.gpus}), one host thread per device",
+                   "l2": "working set is 10 KB per device; the kernel is FP64-issue bound"},
+        "seconds_per_permanent": dev_ms / args.steps * 1e-3, "permanent": perm,
+        "roofline": {"bound": "fp64_issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s (thread-level FP64)",
+                     "frac": achieved / peak, "traffic": None, "kernel": "spb::ryser_reg_kernel"},
+        "cpu_baseline": None,
+        "e2e": {"value": units / wall, "unit": "iterations/s", "ms_per_step": 1e3 * wall / args.steps,
+                "h2d_bytes_per_step": 8 * (n * n + n) * args.gpus, "d2h_bytes_per_step": 8 * args.gpus,
+                "api": "sp_dense_ryser(host mat, nov, 5, gpu_num, ...) -> double"},
+        "gpu_launches": launches, "clocks": sampler.summary(t0w, t1w),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,6 +284,8 @@ def main():
         print("bench.py: no CUDA device; superman_b200 has no CPU fallback", file=sys.stderr)
         return 2
     torch.cuda.set_device(local_rank)
+    if world == 1 and args.gpus > 1:
+        return run_in_process_multi_gpu(args)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # rank 0 must print exactly one line: keep NCCL's version banner off stdout

@@ -187,6 +187,10 @@ double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptr
                               unsigned long long seed, long long trial, int count, double *values,
                               sp_stats *stats);
 
+double sp_approx_trial_dense(const double *mat, int nov, int scaling, int scale_intervals, int scale_times,
+                             unsigned long long seed, long long trial, int count, double *values,
+                             sp_stats *stats);
+
 /* ---------------------------------------------------------------------------------------------
  * The reference's Python / MATLAB shim on the GPU engine (interface_connector.c:61-231,
  * matlab_calculate_return.h:4,12,20): same names and arguments; see superman_b200/host/sp_connector.c

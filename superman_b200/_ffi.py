@@ -101,6 +101,7 @@ _sig("sp_rasmussen_dense", C.c_double, [_dp, C.c_int, C.c_longlong, C.c_int, C.c
 _sig("sp_scaling_dense", C.c_double, [_dp, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, _sp])
 _sig("sp_approx_trial_sparse", C.c_double, [_ip, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, _dp, _sp])
 
+_sig("sp_approx_trial_dense", C.c_double, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, _dp, _sp])
 _sig("sp_connect", None, [])
 _sig("read_calculate_return", C.c_double, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int])
 _sig("matlab_calculate_return_int", C.c_double, [_ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int])

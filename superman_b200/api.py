@@ -15,7 +15,7 @@ __all__ = [
     "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
     "dense_ryser", "dense_ryser_range", "DenseHandle",
     "sparse_ryser", "skipper", "sparse_ryser_range",
-    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse",
+    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense",
     "gpu_perman64_rasmussen_sparse", "gpu_perman64_rasmussen_multigpucpu_chunks_sparse",
     "gpu_perman64_approximation_sparse", "gpu_perman64_approximation_multigpucpu_chunks_sparse",
     "gpu_perman64_rasmussen", "gpu_perman64_rasmussen_multigpucpu_chunks",
@@ -281,6 +281,17 @@ def approx_trials_sparse(rptrs, cols, cptrs, rows, nov, nnz, scaling=False, scal
     st = SpStats()
     v = lib.sp_approx_trial_sparse(_iptr(rp), _iptr(co), _iptr(cp), _iptr(ro), nov, nnz, int(scaling), scale_intervals,
                                    scale_times, seed, first, count, _ptr(out), C.byref(st))
+    _check(v, st)
+    return out
+
+
+def approx_trials_dense(mat, nov, scaling=False, scale_intervals=4, scale_times=5, seed=1, first=0, count=1):
+    """Per-trial estimates of the dense twins for trials [first, first+count)."""
+    a = _dmat(mat, nov)
+    out = np.zeros(count, dtype=np.float64)
+    st = SpStats()
+    v = lib.sp_approx_trial_dense(_ptr(a), nov, int(scaling), scale_intervals, scale_times, seed, first, count,
+                                  _ptr(out), C.byref(st))
     _check(v, st)
     return out
 

@@ -516,3 +516,34 @@ double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptr
   if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
   return total;
 }
+
+/* per-trial estimates of the dense twins (pattern = entries != 0; the scaled estimator weights its
+ * Sinkhorn sums by the entries, gpu_approximation_dense.cu:286-313) */
+double sp_approx_trial_dense(const double *mat, int nov, int scaling, int scale_intervals, int scale_times,
+                             unsigned long long seed, long long trial, int count, double *values,
+                             sp_stats *stats) {
+  stats_clear(stats);
+  if (!mat || !values || count < 1 || trial < 0) { sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
+  if (nov < 1 || nov > SP_MAX_NOV) { sp_set_error("matrix order %d out of range", nov); return fail(stats, SP_ELIMIT); }
+  int *rptrs = NULL, *cols = NULL, *cptrs = NULL, *rows = NULL, nnz = 0;
+  double *rvals = NULL, *cvals = NULL;
+  int rc = dense_pattern(mat, nov, &rptrs, &cols, &rvals, &cptrs, &rows, &cvals, &nnz);
+  double total = NAN;
+  if (rc == SP_OK) {
+    spd_approx_plan *plan = NULL;
+    rc = spd_approx_plan_create(0, rptrs, cols, cptrs, rows, scaling ? rvals : NULL, scaling ? cvals : NULL, nov, nnz,
+                                scaling, scale_intervals, scale_times, pick_seed(seed), &plan);
+    if (rc == SPD_OK) {
+      total = 0.0;
+      for (int i = 0; i < count && rc == SPD_OK; ++i) {
+        rc = spd_approx_plan_trial(plan, (unsigned long long)trial + (unsigned long long)i, &values[i]);
+        total += values[i];
+      }
+      spd_approx_plan_destroy(plan);
+    }
+    if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); total = NAN; }
+  }
+  free(rptrs); free(cols); free(cptrs); free(rows); free(rvals); free(cvals);
+  if (rc != SP_OK) return fail(stats, rc);
+  return total;
+}

@@ -117,6 +117,31 @@ def test_dense_twins(sp, oracle):
     assert sp.gpu_perman64_approximation(B, n, 1000, 4, 5, seed=2) == sp.scaling_dense(B, n, 1000, 4, 5, 1, seed=2)
 
 
+def test_dense_twins_trials_bitwise(sp, oracle):
+    """dense scaled estimator: Sinkhorn sums weighted by the entries, in double
+    (gpu_approximation_dense.cu:286-313); dense Rasmussen: pattern of the entries != 0"""
+    rng = np.random.default_rng(23)
+    n = 14
+    pat = rng.random((n, n)) < 0.5
+    pat[np.arange(n), rng.permutation(n)] = True
+    A = pat * np.round(rng.uniform(0.2, 3, (n, n)), 3)
+    # pattern + values in the order the library builds them (row-major CRS, column-major CCS)
+    rptrs, cols, rvals, cptrs, rows, cvals = [0], [], [], [0], [], []
+    for i in range(n):
+        for j in range(n):
+            if A[i, j] != 0:
+                cols.append(j); rvals.append(A[i, j])
+            if A[j, i] != 0:
+                rows.append(j); cvals.append(A[j, i])
+        rptrs.append(len(cols)); cptrs.append(len(rows))
+    got = sp.approx_trials_dense(A, n, scaling=True, scale_intervals=3, scale_times=4, seed=77, first=0, count=30)
+    for t in range(30):
+        assert got[t] == oracle.scaling_trial(rptrs, cols, cptrs, rows, n, 3, 4, 77, t, rvals=rvals, cvals=cvals)
+    got = sp.approx_trials_dense(A, n, scaling=False, seed=77, first=10, count=30)
+    for t in range(30):
+        assert got[t] == oracle.rasmussen_trial(rptrs, cols, n, 77, 10 + t)
+
+
 def test_dead_ends_and_errors(sp):
     # a pattern with an empty row: every trial is 0
     pat = np.ones((5, 5)); pat[2, :] = 0
