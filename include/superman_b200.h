@@ -87,6 +87,10 @@ int  sp_matrix_compress(sp_matrix *m, int preprocessing);
 /* gridGraph2compressed (util.h:403-520): biadjacency matrix of the m x n grid, nov = m*n/2,
  * with CRS and CCS.  Fails when both dimensions are odd. */
 int  sp_matrix_grid(int m, int n, sp_matrix *out);
+/* Degree-0/1/2 compression (exact; the revised front-end's d1compress / d2compress,
+ * revised_perman/util.h:1199-1407): shrinks m in place, perm(original) = *factor * perm(reduced).
+ * Returns the number of rows removed (>= 0) or a negative SP_E* code; drops CRS/CCS. */
+int  sp_matrix_reduce(sp_matrix *m, double *factor);
 void sp_matrix_free(sp_matrix *m);
 
 /* ---------------------------------------------------------------------------------------------

@@ -112,6 +112,7 @@ _sig("sp_matrix_read", C.c_int, [C.c_char_p, C.c_int, _mp])
 _sig("sp_matrix_from_dense", C.c_int, [_dp, C.c_int, _mp])
 _sig("sp_matrix_compress", C.c_int, [_mp, C.c_int])
 _sig("sp_matrix_grid", C.c_int, [C.c_int, C.c_int, _mp])
+_sig("sp_matrix_reduce", C.c_int, [_mp, _dp])
 _sig("sp_matrix_free", None, [_mp])
 
 

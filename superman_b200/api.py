@@ -100,6 +100,14 @@ class Matrix:
             raise SupermanError(rc, _ffi.last_error())
         return self
 
+    def reduce(self) -> float:
+        """degree-0/1/2 compression in place; returns the factor with perm(original) = factor * perm(self)"""
+        f = C.c_double(1.0)
+        rc = lib.sp_matrix_reduce(C.byref(self._m), C.byref(f))
+        if rc < 0:
+            raise SupermanError(rc, _ffi.last_error())
+        return f.value
+
     # -- views (copies) ------------------------------------------------------------------------
     nov = property(lambda self: self._m.nov)
     nnz = property(lambda self: self._m.nnz)

@@ -8,7 +8,8 @@
  * -g) are the reference's algo.h paths and are NOT provided here (BASELINE.json: "no CPU
  * fallback"): they exit with status 1 and a message.  With -g, -c only meant "a CPU thread also
  * pulls chunks" (main.cu:66); it is accepted and ignored.
- * Extra, off by default: the environment variable PERMAN_PRECISION=<digits> adds a second line
+ * Extra, off by default: `--reduce` applies the exact degree-0/1/2 compression of the revised
+ * front-end before the exact algorithms; the environment variable PERMAN_PRECISION=<digits> adds a second line
  * `Result17: <name> <value>` with that many significant digits (the reference prints 6).
  */
 #define _POSIX_C_SOURCE 200809L
@@ -63,6 +64,8 @@ static int report_failure(void) {
   return 1;
 }
 
+static double g_factor = 1.0;   /* --reduce: perm(original) = g_factor * perm(reduced) */
+
 static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int threads, int cpu, int dense,
                       int approximation, int number_of_times, int scale_intervals, int scale_times) {
   sp_stats st;
@@ -88,7 +91,7 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
       }
       if (perman_algo < 0 || perman_algo > 6) { printf("Unknown Algorithm ID\n"); return 0; }
       start = now_s();
-      perman = sp_dense_ryser(m->mat, nov, perman_algo, gpu_num, cpu, threads, &st);
+      perman = g_factor * sp_dense_ryser(m->mat, nov, perman_algo, gpu_num, cpu, threads, &st);
       if (isnan(perman) && st.error) return report_failure();
       print_kernel_lines(&st);
       result_cout(names[perman_algo], perman, now_s() - start);
@@ -134,6 +137,7 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
       else
         perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, nov, perman_algo, gpu_num, cpu, threads, &st);
       if (isnan(perman) && st.error) return report_failure();
+      perman *= g_factor;
       print_kernel_lines(&st);
       result_cout(name, perman, now_s() - start);
     } else {
@@ -217,6 +221,7 @@ int main(int argc, char **argv) {
   int perman_algo = 1, preprocessing = 0;            /* main.cu:335-336 */
   int number_of_times = 100000, scale_intervals = 4, scale_times = 5;   /* main.cu:338-340 */
   int grid_graph = 0, gridm = 36, gridn = 36;        /* main.cu:342-344 */
+  int reduce = 0;                                    /* --reduce: not a reference flag, off by default */
 
   static const char *short_options = "bsr:t:f:gd:cap:x:y:z:im:n:";
   static const struct option long_options[] = {
@@ -225,7 +230,7 @@ int main(int argc, char **argv) {
       {"device", 1, NULL, 'd'},        {"cpu", 0, NULL, 'c'},          {"approximation", 0, NULL, 'a'},
       {"perman", 1, NULL, 'p'},        {"numOfTimes", 1, NULL, 'x'},   {"scaleIntervals", 1, NULL, 'y'},
       {"scaleTimes", 1, NULL, 'z'},    {"grid", 0, NULL, 'i'},         {"gridm", 1, NULL, 'm'},
-      {"gridn", 1, NULL, 'n'},         {NULL, 0, NULL, 0}};
+      {"gridn", 1, NULL, 'n'},         {"reduce", 0, NULL, 1000},      {NULL, 0, NULL, 0}};
 
   int opt;
   while ((opt = getopt_long(argc, argv, short_options, long_options, NULL)) != -1) {
@@ -252,6 +257,7 @@ int main(int argc, char **argv) {
       case 'i': grid_graph = 1; break;
       case 'm': gridm = atoi(optarg); break;
       case 'n': gridn = atoi(optarg); break;
+      case 1000: reduce = 1; break;
       case '?': return 1;
       default: abort();
     }
@@ -283,6 +289,13 @@ int main(int argc, char **argv) {
 
   sp_matrix m;
   if (sp_matrix_read(filename, !generic, &m) != SP_OK) return report_failure();
+  if (reduce && !approximation) {
+    /* degree-0/1/2 compression (revised_perman/util.h:1199-1407): exact, shrinks n before the
+     * exponential kernel; the result line reports the permanent of the ORIGINAL matrix */
+    const int before = m.nov;
+    if (sp_matrix_reduce(&m, &g_factor) < 0) { sp_matrix_free(&m); return report_failure(); }
+    printf("Reduced: nov %d -> %d\n", before, m.nov);
+  }
   if (sp_matrix_compress(&m, preprocessing) != SP_OK) { sp_matrix_free(&m); return report_failure(); }
   const int rc = run_matrix(&m, perman_algo, gpu_num, threads, cpu, dense, approximation, number_of_times,
                             scale_intervals, scale_times);

@@ -108,3 +108,12 @@ def test_dense_approximation_on_file(files):
         got_name, v = result_of(r.stdout)
         assert got_name == name
         assert v == pytest.approx(float(e["i128_binary"]), rel=0.25)
+
+
+def test_reduce_flag(files):
+    for path, e in files[5:9]:
+        for extra in ((), ("-s", "-r", "1", "-p", "4"), ("-s", "-r", "2", "-p", "7")):
+            r = run("-f", path, "--reduce", *(extra or ("-p", "4")), env={"PERMAN_PRECISION": "17"})
+            assert r.returncode == 0, r.stderr
+            assert re.search(r"^Reduced: nov %d -> \d+$" % e["n"], r.stdout, flags=re.M)
+            assert result_of(r.stdout)[1] == pytest.approx(e["ld"], rel=1e-9)

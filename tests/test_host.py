@@ -89,6 +89,38 @@ def test_matrix_market_reader(sp, tmp_path):
             sp.Matrix.read(str(q))
 
 
+def test_degree_compression_preserves_the_permanent(sp, oracle):
+    rng = np.random.default_rng(11)
+    shrunk = 0
+    for trial in range(40):
+        n = int(rng.integers(4, 15))
+        pat = rng.random((n, n)) < rng.choice([0.15, 0.25, 0.4])
+        pat[np.arange(n), rng.permutation(n)] = True
+        A = pat * rng.integers(1, 4, (n, n)).astype(float)
+        want = oracle.perm_ld(A)
+        m = sp.Matrix.from_dense(A)
+        f = m.reduce()
+        k = m.nov
+        assert 1 <= k <= n
+        shrunk += n - k
+        R = m.mat
+        got = f * (oracle.perm_ld(R) if k > 1 else R[0, 0])
+        assert got == pytest.approx(want, rel=1e-12, abs=1e-9), (trial, n, k)
+        if k > 2:   # nothing of degree <= 2 is left
+            assert ((R != 0).sum(axis=0) >= 3).all() and ((R != 0).sum(axis=1) >= 3).all()
+        m.compress(1)                      # CRS / CCS can be rebuilt on the reduced matrix
+        assert m.nnz == int((R > 0).sum())
+    assert shrunk > 40
+    # empty row -> 0; grid graphs (degrees 2..4) collapse a long way
+    Z = np.ones((5, 5)); Z[3, :] = 0
+    m = sp.Matrix.from_dense(Z)
+    assert m.reduce() == 0.0 and m.nov == 1
+    g = sp.Matrix.grid(4, 6)
+    f = g.reduce()
+    assert f * (oracle.perm_ld(g.mat) if g.nov > 1 else g.mat[0, 0]) == pytest.approx(281.0, rel=1e-12)
+    assert g.nov < 12
+
+
 def test_grid_matches_reference_golden(sp):
     for g in _golden.grids():
         m = sp.Matrix.grid(g["m"], g["n"])
