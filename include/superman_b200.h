@@ -55,6 +55,8 @@ typedef struct sp_stats {
 const char *sp_last_error(void);
 int         sp_device_count(void);
 const char *sp_version(void);
+/* create contexts / streams / buffers of devices 0..gpu_num-1 ahead of time (optional) */
+int         sp_warmup(int gpu_num);
 
 /* ---------------------------------------------------------------------------------------------
  * Matrix input and preprocessing (host, C): what main.cu does before RunAlgo.
