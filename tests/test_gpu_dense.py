@@ -169,6 +169,13 @@ def test_n36_properties(sp):
     p0 = sp.dense_ryser(A, n, 4, stats=st)
     assert st.units == 1 << 35 and st.path == 1
     assert math.isfinite(p0) and p0 > 0
+    # the headline workload itself against the long-double oracle (tests/golden/bench36.json, made by
+    # tests/golden/make_bench_golden.py: 2^35 indices in x87 long double, 17 min on 8 cores)
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bench36.json")))
+    assert g["n"] == 36 and g["checksum"] == float(A.sum())
+    assert p0 == pytest.approx(g["ld"], rel=REL)
+    assert abs(p0 / g["ld"] - 1.0) < 2e-10           # observed 3e-11
     rng = np.random.default_rng(1)
     assert sp.dense_ryser(A.T.copy(), n, 4) == pytest.approx(p0, rel=REL)
     assert sp.dense_ryser(A[rng.permutation(n)][:, rng.permutation(n)].copy(), n, 4) == pytest.approx(p0, rel=REL)
