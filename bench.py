@@ -53,6 +53,17 @@ def synthetic_matrix(n: int, density: float, instance: int = 0):
     return (pat * val).astype(np.float64)
 
 
+def golden_rel_err(n: int, value: float):
+    """relative difference to the committed long-double oracle value of this very workload
+    (tests/golden/bench<n>.json, a number in a fixture file -- nothing of oracle/ runs here)"""
+    p = os.path.join(ROOT, "tests", "golden", "bench%d.json" % n)
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        g = json.load(f)
+    return abs(value / g["ld"] - 1.0)
+
+
 def rank_slice(total: int, rank: int, world: int, align_log2: int = ALIGN_LOG2):
     """Contiguous slice of [0, total) for `rank`, boundaries rounded down to 2^align_log2
     (same rule as sp_sched_boundary in superman_b200/host/sp_sched.c)."""
@@ -420,6 +431,7 @@ def main():
             },
             "seconds_per_permanent": dev_ms_max / args.steps * 1e-3,
             "permanent": perm_resident, "permanent_e2e": perm_e2e,
+            "permanent_rel_err_vs_long_double_golden": golden_rel_err(n, perm_resident),
             "wall_ms_per_step_resident_incl_flush": 1e3 * wall_resident / args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
