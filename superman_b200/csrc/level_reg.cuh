@@ -202,11 +202,10 @@ level_reg_kernel(const LevelArgs a) {
         }
       } else {
         // ---- hot slots: level L = slot / S takes 2^(B-L) values ----
-        double PL[2 * NB];                       // PL[L][w] at PL[(NB >> L) + w] ... packed below
+        double PL[2 * NB];
         // layout: level L occupies indices [off(L), off(L) + 2^(B-L)), off(L) = 2*NB - 2*(NB >> L)
 #pragma unroll
         for (int i = 0; i < HS; ++i) {
-          constexpr int dummy = 0; (void)dummy;
           const int L = i / S;                   // compile-time after unrolling
           const int off = 2 * NB - 2 * (NB >> L);
           const int cnt = NB >> L;
