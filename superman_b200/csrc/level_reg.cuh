@@ -10,6 +10,8 @@
 //     level's 2^(B-L) running products PL[L][.] instead of 2^B of each; the 2^B terms of a block are
 //     recombined as  term_u = PL[0][u] * PL[1][u>>1] * ... * PL[B-1][u>>(B-1)] * Q.
 //     Everything here is compile-time structured: straight-line code, no runtime branch.
+//   register-cold rows: the R cold rows of lowest level (the ones refreshed most often) also stay
+//     in registers: one update and one multiply per block, in straight-line code.
 //   cold rows (level >= B): X in shared memory (X[row][thread], conflict-free), sorted by level.
 //     Their product Q is kept as suffix products SP[i] = prod(rows of level >= B+i): the block that
 //     flips high column k only touches the rows of level <= k, refreshes SP[k-B .. 0] and reuses
@@ -31,10 +33,10 @@ namespace spb {
 
 struct LevelArgs {
   // packed device image (doubles unless noted), see sp_sparse.cu: level_pack()
-  const double* colT_hot;    // [(n-1) * HSP]   colT_hot[k*HSP + s]  = D[slot s][k]
+  const double* colT_hot;    // [(n-1) * HSP]   colT_hot[k*HSP + s]  = D[slot s][k]   (hot slots, then R register-cold)
   const double* lowR;        // [HS * LB]       lowR[s*LB + q]       = D[slot s][q], q < B
   const double* dcold;       // [(n-1) * NCP]   dcold[k*NCP + jc]    = D[cold row jc][k]
-  const double* xb_hot;      // [HS]
+  const double* xb_hot;      // [HS + R]
   const double* xb_cold;     // [NC]
   const int* cold_start;     // [n - B + 2]     first cold row of level >= B+i
   double* partials;
@@ -45,20 +47,21 @@ struct LevelArgs {
   int tiles_per_warp;
 };
 
-template <int B, int S>
+template <int B, int S, int R>
 struct LevelLayout {
-  static constexpr int HS = B * S;
-  static constexpr int HSP = HS + (HS & 1);
+  static constexpr int HS = B * S;           // level slots
+  static constexpr int HT = HS + R;          // + register-cold rows
+  static constexpr int HSP = HT + (HT & 1);
   static constexpr int LB = B + (B & 1);
 };
 
 // dynamic shared memory (doubles):  colT_hot | lowR | dcold | xb_hot | xb_cold | Xc[NC][T] | SP[c-B+1][T]
 // then ints: cold_start
-template <int B, int S, int THREADS, int MINBLOCKS, bool SKIP>
+template <int B, int S, int R, int THREADS, int MINBLOCKS, bool SKIP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 level_reg_kernel(const LevelArgs a) {
-  using LL = LevelLayout<B, S>;
-  constexpr int HS = LL::HS, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
+  using LL = LevelLayout<B, S, R>;
+  constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
   extern __shared__ __align__(16) double dsm[];
   const int n = a.n, NC = a.NC, NCP = a.NCP, c = a.c;
   const int nseg = c - B;                       // SP[0 .. nseg]
@@ -77,7 +80,7 @@ level_reg_kernel(const LevelArgs a) {
   for (int e = threadIdx.x; e < (n - 1) * HSP; e += THREADS) s_colT[e] = a.colT_hot[e];
   for (int e = threadIdx.x; e < HS * LB; e += THREADS) s_lowR[e] = a.lowR[e];
   for (int e = threadIdx.x; e < (n - 1) * NCP; e += THREADS) s_dcold[e] = a.dcold[e];
-  for (int e = threadIdx.x; e < HS; e += THREADS) s_xbh[e] = a.xb_hot[e];
+  for (int e = threadIdx.x; e < HT; e += THREADS) s_xbh[e] = a.xb_hot[e];
   for (int e = threadIdx.x; e < NC; e += THREADS) s_xbc[e] = a.xb_cold[e];
   for (int e = threadIdx.x; e < n - B + 2; e += THREADS) s_cs[e] = a.cold_start[e];
   __syncthreads();
@@ -130,14 +133,14 @@ level_reg_kernel(const LevelArgs a) {
     // ---- explicit X at the tile start (cf. gpu_exact_sparse.cu:497-503) -------------------------
     const unsigned long long s = (a.tile_first + my_tile) << c;
     const unsigned long long g = s ^ (s >> 1);
-    double xh[HS];
+    double xh[HT];
 #pragma unroll
-    for (int i = 0; i < HS; ++i) xh[i] = s_xbh[i];
+    for (int i = 0; i < HT; ++i) xh[i] = s_xbh[i];
     for (int k = c - 1; k < n - 1; ++k) {
       const double f = (double)((g >> k) & 1ull);
       const double* col = s_colT + k * HSP;
 #pragma unroll
-      for (int i = 0; i < HS; ++i) xh[i] = fma(f, col[i], xh[i]);
+      for (int i = 0; i < HT; ++i) xh[i] = fma(f, col[i], xh[i]);
     }
     {
       // cold rows, from the last (highest level) to the first, building the suffix products
@@ -190,6 +193,18 @@ level_reg_kernel(const LevelArgs a) {
       }
 
       const uint32_t hi_addr = sm_colT + (uint32_t)(k * HSP * 8);
+      // ---- register-cold rows: one update, one multiply ----
+      if (R > 0) {
+        double r0 = 1.0, r1 = 1.0;
+#pragma unroll
+        for (int i = HS; i < HT; ++i) {
+          double d;
+          lds_f64(hi_addr + (uint32_t)(i * 8), d);
+          xh[i] = fma(sg, d, xh[i]);
+          if (i & 1) r1 *= xh[i]; else r0 *= xh[i];
+        }
+        Q *= r0 * r1;
+      }
       const bool skip_blk = SKIP && __all_sync(0xffffffffu, !active || Q == 0.0);
       if (skip_blk) {
         // exact zeros: only the block's net effect on the hot slots (high column + column B-1)

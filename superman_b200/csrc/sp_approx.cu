@@ -315,7 +315,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     set_error("approx plan upload: %s", cudaGetErrorString(e));
     return fail(SPD_ECUDA);
   }
-  if (p->smem_bytes > 48 * 1024) {
+  if (p->smem_bytes > 40 * 1024) {
     e = p->weighted ? cudaFuncSetAttribute(approx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes)
                     : cudaFuncSetAttribute(approx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->smem_bytes, cudaGetErrorString(e)); return fail(SPD_ECUDA); }

@@ -10,12 +10,12 @@
 
 namespace spb {
 
-template <int B, int S, bool SKIP>
+template <int B, int S, int R, bool SKIP>
 static int launch_level(cudaStream_t st, const LevelArgs& a, unsigned blocks, size_t smem) {
-  // registers: X of the hot slots 2*B*S, level products 2*(2^(B+1)-2): 128 registers up to 16 slots
-  constexpr int MB = (B * S <= 16) ? 4 : 3;
-  auto kern = level_reg_kernel<B, S, SPB_REG_THREADS, MB, SKIP>;
-  if (smem > 48 * 1024) {
+  // registers: X of the slots 2*(B*S + R), level products 2*(2^(B+1)-2): 128 registers up to 16 slots
+  constexpr int MB = (B * S + R <= 16) ? 4 : 3;
+  auto kern = level_reg_kernel<B, S, R, SPB_REG_THREADS, MB, SKIP>;
+  if (smem > 40 * 1024) {   // static shared memory (queue, partials) counts against the 48 KiB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return SPD_ECUDA; }
   }
@@ -26,17 +26,19 @@ static int launch_level(cudaStream_t st, const LevelArgs& a, unsigned blocks, si
 #define SPB_GLUE3(a, b, c, d) a##b##c##d
 #define SPB_GLUE(a, b, c, d) SPB_GLUE3(a, b, c, d)
 
-extern "C" int SPB_GLUE(spb_level_launch_b, SPB_LV_B, _s, SPB_LV_SKIP)(int S, cudaStream_t st, const LevelArgs* a,
+#define SPB_LV_CASE(S_)                                                              \
+  case S_:                                                                           \
+    if (R == 0) return launch_level<B, S_, 0, SKIP>(st, *a, blocks, smem);           \
+    if (R == 4) return launch_level<B, S_, 4, SKIP>(st, *a, blocks, smem);           \
+    if (R == 8) return launch_level<B, S_, 8, SKIP>(st, *a, blocks, smem);           \
+    return SPD_ELIMIT;
+
+extern "C" int SPB_GLUE(spb_level_launch_b, SPB_LV_B, _s, SPB_LV_SKIP)(int S, int R, cudaStream_t st, const LevelArgs* a,
                                                                       unsigned blocks, size_t smem) {
   constexpr int B = SPB_LV_B;
   constexpr bool SKIP = SPB_LV_SKIP != 0;
   switch (S) {
-    case 1: return launch_level<B, 1, SKIP>(st, *a, blocks, smem);
-    case 2: return launch_level<B, 2, SKIP>(st, *a, blocks, smem);
-    case 3: return launch_level<B, 3, SKIP>(st, *a, blocks, smem);
-    case 4: return launch_level<B, 4, SKIP>(st, *a, blocks, smem);
-    case 6: return launch_level<B, 6, SKIP>(st, *a, blocks, smem);
-    case 8: return launch_level<B, 8, SKIP>(st, *a, blocks, smem);
+    SPB_LV_CASE(1) SPB_LV_CASE(2) SPB_LV_CASE(3) SPB_LV_CASE(4) SPB_LV_CASE(6) SPB_LV_CASE(8)
     default: return SPD_ELIMIT;
   }
 }

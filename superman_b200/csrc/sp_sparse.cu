@@ -23,17 +23,17 @@ SPB_DECL(0) SPB_DECL(1) SPB_DECL(2) SPB_DECL(3) SPB_DECL(4) SPB_DECL(5) SPB_DECL
 }
 
 extern "C" {
-int spb_level_launch_b3_s0(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
-int spb_level_launch_b3_s1(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
-int spb_level_launch_b4_s0(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
-int spb_level_launch_b4_s1(int S, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+int spb_level_launch_b3_s0(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+int spb_level_launch_b3_s1(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+int spb_level_launch_b4_s0(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+int spb_level_launch_b4_s1(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
 }
 
 using namespace spb;
 
-static int level_launch(int B, int S, int skip, cudaStream_t st, const LevelArgs* a, unsigned blocks, size_t smem) {
-  if (B == 3) return skip ? spb_level_launch_b3_s1(S, st, a, blocks, smem) : spb_level_launch_b3_s0(S, st, a, blocks, smem);
-  if (B == 4) return skip ? spb_level_launch_b4_s1(S, st, a, blocks, smem) : spb_level_launch_b4_s0(S, st, a, blocks, smem);
+static int level_launch(int B, int S, int R, int skip, cudaStream_t st, const LevelArgs* a, unsigned blocks, size_t smem) {
+  if (B == 3) return skip ? spb_level_launch_b3_s1(S, R, st, a, blocks, smem) : spb_level_launch_b3_s0(S, R, st, a, blocks, smem);
+  if (B == 4) return skip ? spb_level_launch_b4_s1(S, R, st, a, blocks, smem) : spb_level_launch_b4_s0(S, R, st, a, blocks, smem);
   return SPD_ELIMIT;
 }
 
@@ -58,7 +58,7 @@ struct spd_sparse_plan {
   double* d_xbase = nullptr;
   std::vector<int> level;      // sorted ascending: level[j] of the row now at position j
   // LevelRyser image (level_reg.cuh); lvB == 0 when the matrix does not fit its slots
-  int lvB = 0, lvS = 0, NC = 0, NCP = 0, HSP = 0;
+  int lvB = 0, lvS = 0, lvR = 0, NC = 0, NCP = 0, HSP = 0;
   double lv_cost = 1e300, hc_cost = 1e300;
   double *d_colT_hot = nullptr, *d_lowR = nullptr, *d_dcold = nullptr, *d_xb_hot = nullptr, *d_xb_cold = nullptr;
   int* d_cold_start = nullptr;
@@ -83,12 +83,12 @@ static double hotcold_cost(const spd_sparse_plan* p, int B) {
 // Packs the rows into the LevelRyser layout for (B, S): S register slots per level < B, the other
 // rows cold, sorted by level.  lvl[] / dmat_t / xbase are in the ORIGINAL row order.  Returns
 // false when some level has more rows than the slots at or below it can take.
-static bool level_pack(int n, int B, int S, const std::vector<int>& lvl, const double* dmat_t,
+static bool level_pack(int n, int B, int S, int R, const std::vector<int>& lvl, const double* dmat_t,
                        const double* xbase, std::vector<double>& colT_hot, std::vector<double>& lowR,
                        std::vector<double>& dcold, std::vector<double>& xb_hot, std::vector<double>& xb_cold,
                        std::vector<int>& cold_start, int* NC_out, double* cost_out) {
-  const int HS = B * S, HSP = HS + (HS & 1), LB = B + (B & 1);
-  std::vector<int> slot_row(HS, -1);
+  const int HS = B * S, HT = HS + R, HSP = HT + (HT & 1), LB = B + (B & 1);
+  std::vector<int> slot_row(HT, -1);
   std::vector<int> order(n);
   for (int j = 0; j < n; ++j) order[j] = j;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lvl[a] < lvl[b]; });
@@ -104,18 +104,23 @@ static bool level_pack(int n, int B, int S, const std::vector<int>& lvl, const d
     if (placed < 0) return false;
     slot_row[placed] = j;
   }
+  // the R cold rows of lowest level (refreshed most often) stay in registers too
+  const int nrc = std::min(R, (int)cold.size());
+  for (int t = 0; t < nrc; ++t) slot_row[HS + t] = cold[t];
+  cold.erase(cold.begin(), cold.begin() + nrc);
   const int NC = (int)cold.size(), NCP = NC + (NC & 1) + ((NC == 0) ? 2 : 0);
   colT_hot.assign((size_t)(n - 1) * HSP, 0.0);
   lowR.assign((size_t)HS * LB, 0.0);
   dcold.assign((size_t)(n - 1) * NCP, 0.0);
   xb_hot.assign(HSP, 1.0);
   xb_cold.assign(NCP, 1.0);
-  for (int sl = 0; sl < HS; ++sl) {
+  for (int sl = 0; sl < HT; ++sl) {
     const int j = slot_row[sl];
     if (j < 0) continue;                          // neutral slot: x = 1, all entries 0
     xb_hot[sl] = xbase[j];
     for (int k = 0; k < n - 1; ++k) colT_hot[(size_t)k * HSP + sl] = dmat_t[(size_t)k * n + j];
-    for (int q = 0; q < B; ++q) lowR[(size_t)sl * LB + q] = dmat_t[(size_t)q * n + j];
+    if (sl < HS)
+      for (int q = 0; q < B; ++q) lowR[(size_t)sl * LB + q] = dmat_t[(size_t)q * n + j];
   }
   cold_start.assign(n - B + 2, NC);
   for (int jc = NC - 1; jc >= 0; --jc) {
@@ -137,7 +142,7 @@ static bool level_pack(int n, int B, int S, const std::vector<int>& lvl, const d
   for (int L = 0; L < B; ++L) hot += (double)S * 2.0 * (double)(1 << (B - L));
   double coldc = 0.0, w = 0.5;
   for (int z = 0; z < 16 && B + z <= n; ++z, w *= 0.5) coldc += w * 3.0 * (double)cold_start[(z + 1 <= n - B + 1) ? z + 1 : n - B + 1];
-  const double per_block = hot + (double)((2 << B) - 2) + (double)(1 << B) + coldc;
+  const double per_block = hot + 2.0 * R + (double)((2 << B) - 2) + (double)(1 << B) + coldc;
   *cost_out = per_block / (double)(1 << B);
   *NC_out = NC;
   return true;
@@ -225,8 +230,8 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
                            (size_t)p->NC * SPB_REG_THREADS + (size_t)(c - B + 1) * SPB_REG_THREADS;
         const size_t smem = dbl * sizeof(double) + (size_t)(n - B + 2) * sizeof(int);
         if (smem > 220 * 1024) { set_error("level engine needs %zu B of shared memory", smem); return SPD_ELIMIT; }
-        rc = level_launch(p->lvB, p->lvS, p->skip, L.stream, &la, (unsigned)blocks, smem);
-        if (rc != SPD_OK) { if (rc == SPD_ELIMIT) set_error("no level kernel for B=%d S=%d", p->lvB, p->lvS); return rc; }
+        rc = level_launch(p->lvB, p->lvS, p->lvR, p->skip, L.stream, &la, (unsigned)blocks, smem);
+        if (rc != SPD_OK) { if (rc == SPD_ELIMIT) set_error("no level kernel for B=%d S=%d R=%d", p->lvB, p->lvS, p->lvR); return rc; }
       } else {
         SparseArgs a;
         a.mat_t = p->d_mat_t; a.xbase = p->d_xbase;
@@ -327,24 +332,31 @@ int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase
     for (int B = 3; B <= 4; ++B) {
       if (B + 2 > n - 1) continue;
       if (forceB && forceB != B) continue;
+      const int forceR = env_int("SP_LEVEL_REGCOLD", -1);
       for (int si = 0; si < 6; ++si) {
         if (forceS && forceS != s_opts[si]) continue;
-        std::vector<double> h, l, d, xh, xc;
-        std::vector<int> cs;
-        int NC = 0;
-        double cost = 0;
-        if (!level_pack(n, B, s_opts[si], lvl, dmat_t, xbase, h, l, d, xh, xc, cs, &NC, &cost)) continue;
-        cost *= 1.15;
-        if (cost < p->lv_cost) {
-          p->lv_cost = cost; p->lvB = B; p->lvS = s_opts[si]; p->NC = NC;
-          bh.swap(h); bl.swap(l); bd.swap(d); bxh.swap(xh); bxc.swap(xc); bcs.swap(cs);
+        bool fits = false;
+        for (int R = 0; R <= 8; R += 4) {
+          if (forceR >= 0 && forceR != R) continue;
+          std::vector<double> h, l, d, xh, xc;
+          std::vector<int> cs;
+          int NC = 0;
+          double cost = 0;
+          if (!level_pack(n, B, s_opts[si], R, lvl, dmat_t, xbase, h, l, d, xh, xc, cs, &NC, &cost)) break;
+          fits = true;
+          cost *= 1.15;
+          if (B * s_opts[si] + R > 16) cost *= 1.1;      // 3 instead of 4 blocks per SM
+          if (cost < p->lv_cost) {
+            p->lv_cost = cost; p->lvB = B; p->lvS = s_opts[si]; p->lvR = R; p->NC = NC;
+            bh.swap(h); bl.swap(l); bd.swap(d); bxh.swap(xh); bxc.swap(xc); bcs.swap(cs);
+          }
         }
-        break;   // a larger S for the same B only costs more
+        if (fits) break;   // a larger S for the same B only costs more
       }
     }
     if (p->lvB && (engine == 2 || p->lv_cost < p->hc_cost || n > SPB_SPARSE_NMAX)) {
-      const int HS = p->lvB * p->lvS;
-      p->HSP = HS + (HS & 1);
+      const int HT = p->lvB * p->lvS + p->lvR;
+      p->HSP = HT + (HT & 1);
       p->NCP = (int)bxc.size();
       auto up = [&](const void* src, size_t bytes, void** dst) -> int {
         int r = lane_arena_alloc(&L, bytes ? bytes : 8, dst);

@@ -98,3 +98,23 @@ def test_sparse_above_48_rows(sp, oracle):
         for skip in (False, True):
             got = sp.sparse_ryser_range(m.mat, m.cptrs, m.rows, m.cvals, lo, hi, n, skipper=skip)
             assert got == pytest.approx(want, rel=1e-9, abs=1e-13 * sc), (n, skip)
+
+
+def test_every_order_30_to_50_short_range(sp, oracle):
+    """sweeps n (and with it every shared-memory footprint of the sparse engines, including the ones
+    just under the 48 KiB default limit) on a short range of Gray indices"""
+    rng = np.random.default_rng(8)
+    for n in range(30, 51):
+        pat = rng.random((n, n)) < 4.0 / n
+        pat[np.arange(n), rng.permutation(n)] = True
+        A = pat * rng.integers(1, 4, (n, n)).astype(float)
+        sc = float(np.prod(np.maximum(np.abs(A).sum(axis=1), 1)))
+        for pre in (1, 2):
+            m = sp.Matrix.from_dense(A).compress(pre)
+            lo, hi = 1 << 15, (1 << 15) + (1 << 16)
+            want = oracle.sparyser_range(m.mat, m.cptrs, m.rows, m.cvals, lo, hi)
+            for skip in (False, True):
+                got = sp.sparse_ryser_range(m.mat, m.cptrs, m.rows, m.cvals, lo, hi, n, skipper=skip)
+                assert got == pytest.approx(want, rel=1e-9, abs=1e-13 * sc), (n, pre, skip)
+            wantd = oracle.ryser_range_ld(A, lo, hi)
+            assert sp.dense_ryser_range(A, lo, hi, n) == pytest.approx(wantd, rel=1e-9, abs=1e-13 * sc), n
