@@ -10,6 +10,7 @@
 #include "util.h"
 #include "gpu_exact_dense.cu"
 #include "gpu_exact_sparse.cu"
+#include "gpu_approximation_sparse.cu"
 
 extern "C" {
 
@@ -42,6 +43,18 @@ double ref_gpu_sparse_multigpu(const double* mat, const int* cptrs, const int* r
                                int nov, int gpu_num, int grid_dim, int block_dim) {
   return gpu_perman64_xshared_coalescing_mshared_multigpu_sparse((double*)mat, (int*)cptrs, (int*)rows,
                                                                  (double*)cvals, nov, gpu_num, grid_dim, block_dim);
+}
+// gpu_approximation_sparse.cu:497 / 663 with gpu_num devices: every launch runs 1024 x 1024 trials
+// (the reference's own granularity), so number_of_times is effectively rounded up to 2^20 per launch
+double ref_gpu_rasmussen_chunks_sparse(const int* cptrs, const int* rows, const int* rptrs, const int* cols,
+                                       int nov, int nnz, int number_of_times, int gpu_num) {
+  return gpu_perman64_rasmussen_multigpucpu_chunks_sparse((int*)cptrs, (int*)rows, (int*)rptrs, (int*)cols, nov, nnz,
+                                                          number_of_times, gpu_num, false, 1, true);
+}
+double ref_gpu_scaling_chunks_sparse(const int* cptrs, const int* rows, const int* rptrs, const int* cols,
+                                     int nov, int nnz, int number_of_times, int gpu_num, int y, int z) {
+  return gpu_perman64_approximation_multigpucpu_chunks_sparse((int*)cptrs, (int*)rows, (int*)rptrs, (int*)cols, nov, nnz,
+                                                              number_of_times, gpu_num, false, y, z, 1, true);
 }
 int ref_gpu_max_threads() { return omp_get_max_threads(); }
 

@@ -26,6 +26,7 @@
 #include "sp_internal.cuh"
 #include <string.h>
 #include <new>
+#include <vector>
 
 namespace spb {
 
@@ -237,6 +238,173 @@ approx_kernel(const ApproxArgs a) {
   }
 }
 
+
+// ---- thread-per-trial variant for nov <= 64 -----------------------------------------------------
+// With at most 64 rows and columns a row's pattern is one 64-bit word: the remaining degree of a
+// row is popc(rowmask[r] & ~colx), read from shared memory at a warp-uniform address (broadcast),
+// the two "extracted" sets live in two registers, and one THREAD runs a trial -- 32 trials per warp
+// instead of one.  Lanes are persistent: a lane whose trial ends (dead end or last step) starts
+// its next trial in the following loop trip, so the warp stays full until the range is exhausted.
+// Same estimators, same Philox stream, same order of every floating-point operation as the
+// warp-per-trial kernel above and as the oracle (per-trial values are bit-identical).
+#define APS_THREADS 128
+
+struct SmallArgs {
+  const unsigned long long* rowmask;   // [nov] columns of row r
+  const unsigned long long* colmask;   // [nov] rows of column c
+  const double* wdense;                // [nov*nov] entry weights (scaled dense twin) or nullptr
+  double* partial_sum;
+  double* partial_sq;
+  unsigned long long trial_lo, trial_hi;
+  unsigned long long seed;
+  double sq_scale;
+  int nov;
+  int scaling, scale_intervals, scale_times;
+};
+
+template <bool SCALING, bool WEIGHTED>
+__global__ void __launch_bounds__(APS_THREADS)
+approx_small_kernel(const SmallArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int nov = a.nov;
+  unsigned long long* s_row = reinterpret_cast<unsigned long long*>(smraw);
+  unsigned long long* s_col = s_row + nov;
+  double* s_w = reinterpret_cast<double*>(s_col + nov);                 // WEIGHTED: nov*nov
+  float* s_d = reinterpret_cast<float*>(s_w + (WEIGHTED ? nov * nov : 0));   // SCALING: d_r | d_c, [i][thread]
+  float* d_r = s_d + threadIdx.x;
+  float* d_c = s_d + (size_t)nov * APS_THREADS + threadIdx.x;
+  __shared__ double blk_sum[APS_THREADS / 32], blk_sq[APS_THREADS / 32];
+  for (int e = threadIdx.x; e < nov; e += APS_THREADS) { s_row[e] = a.rowmask[e]; s_col[e] = a.colmask[e]; }
+  if (WEIGHTED) for (int e = threadIdx.x; e < nov * nov; e += APS_THREADS) s_w[e] = a.wdense[e];
+  __syncthreads();
+
+  const unsigned long long total = (unsigned long long)gridDim.x * APS_THREADS;
+  unsigned long long trial = a.trial_lo + (unsigned long long)blockIdx.x * APS_THREADS + threadIdx.x;
+  const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+  double tsum = 0.0, tsq = 0.0, perm = 1.0;
+  unsigned long long rowx = 0ull, colx = 0ull;
+  uint32_t rnd0 = 0, rnd1 = 0, rnd2 = 0, rnd3 = 0;
+  int step = 0;
+
+  for (int it = 0;; ++it) {
+    const bool have = trial < a.trial_hi;
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (!have) continue;
+    // scaled estimator: a new trial only starts on a loop trip that is a multiple of the scaling
+    // interval, so the (expensive) Sinkhorn steps of the 32 lanes coincide instead of making every
+    // trip pay for the one lane that happens to be scaling
+    if (SCALING && step == 0 && (it % a.scale_intervals) != 0) continue;
+    if (step == 0) {
+      rowx = 0ull; colx = 0ull; perm = 1.0;
+      if (SCALING) for (int i = 0; i < nov; ++i) { d_r[i * APS_THREADS] = 1.0f; d_c[i * APS_THREADS] = 1.0f; }
+    }
+    if ((step & 3) == 0) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)(step >> 2), 0u, k0, k1, r);
+      rnd0 = r[0]; rnd1 = r[1]; rnd2 = r[2]; rnd3 = r[3];
+    }
+    const int rw = step & 3;
+    const uint32_t draw = (rw == 0) ? rnd0 : (rw == 1) ? rnd1 : (rw == 2) ? rnd2 : rnd3;
+    // ---- minimum-degree remaining row, first in ascending order ----
+    unsigned best = 0xffffffffu;
+    for (int r = 0; r < nov; ++r) {
+      const unsigned d = (unsigned)__popcll(s_row[r] & ~colx);
+      const unsigned key = ((rowx >> r) & 1ull) ? 0xffffffffu : ((d << 8) | (unsigned)r);
+      best = min(best, key);
+    }
+    const int row = (int)(best & 0xffu);
+    const int dmin = (int)(best >> 8);
+    bool dead = (dmin == 0);
+    int col = 0;
+    if (!dead) {
+      const unsigned long long avail = s_row[row] & ~colx;
+      if (!SCALING) {
+        perm *= (double)dmin;
+        const int want = (int)(((uint64_t)draw * (uint64_t)dmin) >> 32);
+        // want-th (0-based) set bit of avail
+        const unsigned lo32 = (unsigned)avail, hi32 = (unsigned)(avail >> 32);
+        const int nlo = __popc(lo32);
+        col = (want < nlo) ? (int)__fns(lo32, 0, want + 1) : 32 + (int)__fns(hi32, 0, want - nlo + 1);
+      } else {
+        if (step % a.scale_intervals == 0) {
+          for (int sweep = 0; sweep < a.scale_times && !dead; ++sweep) {
+            for (int j = 0; j < nov && !dead; ++j) {
+              if ((colx >> j) & 1ull) continue;
+              unsigned long long m = s_col[j] & ~rowx;
+              if (WEIGHTED) {
+                double cs = 0.0;
+                while (m) { const int r = __ffsll((long long)m) - 1; m &= m - 1ull; cs += (double)d_r[r * APS_THREADS] * s_w[r * nov + j]; }
+                if (cs == 0.0) dead = true; else d_c[j * APS_THREADS] = (float)(1.0 / cs);
+              } else {
+                float cs = 0.0f;
+                while (m) { const int r = __ffsll((long long)m) - 1; m &= m - 1ull; cs += d_r[r * APS_THREADS]; }
+                if (cs == 0.0f) dead = true; else d_c[j * APS_THREADS] = 1.0f / cs;
+              }
+            }
+            for (int i = 0; i < nov && !dead; ++i) {
+              if ((rowx >> i) & 1ull) continue;
+              unsigned long long m = s_row[i] & ~colx;
+              if (WEIGHTED) {
+                double rs = 0.0;
+                while (m) { const int cc = __ffsll((long long)m) - 1; m &= m - 1ull; rs += s_w[i * nov + cc] * (double)d_c[cc * APS_THREADS]; }
+                if (rs == 0.0) dead = true; else d_r[i * APS_THREADS] = (float)(1.0 / rs);
+              } else {
+                float rs = 0.0f;
+                while (m) { const int cc = __ffsll((long long)m) - 1; m &= m - 1ull; rs += d_c[cc * APS_THREADS]; }
+                if (rs == 0.0f) dead = true; else d_r[i * APS_THREADS] = 1.0f / rs;
+              }
+            }
+          }
+        }
+        if (!dead) {
+          const float dr = d_r[row * APS_THREADS];
+          double tot = 0.0;
+          unsigned long long m = avail;
+          while (m) { const int cc = __ffsll((long long)m) - 1; m &= m - 1ull; tot += (double)(dr * d_c[cc * APS_THREADS]); }
+          if (tot == 0.0) {
+            dead = true;
+          } else {
+            const double target = ((double)draw + 1.0) * (1.0 / 4294967296.0) * tot;
+            double run = 0.0;
+            bool picked = false;
+            m = avail;
+            while (m) {
+              const int cc = __ffsll((long long)m) - 1; m &= m - 1ull;
+              const double sv = (double)(dr * d_c[cc * APS_THREADS]);
+              run += sv;
+              if (target <= run) { col = cc; perm /= (sv / tot); picked = true; break; }
+            }
+            if (!picked) dead = true;
+          }
+        }
+      }
+    }
+    if (dead) perm = 0.0;
+    else { rowx |= 1ull << row; colx |= 1ull << col; }
+    ++step;
+    if (dead || step == nov) {
+      tsum += perm;
+      const double q = perm * a.sq_scale;
+      tsq += q * q;
+      trial += total;
+      step = 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+    tsq += __shfl_down_sync(0xffffffffu, tsq, o);
+  }
+  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sv = 0.0, qv = 0.0;
+    for (int w = 0; w < APS_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; }
+    a.partial_sum[blockIdx.x] = sv;
+    a.partial_sq[blockIdx.x] = qv;
+  }
+}
+
 }  // namespace spb
 
 using namespace spb;
@@ -252,9 +420,29 @@ struct spd_approx_plan {
   double *d_rvals = nullptr, *d_cvals = nullptr;
   size_t smem_bytes = 0;
   int blocks = 0;
+  // thread-per-trial engine (nov <= 64)
+  bool small = false;
+  unsigned long long *d_rowmask = nullptr, *d_colmask = nullptr;
+  double* d_wdense = nullptr;
+  size_t small_smem = 0;
+  int small_blocks = 0;
   bool pending = false;
   spd_run_info info;
 };
+
+template <typename K>
+static int small_prepare(spd_approx_plan* p, K kern) {
+  cudaError_t e;
+  if (p->small_smem > 40 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->small_smem);
+    if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->small_smem, cudaGetErrorString(e)); return SPD_ECUDA; }
+  }
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, APS_THREADS, p->small_smem);
+  if (e != cudaSuccess || per_sm < 1) { set_error("small approx kernel does not fit on an SM"); return SPD_ECUDA; }
+  p->small_blocks = per_sm * p->lanep->sm_count;
+  return SPD_OK;
+}
 
 extern "C" {
 
@@ -320,6 +508,39 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
                     : cudaFuncSetAttribute(approx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->smem_bytes, cudaGetErrorString(e)); return fail(SPD_ECUDA); }
   }
+  // ---- thread-per-trial engine for nov <= 64: 64-bit pattern words ----
+  if (nov <= 64 && env_int("SP_APPROX_FORCE_WARP", 0) == 0) {
+    unsigned long long rm[64], cm[64];
+    for (int i = 0; i < nov; ++i) {
+      rm[i] = 0ull; cm[i] = 0ull;
+      for (int t = rptrs[i]; t < rptrs[i + 1]; ++t) rm[i] |= 1ull << cols[t];
+      for (int t = cptrs[i]; t < cptrs[i + 1]; ++t) cm[i] |= 1ull << rows[t];
+    }
+    if ((rc = lane_arena_alloc(&L, 64 * 8, (void**)&p->d_rowmask)) != SPD_OK) return fail(rc);
+    if ((rc = lane_arena_alloc(&L, 64 * 8, (void**)&p->d_colmask)) != SPD_OK) return fail(rc);
+    std::vector<double> wd;
+    if (p->weighted) {
+      wd.assign((size_t)nov * nov, 0.0);
+      for (int i = 0; i < nov; ++i)
+        for (int t = rptrs[i]; t < rptrs[i + 1]; ++t) wd[(size_t)i * nov + cols[t]] = rvals[t];
+      if ((rc = lane_arena_alloc(&L, wd.size() * 8, (void**)&p->d_wdense)) != SPD_OK) return fail(rc);
+    }
+    if ((e = cudaMemcpyAsync(p->d_rowmask, rm, (size_t)nov * 8, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(p->d_colmask, cm, (size_t)nov * 8, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+        (p->weighted && (e = cudaMemcpyAsync(p->d_wdense, wd.data(), wd.size() * 8, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess) ||
+        (e = cudaStreamSynchronize(L.stream)) != cudaSuccess) {
+      set_error("approx plan upload: %s", cudaGetErrorString(e));
+      return fail(SPD_ECUDA);
+    }
+    p->small_smem = (size_t)2 * nov * 8 + (p->weighted ? (size_t)nov * nov * 8 : 0) +
+                    (scaling ? (size_t)2 * nov * APS_THREADS * 4 : 0);
+    if (!scaling) rc = small_prepare(p, approx_small_kernel<false, false>);
+    else if (p->weighted) rc = small_prepare(p, approx_small_kernel<true, true>);
+    else rc = small_prepare(p, approx_small_kernel<true, false>);
+    if (rc != SPD_OK) return fail(rc);
+    p->small = true;
+    if ((rc = lane_reserve_partials(&L, (size_t)2 * p->small_blocks + 16)) != SPD_OK) return fail(rc);
+  }
   int per_sm = 0;
   e = p->weighted ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<true>, APX_THREADS, p->smem_bytes)
                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<false>, APX_THREADS, p->smem_bytes);
@@ -346,6 +567,29 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
   p->info.units = hi - lo;
   p->info.visited = hi - lo;
   p->info.path = p->scaling ? SPD_PATH_SCALING : SPD_PATH_RASMUSSEN;
+  if (p->small) {
+    int blocks = p->small_blocks;
+    const unsigned long long need = (hi - lo + APS_THREADS - 1) / APS_THREADS;
+    if (need < (unsigned long long)blocks) blocks = (int)(need ? need : 1);
+    SmallArgs sa;
+    sa.rowmask = p->d_rowmask; sa.colmask = p->d_colmask; sa.wdense = p->d_wdense;
+    sa.partial_sum = L.d_partials; sa.partial_sq = L.d_partials + blocks;
+    sa.trial_lo = lo; sa.trial_hi = hi; sa.seed = p->seed; sa.sq_scale = p->sq_scale;
+    sa.nov = p->nov; sa.scaling = p->scaling; sa.scale_intervals = p->y; sa.scale_times = p->z;
+    SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
+    if (!p->scaling) approx_small_kernel<false, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
+    else if (p->weighted) approx_small_kernel<true, true><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
+    else approx_small_kernel<true, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
+    SPB_CUDA(cudaGetLastError());
+    int rc2;
+    if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
+    if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc2;
+    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
+    p->info.launches = 3;
+    p->pending = true;
+    return SPD_OK;
+  }
   unsigned long long warps_needed = (hi - lo);
   int blocks = p->blocks;
   const unsigned long long need_blocks = (warps_needed + APX_WARPS - 1) / APX_WARPS;

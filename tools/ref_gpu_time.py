@@ -43,4 +43,25 @@ sp.sparse_ryser(m.mat, cp, ro, cv, n, 4)
 t = time.perf_counter(); ours = sp.sparse_ryser(m.mat, cp, ro, cv, n, 4); to = time.perf_counter() - t
 out.append(dict(case="SpaRyser -s -p5 -r1 (int, p=0.2)", n=n, gpus=1, ref_s=tr, ours_s=to, speedup=tr / to, ref_value=ref, ours_value=ours, rel_diff=abs(ref / ours - 1)))
 print(out[-1], flush=True)
+# config 5: estimators on grid graphs, 2^20 trials (one reference launch)
+ip = C.POINTER(C.c_int)
+lib.ref_gpu_rasmussen_chunks_sparse.restype = C.c_double
+lib.ref_gpu_rasmussen_chunks_sparse.argtypes = [ip, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
+lib.ref_gpu_scaling_chunks_sparse.restype = C.c_double
+lib.ref_gpu_scaling_chunks_sparse.argtypes = [ip, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+for gm, gn in ((8, 8), (36, 36)):
+    g = sp.Matrix.grid(gm, gn)
+    cp, ro, rp, co = g.cptrs, g.rows, g.rptrs, g.cols
+    args = (cp.ctypes.data_as(ip), ro.ctypes.data_as(ip), rp.ctypes.data_as(ip), co.ctypes.data_as(ip), g.nov, g.nnz, 1 << 20, 1)
+    trials = 1 << 20
+    for name, rf, of in (("Rasmussen", lambda: lib.ref_gpu_rasmussen_chunks_sparse(*args),
+                          lambda: sp.rasmussen_sparse(rp, co, cp, ro, g.nov, g.nnz, trials, 1, seed=1)),
+                         ("scaling y4 z5", lambda: lib.ref_gpu_scaling_chunks_sparse(*args, 4, 5),
+                          lambda: sp.scaling_sparse(cp, ro, rp, co, g.nov, g.nnz, trials, 4, 5, 1, seed=1))):
+        rf()
+        t = time.perf_counter(); ref = rf(); tr = time.perf_counter() - t
+        of()
+        t = time.perf_counter(); ours = of(); to = time.perf_counter() - t
+        out.append(dict(case="%s %dx%d grid, 2^20 trials" % (name, gm, gn), gpus=1, ref_s=tr, ours_s=to, speedup=tr / to, ref_value=ref, ours_value=ours))
+        print(out[-1], flush=True)
 json.dump(out, open(os.path.join(R, "gpurun_out", "ref_gpu_time.json"), "w"), indent=1)
