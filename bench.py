@@ -140,7 +140,9 @@ def cpu_reference_rate(mat, n: int, seconds: float, threads: int | None = None):
         lib.ref_cpu_perman64.restype = C.c_double
         lib.ref_cpu_perman64.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_longlong, C.c_longlong, C.c_int]
         lib.ref_gpu_max_threads.restype = C.c_int
-        cores = threads or lib.ref_gpu_max_threads()
+        # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1, which would otherwise
+        # pin the reference's OpenMP region to one thread (cpu_perman64 takes the count explicitly)
+        cores = threads or len(os.sched_getaffinity(0)) or lib.ref_gpu_max_threads()
 
         def run(count):
             t = time.perf_counter()
