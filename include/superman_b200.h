@@ -57,6 +57,9 @@ int         sp_device_count(void);
 const char *sp_version(void);
 /* create contexts / streams / buffers of devices 0..gpu_num-1 ahead of time (optional) */
 int         sp_warmup(int gpu_num);
+/* first device the permanent entry points use (default 0); ids with gpu_num devices use
+ * first .. first+gpu_num-1 (the revised front-end's -l flag) */
+int         sp_set_first_device(int device);
 
 /* ---------------------------------------------------------------------------------------------
  * Matrix input and preprocessing (host, C): what main.cu does before RunAlgo.

@@ -83,6 +83,7 @@ _sig("sp_last_error", C.c_char_p, [])
 _sig("sp_version", C.c_char_p, [])
 _sig("sp_device_count", C.c_int, [])
 _sig("sp_warmup", C.c_int, [C.c_int])
+_sig("sp_set_first_device", C.c_int, [C.c_int])
 _sig("sp_nw_factor", C.c_double, [C.c_int])
 _sig("sp_fp64_peak", C.c_double, [C.c_int, C.c_int])
 _sig("sp_dense_ryser", C.c_double, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _sp])

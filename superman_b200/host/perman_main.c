@@ -8,6 +8,9 @@
  * -g) are the reference's algo.h paths and are NOT provided here (BASELINE.json: "no CPU
  * fallback"): they exit with status 1 and a message.  With -g, -c only meant "a CPU thread also
  * pulls chunks" (main.cu:66); it is accepted and ignored.
+ * Also accepted, from the revised front-end (revised_perman/main.cpp:1298-1325): -k <reps> repeats
+ * the calculation, -l <device> picks the first GPU, -o (= --reduce) applies the degree compression;
+ * -h -w -q -v -e -u (precision and launch-shape knobs) are accepted and ignored.
  * Extra, off by default: `--reduce` applies the exact degree-0/1/2 compression of the revised
  * front-end before the exact algorithms; the environment variable PERMAN_PRECISION=<digits> adds a second line
  * `Result17: <name> <value>` with that many significant digits (the reference prints 6).
@@ -223,7 +226,12 @@ int main(int argc, char **argv) {
   int grid_graph = 0, gridm = 36, gridn = 36;        /* main.cu:342-344 */
   int reduce = 0;                                    /* --reduce: not a reference flag, off by default */
 
-  static const char *short_options = "bsr:t:f:gd:cap:x:y:z:im:n:";
+  /* the reference's option string (main.cu:347) plus the revised front-end's extra letters
+   * (revised_perman/main.cpp:1298): -k reps, -l device id, -o degree compression, and the
+   * precision / launch-shape flags -h -w -q -v -e -u, which are accepted and ignored (this engine
+   * always computes in FP64 and sizes its own launches) */
+  static const char *short_options = "bsr:t:f:gd:cap:x:y:z:im:n:hwqk:e:ol:vu:";
+  int reps = 1, first_device = 0;
   static const struct option long_options[] = {
       {"binary", 0, NULL, 'b'},        {"sparse", 0, NULL, 's'},       {"preprocessing", 1, NULL, 'r'},
       {"threads", 1, NULL, 't'},       {"file", 1, NULL, 'f'},         {"gpu", 0, NULL, 'g'},
@@ -235,7 +243,7 @@ int main(int argc, char **argv) {
   int opt;
   while ((opt = getopt_long(argc, argv, short_options, long_options, NULL)) != -1) {
     /* every valued option refuses an argument that looks like another option (main.cu:381-384) */
-    if (optarg && optarg[0] == '-' && strchr("rtfdpxyzmn", opt)) {
+    if (optarg && optarg[0] == '-' && strchr("rtfdpxyzmnkl", opt)) {
       /* the reference's message names -t for -r as well (main.cu:382); we name the real option */
       fprintf(stderr, "Option -%c requires an argument.\n", opt);
       return 1;
@@ -258,6 +266,10 @@ int main(int argc, char **argv) {
       case 'm': gridm = atoi(optarg); break;
       case 'n': gridn = atoi(optarg); break;
       case 1000: reduce = 1; break;
+      case 'o': reduce = 1; break;                      /* flags.compression */
+      case 'k': reps = atoi(optarg); break;             /* flags.rep */
+      case 'l': first_device = atoi(optarg); break;     /* flags.device_id */
+      case 'h': case 'w': case 'q': case 'v': case 'e': case 'u': break;
       case '?': return 1;
       default: abort();
     }
@@ -280,9 +292,15 @@ int main(int argc, char **argv) {
   const int visible = sp_device_count();
   if (visible <= 0) return report_failure();
   const double t_init1 = now_s();
-  if (gpu_num > visible) {
-    fprintf(stderr, "perman: -d %d but only %d device(s) visible; using %d\n", gpu_num, visible, visible);
-    gpu_num = visible;
+  if (first_device < 0 || first_device >= visible) {
+    fprintf(stderr, "perman: -l %d but %d device(s) visible\n", first_device, visible);
+    return 1;
+  }
+  sp_set_first_device(first_device);
+  if (gpu_num > visible - first_device) {
+    fprintf(stderr, "perman: -d %d but only %d device(s) usable; using %d\n", gpu_num, visible - first_device,
+            visible - first_device);
+    gpu_num = visible - first_device;
   }
   if (gpu_num < 1) gpu_num = 1;
   /* CUDA context creation (~0.15 s per device) is not part of any algorithm: do it before the
@@ -292,15 +310,20 @@ int main(int argc, char **argv) {
     if ((!approximation && (perman_algo == 5 || perman_algo == 6 || perman_algo == 8)) ||
         (approximation && (perman_algo == 3 || perman_algo == 4)))
       need = gpu_num;
-    if (perman_algo == 66) need = visible < 4 ? visible : 4;
+    if (perman_algo == 66) need = (visible - first_device) < 4 ? (visible - first_device) : 4;
     if (sp_warmup(need) != SP_OK) return report_failure();
     if (getenv("PERMAN_TIMING"))
       fprintf(stderr, "perman: driver init %.3f s, %d context(s) + buffers %.3f s\n", t_init1 - t_init0, need,
               now_s() - t_init1);
   }
 
-  if (grid_graph)
-    return run_grid(gridm, gridn, perman_algo, gpu_num, number_of_times, scale_intervals, scale_times);
+  if (reps < 1) reps = 1;
+  if (grid_graph) {
+    int rcg = 0;
+    for (int r = 0; r < reps && rcg == 0; ++r)
+      rcg = run_grid(gridm, gridn, perman_algo, gpu_num, number_of_times, scale_intervals, scale_times);
+    return rcg;
+  }
 
   sp_matrix m;
   if (sp_matrix_read(filename, !generic, &m) != SP_OK) return report_failure();
@@ -312,8 +335,10 @@ int main(int argc, char **argv) {
     printf("Reduced: nov %d -> %d\n", before, m.nov);
   }
   if (sp_matrix_compress(&m, preprocessing) != SP_OK) { sp_matrix_free(&m); return report_failure(); }
-  const int rc = run_matrix(&m, perman_algo, gpu_num, threads, cpu, dense, approximation, number_of_times,
-                            scale_intervals, scale_times);
+  int rc = 0;
+  for (int r = 0; r < reps && rc == 0; ++r)
+    rc = run_matrix(&m, perman_algo, gpu_num, threads, cpu, dense, approximation, number_of_times,
+                    scale_intervals, scale_times);
   sp_matrix_free(&m);
   return rc;
 }

@@ -13,6 +13,15 @@
 
 const char *sp_version(void) { return "superman_b200 0.1 (sm_100a)"; }
 
+/* first device used by the permanent entry points (the revised front-end's -l device id,
+ * revised_perman/main.cpp:1443-1449); multi-GPU ids use first .. first+gpu_num-1 */
+static int g_first_device = 0;
+int sp_set_first_device(int device) {
+  if (device < 0) { sp_set_error("negative device id"); return SP_EINVAL; }
+  g_first_device = device;
+  return SP_OK;
+}
+
 int sp_device_count(void) {
   int n = spd_device_count();
   if (n < 0) sp_set_error("%s", spd_last_error());
@@ -54,7 +63,7 @@ int sp_warmup(int gpu_num) {
   /* every device opens a plan on a 2x2 matrix and runs an empty range: creates the context and the
    * pooled lane (stream, events, pinned slot, arena, partial buffers) */
   /* dynamic mode: two plans (two lanes) per device, as the chunk-queue paths use */
-  return sp_sched_run(&ops, &job, SP_SCHED_DYNAMIC, gpu_num, 0, 0ull, 0ull, 0, (unsigned long long)(2 * gpu_num), &sum, &st);
+  return sp_sched_run(&ops, &job, SP_SCHED_DYNAMIC, gpu_num, g_first_device, 0ull, 0ull, 0, (unsigned long long)(2 * gpu_num), &sum, &st);
 }
 
 static void stats_clear(sp_stats *st) {
@@ -156,7 +165,7 @@ double sp_dense_ryser(const double *mat, int nov, int algo_id, int gpu_num, int 
   const unsigned long long chunks = (mode == SP_SCHED_DYNAMIC) ? sp_dynamic_chunks(nov, 29, gpu_num) : 0;
   double sum = 0.0;
   /* index 0 (the base term p = prod x, gpu_exact_dense.cu:653) is part of device 0's range */
-  int rc = sp_sched_run(&g_dense_ops, &job, mode, gpu_num, 0, 0ull, end, 16, chunks, &sum, stats);
+  int rc = sp_sched_run(&g_dense_ops, &job, mode, gpu_num, g_first_device, 0ull, end, 16, chunks, &sum, stats);
   free(mat_t);
   if (stats) stats->wall_ms = sp_now_ms() - t0;
   if (rc != SP_OK) return fail(stats, rc);
@@ -300,7 +309,7 @@ static double sparse_common(const double *mat, const int *cptrs, const int *rows
     if (skip) { int k = 0; while (k < 2 && end / (chunks * 2) >= (1ull << 22)) { chunks *= 2; ++k; } }
   }
   double sum = 0.0;
-  rc = sp_sched_run(&g_sparse_ops, &job, mode, gpu_num, 0, 0ull, end, 14, chunks, &sum, stats);
+  rc = sp_sched_run(&g_sparse_ops, &job, mode, gpu_num, g_first_device, 0ull, end, 14, chunks, &sum, stats);
   free(dmat_t);
   if (stats) stats->wall_ms = sp_now_ms() - t0;
   if (rc != SP_OK) return fail(stats, rc);
@@ -429,7 +438,7 @@ static double approx_common(const approx_job *job, long long trials, int gpu_num
   if (gpu_num == 1) {
     /* single device: run on the calling thread so that the squared sum can be read back directly */
     g_sq_acc = 0.0; g_sq_scale = 1.0;
-    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, 1, 0, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
+    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, 1, g_first_device, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
     if (rc == SP_OK) {
       const double n = (double)trials, mean = sum / n, ms = mean * g_sq_scale;
       double var = g_sq_acc / n - ms * ms;
@@ -439,7 +448,7 @@ static double approx_common(const approx_job *job, long long trials, int gpu_num
   } else {
     /* several devices: static even split of the trial indices; the standard error is taken from
      * the per-device means (batch means) */
-    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, gpu_num, 0, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
+    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, gpu_num, g_first_device, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
     if (rc == SP_OK) {
       const double mean = sum / (double)trials;
       double acc = 0.0;
