@@ -405,6 +405,181 @@ approx_small_kernel(const SmallArgs a) {
   }
 }
 
+// ---- thread-per-trial Rasmussen for 64 < nov (sparse patterns, e.g. the 36x36 grid: nov = 648) ----
+// One thread runs a trial; its state lives in shared memory as 32-bit words laid out [word][thread]
+// (every lane stays in its own bank):
+//   deg   one byte per row: remaining column count, 0xFF once the row is extracted
+//   gmin  one byte per group of 32 rows: the minimum of the group's deg bytes
+//   colx  one bit per column: extracted
+// The minimum-degree row (first in ascending order, as gpu_approximation_sparse.cu:242-256 scans) is
+// found through gmin: SIMD byte minimum over the ngroups bytes, first group holding it, first row of
+// that group holding it -- about 100 instructions per step instead of a scan of every CRS row.
+// Persistent lanes as in approx_small_kernel.  Per-trial values are bit-identical to the other
+// engines and to the oracle.
+#define APM_THREADS 256
+
+struct MidArgs {
+  const int* rptrs; const int* cols; const int* cptrs; const int* rows;
+  double* partial_sum;
+  double* partial_sq;
+  unsigned long long trial_lo, trial_hi;
+  unsigned long long seed;
+  double sq_scale;
+  int nov, nnz;
+};
+
+__device__ __forceinline__ unsigned byte_min4(unsigned w) {   // minimum of the four bytes of w
+  unsigned m = __vminu4(w, w >> 16);
+  m = __vminu4(m, m >> 8);
+  return m & 0xffu;
+}
+
+__global__ void __launch_bounds__(APM_THREADS)
+rasmussen_mid_kernel(const MidArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int nov = a.nov, nnz = a.nnz;
+  const int WD = (nov + 3) >> 2;                 // deg words
+  const int NG = (nov + 31) >> 5;                // groups of 32 rows
+  const int WG = (NG + 3) >> 2;                  // gmin words
+  const int WC = (nov + 31) >> 5;                // colx words
+  int* s_rptrs = reinterpret_cast<int*>(smraw);
+  int* s_cptrs = s_rptrs + (nov + 1);
+  int* s_cols = s_cptrs + (nov + 1);
+  int* s_rows = s_cols + nnz;
+  unsigned* s_deg0 = reinterpret_cast<unsigned*>(s_rows + nnz);      // initial deg words
+  unsigned* s_gmin0 = s_deg0 + WD;                                    // initial gmin words
+  unsigned* st = s_gmin0 + WG;                                        // per-thread state, [word][thread]
+  unsigned* deg = st + threadIdx.x;
+  unsigned* gmin = deg + (size_t)WD * APM_THREADS;
+  unsigned* colx = gmin + (size_t)WG * APM_THREADS;
+  __shared__ double blk_sum[APM_THREADS / 32], blk_sq[APM_THREADS / 32];
+
+  for (int e = threadIdx.x; e <= nov; e += APM_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
+  for (int e = threadIdx.x; e < nnz; e += APM_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
+  __syncthreads();
+  for (int w = threadIdx.x; w < WD; w += APM_THREADS) {
+    unsigned v = 0;
+    for (int b = 0; b < 4; ++b) {
+      const int r = 4 * w + b;
+      const unsigned d = (r < nov) ? (unsigned)min(254, s_rptrs[r + 1] - s_rptrs[r]) : 0xffu;   // padding rows: extracted
+      v |= d << (8 * b);
+    }
+    s_deg0[w] = v;
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < WG; w += APM_THREADS) {
+    unsigned v = 0;
+    for (int b = 0; b < 4; ++b) {
+      const int g = 4 * w + b;
+      unsigned m = 0xffu;
+      if (g < NG) for (int q = 0; q < 8; ++q) { const int wi = 8 * g + q; if (wi < WD) m = min(m, byte_min4(s_deg0[wi])); }
+      v |= m << (8 * b);
+    }
+    s_gmin0[w] = v;
+  }
+  __syncthreads();
+
+  const unsigned long long total = (unsigned long long)gridDim.x * APM_THREADS;
+  unsigned long long trial = a.trial_lo + (unsigned long long)blockIdx.x * APM_THREADS + threadIdx.x;
+  const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+  double tsum = 0.0, tsq = 0.0, perm = 1.0;
+  uint32_t rnd0 = 0, rnd1 = 0, rnd2 = 0, rnd3 = 0;
+  int step = 0;
+
+  for (;;) {
+    const bool have = trial < a.trial_hi;
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (!have) continue;
+    if (step == 0) {
+      perm = 1.0;
+      for (int w = 0; w < WD; ++w) deg[w * APM_THREADS] = s_deg0[w];
+      for (int w = 0; w < WG; ++w) gmin[w * APM_THREADS] = s_gmin0[w];
+      for (int w = 0; w < WC; ++w) colx[w * APM_THREADS] = 0u;
+    }
+    if ((step & 3) == 0) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)(step >> 2), 0u, k0, k1, r);
+      rnd0 = r[0]; rnd1 = r[1]; rnd2 = r[2]; rnd3 = r[3];
+    }
+    const int rw = step & 3;
+    const uint32_t draw = (rw == 0) ? rnd0 : (rw == 1) ? rnd1 : (rw == 2) ? rnd2 : rnd3;
+    // ---- minimum remaining degree, first group and first row holding it ----
+    unsigned acc4 = 0xffffffffu;
+    for (int w = 0; w < WG; ++w) acc4 = __vminu4(acc4, gmin[w * APM_THREADS]);
+    const unsigned dmin = byte_min4(acc4);
+    bool dead = (dmin == 0u);
+    if (!dead) {
+      const unsigned pat = dmin * 0x01010101u;
+      int g = 0;
+      for (int w = 0; w < WG; ++w) {
+        const unsigned eq = __vcmpeq4(gmin[w * APM_THREADS], pat);     // 0xFF in every matching byte
+        if (eq) { g = 4 * w + ((__ffs(eq) - 1) >> 3); break; }
+      }
+      int row = 0;
+      for (int q = 0; q < 8; ++q) {
+        const int wi = 8 * g + q;
+        if (wi >= WD) break;
+        const unsigned eq = __vcmpeq4(deg[wi * APM_THREADS], pat);
+        if (eq) { row = 4 * wi + ((__ffs(eq) - 1) >> 3); break; }
+      }
+      perm *= (double)dmin;
+      int want = (int)(((uint64_t)draw * (uint64_t)dmin) >> 32);
+      int col = -1;
+      for (int t = s_rptrs[row]; t < s_rptrs[row + 1]; ++t) {
+        const int c = s_cols[t];
+        if ((colx[(c >> 5) * APM_THREADS] >> (c & 31)) & 1u) continue;
+        if (want == 0) { col = c; break; }
+        --want;
+      }
+      // ---- extract row and column ----
+      colx[(col >> 5) * APM_THREADS] |= 1u << (col & 31);
+      deg[(row >> 2) * APM_THREADS] |= 0xffu << (8 * (row & 3));
+      {
+        unsigned m4 = 0xffffffffu;
+        const int gb = row >> 5;
+        for (int q = 0; q < 8; ++q) { const int wi = 8 * gb + q; if (wi < WD) m4 = __vminu4(m4, deg[wi * APM_THREADS]); }
+        const unsigned gm = byte_min4(m4);
+        unsigned gw = gmin[(gb >> 2) * APM_THREADS];
+        gw = (gw & ~(0xffu << (8 * (gb & 3)))) | (gm << (8 * (gb & 3)));
+        gmin[(gb >> 2) * APM_THREADS] = gw;
+      }
+      for (int t = s_cptrs[col]; t < s_cptrs[col + 1]; ++t) {
+        const int r2 = s_rows[t];
+        const unsigned dw = deg[(r2 >> 2) * APM_THREADS];
+        const unsigned d = (dw >> (8 * (r2 & 3))) & 0xffu;
+        if (d == 0xffu) continue;                                      // extracted
+        deg[(r2 >> 2) * APM_THREADS] = dw - (1u << (8 * (r2 & 3)));
+        const int g2 = r2 >> 5;
+        const unsigned gw = gmin[(g2 >> 2) * APM_THREADS];
+        const unsigned cur = (gw >> (8 * (g2 & 3))) & 0xffu;
+        if (d - 1u < cur) gmin[(g2 >> 2) * APM_THREADS] = (gw & ~(0xffu << (8 * (g2 & 3)))) | ((d - 1u) << (8 * (g2 & 3)));
+      }
+    }
+    if (dead) perm = 0.0;
+    ++step;
+    if (dead || step == nov) {
+      tsum += perm;
+      const double q = perm * a.sq_scale;
+      tsq += q * q;
+      trial += total;
+      step = 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+    tsq += __shfl_down_sync(0xffffffffu, tsq, o);
+  }
+  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sv = 0.0, qv = 0.0;
+    for (int w = 0; w < APM_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; }
+    a.partial_sum[blockIdx.x] = sv;
+    a.partial_sq[blockIdx.x] = qv;
+  }
+}
+
 }  // namespace spb
 
 using namespace spb;
@@ -426,6 +601,10 @@ struct spd_approx_plan {
   double* d_wdense = nullptr;
   size_t small_smem = 0;
   int small_blocks = 0;
+  // thread-per-trial Rasmussen for larger sparse patterns
+  bool mid = false;
+  size_t mid_smem = 0;
+  int mid_blocks = 0;
   bool pending = false;
   spd_run_info info;
 };
@@ -541,6 +720,27 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     p->small = true;
     if ((rc = lane_reserve_partials(&L, (size_t)2 * p->small_blocks + 16)) != SPD_OK) return fail(rc);
   }
+  // ---- thread-per-trial Rasmussen for nov > 64 when the per-thread state fits shared memory ----
+  int maxdeg = 0;
+  for (int r = 0; r < nov; ++r) maxdeg = (rptrs[r + 1] - rptrs[r] > maxdeg) ? rptrs[r + 1] - rptrs[r] : maxdeg;
+  if (!p->small && !scaling && maxdeg <= 254 && env_int("SP_APPROX_FORCE_WARP", 0) == 0) {
+    const int WD = (nov + 3) / 4, NG = (nov + 31) / 32, WG = (NG + 3) / 4, WC = (nov + 31) / 32;
+    const size_t shared_part = (size_t)(2 * (nov + 1) + 2 * nnz) * 4 + (size_t)(WD + WG) * 4;
+    const size_t state = (size_t)(WD + WG + WC) * 4 * APM_THREADS;
+    p->mid_smem = shared_part + state;
+    if (p->mid_smem <= 220 * 1024) {
+      e = cudaFuncSetAttribute(rasmussen_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->mid_smem);
+      int per = 0;
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rasmussen_mid_kernel, APM_THREADS, p->mid_smem);
+      if (e == cudaSuccess && per >= 1) {
+        p->mid = true;
+        p->mid_blocks = per * L.sm_count;
+        if ((rc = lane_reserve_partials(&L, (size_t)2 * p->mid_blocks + 16)) != SPD_OK) return fail(rc);
+      } else {
+        (void)cudaGetLastError();
+      }
+    }
+  }
   int per_sm = 0;
   e = p->weighted ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<true>, APX_THREADS, p->smem_bytes)
                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<false>, APX_THREADS, p->smem_bytes);
@@ -580,6 +780,27 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
     if (!p->scaling) approx_small_kernel<false, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
     else if (p->weighted) approx_small_kernel<true, true><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
     else approx_small_kernel<true, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
+    SPB_CUDA(cudaGetLastError());
+    int rc2;
+    if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
+    if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc2;
+    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
+    p->info.launches = 3;
+    p->pending = true;
+    return SPD_OK;
+  }
+  if (p->mid) {
+    int blocks = p->mid_blocks;
+    const unsigned long long need = (hi - lo + APM_THREADS - 1) / APM_THREADS;
+    if (need < (unsigned long long)blocks) blocks = (int)(need ? need : 1);
+    MidArgs ma;
+    ma.rptrs = p->d_rptrs; ma.cols = p->d_cols; ma.cptrs = p->d_cptrs; ma.rows = p->d_rows;
+    ma.partial_sum = L.d_partials; ma.partial_sq = L.d_partials + blocks;
+    ma.trial_lo = lo; ma.trial_hi = hi; ma.seed = p->seed; ma.sq_scale = p->sq_scale;
+    ma.nov = p->nov; ma.nnz = p->nnz;
+    SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
+    rasmussen_mid_kernel<<<blocks, APM_THREADS, p->mid_smem, L.stream>>>(ma);
     SPB_CUDA(cudaGetLastError());
     int rc2;
     if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
