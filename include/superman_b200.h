@@ -92,10 +92,43 @@ int  sp_matrix_compress(sp_matrix *m, int preprocessing);
 /* gridGraph2compressed (util.h:403-520): biadjacency matrix of the m x n grid, nov = m*n/2,
  * with CRS and CCS.  Fails when both dimensions are odd. */
 int  sp_matrix_grid(int m, int n, sp_matrix *out);
-/* Degree-0/1/2 compression (exact; the revised front-end's d1compress / d2compress,
- * revised_perman/util.h:1199-1407): shrinks m in place, perm(original) = *factor * perm(reduced).
- * Returns the number of rows removed (>= 0) or a negative SP_E* code; drops CRS/CCS. */
+/* Structural preprocessing of the revised front-end (exact; host/sp_reduce.c).  All of them work on
+ * m->mat in place and drop CRS/CCS (call sp_matrix_compress afterwards).
+ *
+ * sp_matrix_min_degree: getMinNnz (revised_perman/util.h:1181).
+ * sp_matrix_reduce_step: one d1compress (util.h:1200), else one d2compress (util.h:1260), picking
+ *   the same row / column as upstream; returns 0 (nothing applied), 1 or 2.  The degree-1 entry is
+ *   multiplied into *factor instead of into the first matrix row (util.h:1251-1253).
+ * sp_matrix_reduce: the loop of compress_singleton_and_then_recurse (revised_perman/main.cpp:1058)
+ *   -- steps until none applies; an empty row or column collapses the matrix to the 1x1 zero matrix
+ *   with *factor = 0.  perm(original) = *factor * perm(reduced).  Returns the rows removed.
+ * sp_matrix_split34: d34compress (util.h:1333) on the first row / column with min_deg (3 or 4)
+ *   non-zeros: m becomes the first (nov-1) matrix, *second (caller frees) the other one, and
+ *   perm(before) = perm(m) + perm(second).  Returns 1, or 0 when no row / column has that degree.
+ * sp_matrix_scale: scalesk + scaleMatrix (util.h:1445-1593), rv / cv receive the nov row / column
+ *   factors; perm(original) = perm(scaled) / prod(cv) / prod(rv).  Returns the number of sweeps.
+ * sp_matrix_dm: Dulmage-Mendelsohn fine decomposition (util.h:309): erases the entries that lie on no
+ *   perfect matching (they cannot contribute to the permanent); *matching receives the size of a
+ *   maximum matching (< nov: the permanent is 0, nothing erased).  Returns the entries erased. */
+int  sp_matrix_min_degree(const sp_matrix *m);
+int  sp_matrix_reduce_step(sp_matrix *m, double *factor);
 int  sp_matrix_reduce(sp_matrix *m, double *factor);
+int  sp_matrix_split34(sp_matrix *m, int min_deg, sp_matrix *second);
+int  sp_matrix_scale(sp_matrix *m, double threshold, double *rv, double *cv);
+int  sp_matrix_dm(sp_matrix *m, int *matching);
+/* compress_singleton_and_then_recurse + compress_and_calculate_recursive + scale_and_calculate
+ * (revised_perman/main.cpp:993-1260) on the GPU engine: degree-1/2 compression, then -- while the
+ * smallest degree is < 5 and nov > leaf_nov (0: upstream's 30; < 0: no compression at all, scaling
+ * only) -- d1 / d2 steps and d34 splits; every leaf is Sinkhorn-scaled to row / column sums
+ * scaling_threshold when that is > 0 (upstream's -u), to 1 when it is 0 and the compression changed
+ * the matrix (merged columns unbalance the row sums and cost FP64 Ryser ~1e-6 of accuracy), not at
+ * all when it is < 0 (upstream's default), then computed
+ * with sp_dense_ryser (sparse == 0; algo_id 0-6) or, after sp_matrix_compress(preprocessing),
+ * sp_sparse_ryser (algo_id 1-6) / sp_skipper (7, 8).  mat is the row-major nov x nov matrix as read
+ * (not reordered).  stats: sums over the leaves, chunks = number of leaves. */
+double sp_permanent_compressed(const double *mat, int nov, int sparse, int preprocessing, int algo_id,
+                               int gpu_num, int threads, double scaling_threshold, int leaf_nov,
+                               sp_stats *stats);
 void sp_matrix_free(sp_matrix *m);
 
 /* ---------------------------------------------------------------------------------------------

@@ -108,6 +108,50 @@ class Matrix:
             raise SupermanError(rc, _ffi.last_error())
         return f.value
 
+    def reduce_step(self, factor: float = 1.0):
+        """one d1compress-else-d2compress step; returns (kind 0/1/2, factor)"""
+        f = C.c_double(factor)
+        rc = lib.sp_matrix_reduce_step(C.byref(self._m), C.byref(f))
+        if rc < 0:
+            raise SupermanError(rc, _ffi.last_error())
+        return rc, f.value
+
+    def min_degree(self) -> int:
+        rc = lib.sp_matrix_min_degree(C.byref(self._m))
+        if rc < 0:
+            raise SupermanError(rc, _ffi.last_error())
+        return rc
+
+    def split34(self, min_deg: int):
+        """d34compress: self becomes the first matrix, returns the second (or None when nothing applies)"""
+        other = Matrix()
+        rc = lib.sp_matrix_split34(C.byref(self._m), min_deg, C.byref(other._m))
+        if rc < 0:
+            raise SupermanError(rc, _ffi.last_error())
+        if rc == 0:
+            return None
+        other._live = True
+        return other
+
+    def scale(self, threshold: float):
+        """scalesk + scaleMatrix; returns (rv, cv, sweeps)"""
+        n = self._m.nov
+        rv = np.zeros(n, dtype=np.float64)
+        cv = np.zeros(n, dtype=np.float64)
+        rc = lib.sp_matrix_scale(C.byref(self._m), float(threshold), rv.ctypes.data_as(_ffi._dp),
+                                 cv.ctypes.data_as(_ffi._dp))
+        if rc < 0:
+            raise SupermanError(rc, _ffi.last_error())
+        return rv, cv, rc
+
+    def dm(self):
+        """Dulmage-Mendelsohn: erase entries on no perfect matching; returns (erased, matching size)"""
+        k = C.c_int(0)
+        rc = lib.sp_matrix_dm(C.byref(self._m), C.byref(k))
+        if rc < 0:
+            raise SupermanError(rc, _ffi.last_error())
+        return rc, k.value
+
     # -- views (copies) ------------------------------------------------------------------------
     nov = property(lambda self: self._m.nov)
     nnz = property(lambda self: self._m.nnz)
@@ -163,6 +207,17 @@ def dense_ryser(mat, nov=None, algo_id=4, gpu_num=1, cpu=False, threads=16, stat
     nov = int(round(math.sqrt(a.size)))
     st = stats if stats is not None else SpStats()
     v = lib.sp_dense_ryser(_ptr(a), nov, algo_id, gpu_num, int(cpu), threads, C.byref(st))
+    return _check(v, st)
+
+
+def permanent_compressed(mat, nov=None, sparse=False, preprocessing=0, algo_id=4, gpu_num=1, threads=16,
+                         scaling_threshold=0.0, leaf_nov=0, stats: SpStats | None = None) -> float:
+    """the revised front-end's -o path: degree compression, d34 splits, optional -u scaling (sp_permanent_compressed)"""
+    a = _dmat(mat, nov)
+    nov = int(round(math.sqrt(a.size)))
+    st = stats if stats is not None else SpStats()
+    v = lib.sp_permanent_compressed(_ptr(a), nov, int(sparse), preprocessing, algo_id, gpu_num, threads,
+                                    float(scaling_threshold), leaf_nov, C.byref(st))
     return _check(v, st)
 
 

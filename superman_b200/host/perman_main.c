@@ -9,10 +9,11 @@
  * fallback"): they exit with status 1 and a message.  With -g, -c only meant "a CPU thread also
  * pulls chunks" (main.cu:66); it is accepted and ignored.
  * Also accepted, from the revised front-end (revised_perman/main.cpp:1298-1325): -k <reps> repeats
- * the calculation, -l <device> picks the first GPU, -o (= --reduce) applies the degree compression;
- * -h -w -q -v -e -u (precision and launch-shape knobs) are accepted and ignored.
- * Extra, off by default: `--reduce` applies the exact degree-0/1/2 compression of the revised
- * front-end before the exact algorithms; the environment variable PERMAN_PRECISION=<digits> adds a second line
+ * the calculation, -l <device> picks the first GPU, -o (= --reduce) applies the degree compression
+ * and the d34 recursion, -u <t> Sinkhorn-scales each matrix to row/column sums t before the kernel;
+ * -h -w -q -v -e (precision and launch-shape knobs) are accepted and ignored.
+ * Extra, off by default: `--dm` erases the entries that lie on no perfect matching (Dulmage-
+ * Mendelsohn, dead code upstream) before the exact algorithms; the environment variable PERMAN_PRECISION=<digits> adds a second line
  * `Result17: <name> <value>` with that many significant digits (the reference prints 6).
  */
 #define _POSIX_C_SOURCE 200809L
@@ -67,7 +68,15 @@ static int report_failure(void) {
   return 1;
 }
 
-static double g_factor = 1.0;   /* --reduce: perm(original) = g_factor * perm(reduced) */
+/* -o / --reduce (flags.compression) and -u <t> (flags.scaling_threshold) of the revised front-end:
+ * the exact ids go through sp_permanent_compressed (degree compression, d34 splits, scaling) */
+static int g_compress = 0;
+static double g_threshold = 0.0;   /* 0: scale leaves only when the compression changed the matrix */
+static int g_preprocessing = 0;
+
+static void print_compressed(const sp_stats *st) {
+  printf("Compressed: %d leaf matrix(es), %llu Gray indices\n", st->chunks, st->units);
+}
 
 static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int threads, int cpu, int dense,
                       int approximation, int number_of_times, int scale_intervals, int scale_times) {
@@ -94,8 +103,15 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
       }
       if (perman_algo < 0 || perman_algo > 6) { printf("Unknown Algorithm ID\n"); return 0; }
       start = now_s();
-      perman = g_factor * sp_dense_ryser(m->mat, nov, perman_algo, gpu_num, cpu, threads, &st);
-      if (isnan(perman) && st.error) return report_failure();
+      if (g_compress || g_threshold > 0) {
+        perman = sp_permanent_compressed(m->mat, nov, 0, 0, perman_algo, gpu_num, threads, g_threshold,
+                                         g_compress ? 0 : -1, &st);
+        if (isnan(perman) && st.error) return report_failure();
+        print_compressed(&st);
+      } else {
+        perman = sp_dense_ryser(m->mat, nov, perman_algo, gpu_num, cpu, threads, &st);
+        if (isnan(perman) && st.error) return report_failure();
+      }
       print_kernel_lines(&st);
       result_cout(names[perman_algo], perman, now_s() - start);
     } else {
@@ -132,7 +148,11 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
         case 66: name = "gpu_perman64_xshared_coalescing_mshared_multigpu_sparse_manual_distribution"; break;
         default: printf("Unknown Algorithm ID\n"); return 0;
       }
-      if (perman_algo == 7 || perman_algo == 8)
+      if ((g_compress || g_threshold > 0) && perman_algo != 66) {
+        perman = sp_permanent_compressed(m->mat, nov, 1, g_preprocessing, perman_algo, gpu_num, threads, g_threshold,
+                                         g_compress ? 0 : -1, &st);
+        if (!(isnan(perman) && st.error)) print_compressed(&st);
+      } else if (perman_algo == 7 || perman_algo == 8)
         perman = sp_skipper(m->mat, m->rptrs, m->cols, m->cptrs, m->rows, m->cvals, nov, perman_algo, gpu_num,
                             cpu, threads, &st);
       else if (perman_algo == 66)
@@ -140,7 +160,6 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
       else
         perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, nov, perman_algo, gpu_num, cpu, threads, &st);
       if (isnan(perman) && st.error) return report_failure();
-      perman *= g_factor;
       print_kernel_lines(&st);
       result_cout(name, perman, now_s() - start);
     } else {
@@ -231,19 +250,20 @@ int main(int argc, char **argv) {
    * precision / launch-shape flags -h -w -q -v -e -u, which are accepted and ignored (this engine
    * always computes in FP64 and sizes its own launches) */
   static const char *short_options = "bsr:t:f:gd:cap:x:y:z:im:n:hwqk:e:ol:vu:";
-  int reps = 1, first_device = 0;
+  int reps = 1, first_device = 0, dm = 0;
   static const struct option long_options[] = {
       {"binary", 0, NULL, 'b'},        {"sparse", 0, NULL, 's'},       {"preprocessing", 1, NULL, 'r'},
       {"threads", 1, NULL, 't'},       {"file", 1, NULL, 'f'},         {"gpu", 0, NULL, 'g'},
       {"device", 1, NULL, 'd'},        {"cpu", 0, NULL, 'c'},          {"approximation", 0, NULL, 'a'},
       {"perman", 1, NULL, 'p'},        {"numOfTimes", 1, NULL, 'x'},   {"scaleIntervals", 1, NULL, 'y'},
       {"scaleTimes", 1, NULL, 'z'},    {"grid", 0, NULL, 'i'},         {"gridm", 1, NULL, 'm'},
-      {"gridn", 1, NULL, 'n'},         {"reduce", 0, NULL, 1000},      {NULL, 0, NULL, 0}};
+      {"gridn", 1, NULL, 'n'},         {"reduce", 0, NULL, 1000},      {"dm", 0, NULL, 1001},
+      {NULL, 0, NULL, 0}};
 
   int opt;
   while ((opt = getopt_long(argc, argv, short_options, long_options, NULL)) != -1) {
     /* every valued option refuses an argument that looks like another option (main.cu:381-384) */
-    if (optarg && optarg[0] == '-' && strchr("rtfdpxyzmnkl", opt)) {
+    if (optarg && optarg[0] == '-' && opt < 256 && strchr("rtfdpxyzmnklu", opt)) {
       /* the reference's message names -t for -r as well (main.cu:382); we name the real option */
       fprintf(stderr, "Option -%c requires an argument.\n", opt);
       return 1;
@@ -269,7 +289,9 @@ int main(int argc, char **argv) {
       case 'o': reduce = 1; break;                      /* flags.compression */
       case 'k': reps = atoi(optarg); break;             /* flags.rep */
       case 'l': first_device = atoi(optarg); break;     /* flags.device_id */
-      case 'h': case 'w': case 'q': case 'v': case 'e': case 'u': break;
+      case 'u': g_threshold = (double)atoi(optarg); break;   /* flags.scaling_threshold (main.cpp:1466) */
+      case 1001: dm = 1; break;
+      case 'h': case 'w': case 'q': case 'v': case 'e': break;
       case '?': return 1;
       default: abort();
     }
@@ -327,13 +349,19 @@ int main(int argc, char **argv) {
 
   sp_matrix m;
   if (sp_matrix_read(filename, !generic, &m) != SP_OK) return report_failure();
-  if (reduce && !approximation) {
-    /* degree-0/1/2 compression (revised_perman/util.h:1199-1407): exact, shrinks n before the
-     * exponential kernel; the result line reports the permanent of the ORIGINAL matrix */
-    const int before = m.nov;
-    if (sp_matrix_reduce(&m, &g_factor) < 0) { sp_matrix_free(&m); return report_failure(); }
-    printf("Reduced: nov %d -> %d\n", before, m.nov);
+  if (dm && !approximation) {
+    /* Dulmage-Mendelsohn: entries on no perfect matching cannot contribute (revised util.h:309) */
+    int matching = 0;
+    const int erased = sp_matrix_dm(&m, &matching);
+    if (erased < 0) { sp_matrix_free(&m); return report_failure(); }
+    printf("DM: maximum matching %d of %d, %d entries erased\n", matching, m.nov, erased);
   }
+  g_compress = reduce && !approximation;
+  g_preprocessing = preprocessing;
+  if (approximation) g_threshold = 0.0;
+  /* with -o / -u the exact ids hand the matrix AS READ to sp_permanent_compressed, which reduces it
+   * and applies the -r ordering per leaf; keep an unordered copy for it */
+  if (g_compress || g_threshold > 0) preprocessing = 0;
   if (sp_matrix_compress(&m, preprocessing) != SP_OK) { sp_matrix_free(&m); return report_failure(); }
   int rc = 0;
   for (int r = 0; r < reps && rc == 0; ++r)

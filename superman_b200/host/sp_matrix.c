@@ -352,92 +352,3 @@ int sp_matrix_grid(int gm, int gn, sp_matrix *out) {
   out->header_nnz = out->nnz;
   return SP_OK;
 }
-
-
-/* ------------------------------------------------------------------------------------------------
- * Degree-1 / degree-2 compression (the revised front-end's d1compress /
- * d2compress, revised_perman/util.h:1199-1407): exact reductions of the permanent that shrink n --
- * and with it the 2^(n-1) index space -- before the exponential kernel runs.
- *   degree 0: a row or column without non-zeros  ->  perm = 0
- *   degree 1: row i has its only non-zero v in column j (or column j its only one in row i):
- *             perm(A) = v * perm(A without row i and column j)
- *   degree 2: row i has exactly two non-zeros a = A[i][p], b = A[i][q]: drop row i and merge the two
- *             columns into  b * col_p + a * col_q  (expansion along row i + multilinearity);
- *             symmetrically for a column with two non-zeros.
- * Repeats until nothing applies.  The scalar factors are accumulated in *factor (the reference
- * folds them into the first matrix row instead, util.h:1251-1253, which destroys 0/1-ness);
- * perm(original) = *factor * perm(reduced).  CRS/CCS are dropped: call sp_matrix_compress after.
- * Returns the number of rows removed, or a negative SP_E* code. */
-static int row_degree(const double *a, int n, int i, int *c1, int *c2) {
-  int d = 0;
-  for (int j = 0; j < n; ++j)
-    if (a[(size_t)i * n + j] != 0) { if (d == 0) *c1 = j; else if (d == 1) *c2 = j; ++d; }
-  return d;
-}
-static int col_degree(const double *a, int n, int j, int *r1, int *r2) {
-  int d = 0;
-  for (int i = 0; i < n; ++i)
-    if (a[(size_t)i * n + j] != 0) { if (d == 0) *r1 = i; else if (d == 1) *r2 = i; ++d; }
-  return d;
-}
-/* remove row r and column c in place (n -> n-1) */
-static void drop_row_col(double *a, int n, int r, int c) {
-  int w = 0;
-  for (int i = 0; i < n; ++i) {
-    if (i == r) continue;
-    for (int j = 0; j < n; ++j) {
-      if (j == c) continue;
-      a[w++] = a[(size_t)i * n + j];
-    }
-  }
-}
-
-int sp_matrix_reduce(sp_matrix *m, double *factor) {
-  if (!m || !m->mat || !factor) { sp_set_error("null argument"); return SP_EINVAL; }
-  free(m->cptrs); free(m->rows); free(m->cvals); free(m->rptrs); free(m->cols); free(m->rvals);
-  m->cptrs = m->rows = m->rptrs = m->cols = NULL;
-  m->cvals = m->rvals = NULL;
-  m->nnz = 0;
-  double *a = m->mat;
-  int n = m->nov, removed = 0;
-  *factor = 1.0;
-  for (;;) {
-    if (n <= 2) break;
-    int done = 1;
-    for (int t = 0; t < 2 * n && done; ++t) {
-      const int is_row = t < n, idx = is_row ? t : t - n;
-      int p = -1, q = -1;
-      const int d = is_row ? row_degree(a, n, idx, &p, &q) : col_degree(a, n, idx, &p, &q);
-      if (d == 0) {                     /* permanent is zero: collapse to the 1x1 zero matrix */
-        *factor = 0.0;
-        removed += n - 1;
-        n = 1;
-        a[0] = 0.0;
-        done = 0;
-        break;
-      }
-      if (d == 1) {
-        const int r = is_row ? idx : p, c = is_row ? p : idx;
-        *factor *= a[(size_t)r * n + c];
-        drop_row_col(a, n, r, c);
-        --n; ++removed; done = 0;
-      } else if (d == 2) {
-        if (is_row) {                   /* merge columns p and q into p, drop row idx and column q */
-          const double va = a[(size_t)idx * n + p], vb = a[(size_t)idx * n + q];
-          for (int i = 0; i < n; ++i)
-            a[(size_t)i * n + p] = vb * a[(size_t)i * n + p] + va * a[(size_t)i * n + q];
-          drop_row_col(a, n, idx, q);
-        } else {                        /* merge rows p and q into p, drop column idx and row q */
-          const double va = a[(size_t)p * n + idx], vb = a[(size_t)q * n + idx];
-          for (int j = 0; j < n; ++j)
-            a[(size_t)p * n + j] = vb * a[(size_t)p * n + j] + va * a[(size_t)q * n + j];
-          drop_row_col(a, n, q, idx);
-        }
-        --n; ++removed; done = 0;
-      }
-    }
-    if (done) break;
-  }
-  m->nov = n;
-  return removed;
-}

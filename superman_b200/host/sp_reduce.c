@@ -1,0 +1,474 @@
+/* Structural preprocessing in C: the exact reductions the reference's revised
+ * front-end applies BEFORE the exponential kernel, so that the kernel sees a smaller n.
+ *
+ * Mirrors, for the drop-in boundary:
+ *   getMinNnz / checkEmpty                      revised_perman/util.h:1165-1197
+ *   d1compress, d2compress                      revised_perman/util.h:1200-1330
+ *   d34compress                                 revised_perman/util.h:1333-1407
+ *   scalesk + scaleMatrix                       revised_perman/util.h:1445-1593
+ *   dulmage_mendehlson                          revised_perman/util.h:143-440 (dead code upstream)
+ *   compress_singleton_and_then_recurse,
+ *   compress_and_calculate_recursive,
+ *   scale_and_calculate                         revised_perman/main.cpp:993-1260
+ *
+ * Every step picks the same row / column and evaluates the same expressions in the same order as
+ * the reference, so the reduced matrices are bit-identical to its -- with one deliberate change:
+ * d1compress folds the removed entry into the first matrix row (util.h:1251-1253: "that's where
+ * matrix could go out of 0-1 form"); here it is accumulated in a separate scalar factor, so a 0/1
+ * matrix stays 0/1 (which keeps SkipPer's exact-zero skipping alive) and perm(original) =
+ * factor * perm(reduced).  An entry counts as non-zero when it is != 0; the reference counts > 0 in
+ * d1/d2 and != 0 in d34 -- identical on the non-negative matrices it supports.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "superman_b200.h"
+#include "sp_sched.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static void drop_compressed(sp_matrix *m) {
+  free(m->cptrs); free(m->rows); free(m->cvals); free(m->rptrs); free(m->cols); free(m->rvals);
+  m->cptrs = m->rows = m->rptrs = m->cols = NULL;
+  m->cvals = m->rvals = NULL;
+  m->nnz = 0;
+}
+
+static int row_deg(const double *a, int n, int i) {
+  int d = 0;
+  for (int j = 0; j < n; ++j) d += a[(size_t)i * n + j] != 0;
+  return d;
+}
+static int col_deg(const double *a, int n, int j) {
+  int d = 0;
+  for (int i = 0; i < n; ++i) d += a[(size_t)i * n + j] != 0;
+  return d;
+}
+
+/* getMinNnz (util.h:1181): smallest number of non-zeros over all rows and columns */
+int sp_matrix_min_degree(const sp_matrix *m) {
+  if (!m || !m->mat) { sp_set_error("null argument"); return SP_EINVAL; }
+  const int n = m->nov;
+  int best = n;
+  for (int i = 0; i < n; ++i) {
+    int d = row_deg(m->mat, n, i);
+    if (d < best) best = d;
+    d = col_deg(m->mat, n, i);
+    if (d < best) best = d;
+  }
+  return best;
+}
+
+/* remove row r and column c in place (n -> n-1) */
+static void drop_row_col(double *a, int n, int r, int c) {
+  size_t w = 0;
+  for (int i = 0; i < n; ++i) {
+    if (i == r) continue;
+    for (int j = 0; j < n; ++j) {
+      if (j == c) continue;
+      a[w++] = a[(size_t)i * n + j];
+    }
+  }
+}
+
+/* d1compress (util.h:1200-1258): the LAST row with one non-zero wins, else the last such column */
+static int step_d1(double *a, int *pn, double *factor) {
+  const int n = *pn;
+  int r = -1, c = -1;
+  for (int i = 0; i < n; ++i) {
+    if (row_deg(a, n, i) == 1) r = i;
+    if (col_deg(a, n, i) == 1) c = i;
+  }
+  if (r == -1 && c == -1) return 0;
+  if (r != -1) {
+    for (int j = 0; j < n; ++j)
+      if (a[(size_t)r * n + j] != 0) { c = j; break; }
+  } else {
+    for (int i = 0; i < n; ++i)
+      if (a[(size_t)i * n + c] != 0) { r = i; break; }
+  }
+  *factor *= a[(size_t)r * n + c];
+  drop_row_col(a, n, r, c);
+  *pn = n - 1;
+  return 1;
+}
+
+/* d2compress (util.h:1260-1330): the first index i whose row (preferred) or column has exactly two
+ * non-zeros.  Row r with entries in columns p < q: drop row r and column q, column p becomes
+ * A[i][p]*A[r][q] + A[i][q]*A[r][p] (expansion along the row + multilinearity); symmetric for a column. */
+static int step_d2(double *a, int *pn) {
+  const int n = *pn;
+  int r = -1, c = -1;
+  for (int i = 0; i < n; ++i) {
+    if (row_deg(a, n, i) == 2) r = i;
+    if (col_deg(a, n, i) == 2) c = i;
+    if (r != -1 || c != -1) break;
+  }
+  if (r == -1 && c == -1) return 0;
+  int p = -1, q = -1;
+  if (r != -1) {
+    for (int j = 0; j < n; ++j)
+      if (a[(size_t)r * n + j] != 0) { if (p == -1) p = j; else { q = j; break; } }
+    const double arp = a[(size_t)r * n + p], arq = a[(size_t)r * n + q];
+    for (int i = 0; i < n; ++i)
+      if (i != r) a[(size_t)i * n + p] = a[(size_t)i * n + p] * arq + a[(size_t)i * n + q] * arp;
+    drop_row_col(a, n, r, q);
+  } else {
+    for (int i = 0; i < n; ++i)
+      if (a[(size_t)i * n + c] != 0) { if (p == -1) p = i; else { q = i; break; } }
+    const double apc = a[(size_t)p * n + c], aqc = a[(size_t)q * n + c];
+    for (int j = 0; j < n; ++j)
+      if (j != c) a[(size_t)p * n + j] = a[(size_t)p * n + j] * aqc + a[(size_t)q * n + j] * apc;
+    drop_row_col(a, n, q, c);
+  }
+  *pn = n - 1;
+  return 2;
+}
+
+static int has_empty_line(const double *a, int n) {          /* checkEmpty, util.h:1165 */
+  for (int i = 0; i < n; ++i)
+    if (row_deg(a, n, i) == 0 || col_deg(a, n, i) == 0) return 1;
+  return 0;
+}
+
+int sp_matrix_reduce_step(sp_matrix *m, double *factor) {
+  if (!m || !m->mat || !factor) { sp_set_error("null argument"); return SP_EINVAL; }
+  drop_compressed(m);
+  if (m->nov <= 1) return 0;
+  int rc = step_d1(m->mat, &m->nov, factor);
+  if (!rc) rc = step_d2(m->mat, &m->nov);
+  return rc;
+}
+
+/* the loop of compress_singleton_and_then_recurse (main.cpp:1058-1090); a row or column without
+ * non-zeros ("Matrix is rank deficient! Perman is 0", exit(1) upstream) collapses the matrix to the
+ * 1x1 zero matrix with factor 0 instead of ending the process */
+int sp_matrix_reduce(sp_matrix *m, double *factor) {
+  if (!m || !m->mat || !factor) { sp_set_error("null argument"); return SP_EINVAL; }
+  drop_compressed(m);
+  *factor = 1.0;
+  int removed = 0;
+  for (;;) {
+    if (has_empty_line(m->mat, m->nov)) {
+      removed += m->nov - 1;
+      m->nov = 1;
+      m->mat[0] = 0.0;
+      *factor = 0.0;
+      break;
+    }
+    if (m->nov <= 1) break;
+    int rc = step_d1(m->mat, &m->nov, factor);
+    if (!rc) rc = step_d2(m->mat, &m->nov);
+    if (!rc) break;
+    ++removed;
+  }
+  return removed;
+}
+
+/* d34compress (util.h:1333-1407).  Row r (or, when no row qualifies at that index, column r -- the
+ * matrix is then transposed, as upstream) with min_deg in {3, 4} non-zeros in columns c0<c1<c2<c3
+ * (for three non-zeros c3 is the last zero column of the row):
+ *   perm(A) = perm(A1) + perm(A2),
+ *   A1 = A without row r and column c1, column c0 := A[r][c0]*A[i][c1] + A[r][c1]*A[i][c0],
+ *   A2 = A without row r and column c3, column c2 := A[r][c2]*A[i][c3] + A[r][c3]*A[i][c2]. */
+int sp_matrix_split34(sp_matrix *m, int min_deg, sp_matrix *second) {
+  if (!m || !m->mat || !second) { sp_set_error("null argument"); return SP_EINVAL; }
+  if (min_deg != 3 && min_deg != 4) { sp_set_error("split34: degree %d is not 3 or 4", min_deg); return SP_EINVAL; }
+  const int n = m->nov;
+  if (n < 5) { sp_set_error("split34 needs n >= 5 (got %d)", n); return SP_ELIMIT; }
+  double *a = m->mat;
+  int r = -1, c = -1;
+  for (int i = 0; i < n; ++i) {
+    if (row_deg(a, n, i) == min_deg) r = i;
+    if (col_deg(a, n, i) == min_deg) c = i;
+    if (r != -1 || c != -1) break;
+  }
+  if (r == -1 && c == -1) return 0;
+  double *t = (double *)malloc((size_t)n * n * sizeof(double));
+  double *b = (double *)calloc((size_t)n * n, sizeof(double));
+  if (!t || !b) { free(t); free(b); sp_set_error("out of memory"); return SP_ENOMEM; }
+  if (r == -1) {
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) t[(size_t)j * n + i] = a[(size_t)i * n + j];
+    r = c;
+  } else {
+    memcpy(t, a, (size_t)n * n * sizeof(double));
+  }
+  int nb[4] = {-1, -1, -1, -1}, k = 0, zeroloc = -1;
+  for (int j = 0; j < n; ++j) {
+    if (t[(size_t)r * n + j] != 0) nb[k++] = j; else zeroloc = j;
+  }
+  if (nb[3] == -1) nb[3] = zeroloc;
+  drop_compressed(m);
+  memset(a, 0, (size_t)n * n * sizeof(double));
+  const int n1 = n - 1;
+  const double *tr = t + (size_t)r * n;
+  for (int i = 0; i < n; ++i) {
+    if (i == r) continue;
+    const int il = i - (i > r);
+    const double *ti = t + (size_t)i * n;
+    for (int j = 0; j < n; ++j) {
+      if (j != nb[1]) {
+        const int jl = j - (j > nb[1]);
+        a[(size_t)il * n1 + jl] = (j != nb[0]) ? ti[j] : tr[nb[0]] * ti[nb[1]] + tr[nb[1]] * ti[nb[0]];
+      }
+      if (j != nb[3]) {
+        const int jl = j - (j > nb[3]);
+        b[(size_t)il * n1 + jl] = (j != nb[2]) ? ti[j] : tr[nb[2]] * ti[nb[3]] + tr[nb[3]] * ti[nb[2]];
+      }
+    }
+  }
+  free(t);
+  m->nov = n1;
+  memset(second, 0, sizeof(*second));
+  second->nov = n1;
+  second->type = m->type;
+  second->mat = b;
+  return 1;
+}
+
+/* scalesk + scaleMatrix (util.h:1445-1593): Sinkhorn-Knopp sweeps (columns, then rows) until the mean
+ * column sum and the mean row sum are both within 10 of `threshold`, then mat[i][j] *= rv[i] * cv[j].
+ * perm(original) = perm(scaled) / prod(cv) / prod(rv).  Sums run in CCS / CRS order (ascending row /
+ * column index) with the products associated as upstream: (val*cv)*rv per column, (val*rv)*cv per
+ * row.  Upstream loops forever when the sweeps do not converge; here at most 1000 sweeps. */
+int sp_matrix_scale(sp_matrix *m, double threshold, double *rv, double *cv) {
+  if (!m || !m->mat || !rv || !cv) { sp_set_error("null argument"); return SP_EINVAL; }
+  if (!(threshold > 0)) { sp_set_error("scaling threshold must be positive"); return SP_EINVAL; }
+  const int n = m->nov;
+  double *a = m->mat;
+  for (int i = 0; i < n; ++i) rv[i] = cv[i] = 1.0;
+  double max_error = 100;
+  int sweeps = 0;
+  while (max_error > 10.0 && sweeps < 1000) {
+    for (int j = 0; j < n; ++j) {
+      double sum = 0;
+      int any = 0;
+      for (int i = 0; i < n; ++i) {
+        const double v = a[(size_t)i * n + j];
+        if (v > 0) { sum += v * cv[j] * rv[i]; any = 1; }
+      }
+      if (any) cv[j] = threshold / sum;
+    }
+    for (int i = 0; i < n; ++i) {
+      double sum = 0;
+      int any = 0;
+      for (int j = 0; j < n; ++j) {
+        const double v = a[(size_t)i * n + j];
+        if (v > 0) { sum += v * rv[i] * cv[j]; any = 1; }
+      }
+      if (any) rv[i] = threshold / sum;
+    }
+    double colsum = 0, rowsum = 0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        const double v = a[(size_t)i * n + j];
+        if (v > 0) colsum += v * cv[j] * rv[i];
+      }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        const double v = a[(size_t)i * n + j];
+        if (v > 0) rowsum += v * rv[i] * cv[j];
+      }
+    const double e1 = fabs(threshold - colsum / n), e2 = fabs(threshold - rowsum / n);
+    max_error = e1 > e2 ? e1 : e2;
+    ++sweeps;
+  }
+  drop_compressed(m);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) a[(size_t)i * n + j] *= rv[i];
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) a[(size_t)i * n + j] *= cv[j];
+  return sweeps;
+}
+
+/* Dulmage-Mendelsohn fine decomposition (util.h:309-440): with a perfect matching M, entry (i, j)
+ * lies on some perfect matching iff row i and the row matched to column j are in the same strongly
+ * connected component of the digraph { i -> M(j) : A[i][j] != 0, (i, j) not in M }.  Entries that
+ * lie on no perfect matching contribute nothing to the permanent and are erased -- which feeds the
+ * degree compression and the sparse kernels.  (Upstream compares component[i] with component[j]
+ * using the column index j directly, which is only right when the matching is the diagonal; the
+ * routine is never called there.)  *matching receives the size of a maximum matching; when it is
+ * < nov the permanent is 0 and nothing is erased.  Returns the number of erased entries. */
+static int dm_augment(const double *a, int n, int i, int *seen, int *col_row, int stamp) {
+  for (int j = 0; j < n; ++j) {
+    if (a[(size_t)i * n + j] == 0 || seen[j] == stamp) continue;
+    seen[j] = stamp;
+    if (col_row[j] < 0 || dm_augment(a, n, col_row[j], seen, col_row, stamp)) { col_row[j] = i; return 1; }
+  }
+  return 0;
+}
+
+int sp_matrix_dm(sp_matrix *m, int *matching) {
+  if (!m || !m->mat) { sp_set_error("null argument"); return SP_EINVAL; }
+  const int n = m->nov;
+  double *a = m->mat;
+  int *buf = (int *)malloc((size_t)n * 9 * sizeof(int));
+  if (!buf) { sp_set_error("out of memory"); return SP_ENOMEM; }
+  int *seen = buf, *col_row = buf + n, *index = buf + 2 * n, *low = buf + 3 * n, *comp = buf + 4 * n,
+      *stack = buf + 5 * n, *call_i = buf + 6 * n, *call_j = buf + 7 * n, *onstack = buf + 8 * n;
+  for (int j = 0; j < n; ++j) { seen[j] = -1; col_row[j] = -1; }
+  int matched = 0;
+  for (int i = 0; i < n; ++i) matched += dm_augment(a, n, i, seen, col_row, i);
+  if (matching) *matching = matched;
+  if (matched < n) { free(buf); return 0; }
+  /* Tarjan, iterative; successor of row i through column j is col_row[j] */
+  for (int i = 0; i < n; ++i) { index[i] = -1; comp[i] = -1; onstack[i] = 0; }
+  int next_index = 0, ncomp = 0, sp = 0;
+  for (int root = 0; root < n; ++root) {
+    if (index[root] != -1) continue;
+    int depth = 0;
+    call_i[0] = root; call_j[0] = 0;
+    index[root] = low[root] = next_index++;
+    stack[sp++] = root; onstack[root] = 1;
+    while (depth >= 0) {
+      const int i = call_i[depth];
+      int advanced = 0;
+      while (call_j[depth] < n) {
+        const int j = call_j[depth]++;
+        if (a[(size_t)i * n + j] == 0 || col_row[j] == i) continue;
+        const int w = col_row[j];
+        if (index[w] == -1) {
+          index[w] = low[w] = next_index++;
+          stack[sp++] = w; onstack[w] = 1;
+          ++depth;
+          call_i[depth] = w; call_j[depth] = 0;
+          advanced = 1;
+          break;
+        }
+        if (onstack[w] && index[w] < low[i]) low[i] = index[w];
+      }
+      if (advanced) continue;
+      if (low[i] == index[i]) {
+        int w;
+        do { w = stack[--sp]; onstack[w] = 0; comp[w] = ncomp; } while (w != i);
+        ++ncomp;
+      }
+      --depth;
+      if (depth >= 0 && low[i] < low[call_i[depth]]) low[call_i[depth]] = low[i];
+    }
+  }
+  int erased = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (a[(size_t)i * n + j] != 0 && comp[i] != comp[col_row[j]]) { a[(size_t)i * n + j] = 0; ++erased; }
+  free(buf);
+  if (erased) drop_compressed(m);
+  return erased;
+}
+
+/* ---- compress_singleton_and_then_recurse / compress_and_calculate_recursive / scale_and_calculate
+ * (main.cpp:993-1260) on the GPU engine ---------------------------------------------------------- */
+typedef struct reduce_ctx {
+  int sparse, preprocessing, algo_id, gpu_num, threads, leaf_nov;
+  double threshold;
+  sp_stats total;
+  int leaves, failed, altered;
+} reduce_ctx;
+
+static void stats_add(sp_stats *t, const sp_stats *s) {
+  t->kernel_ms += s->kernel_ms;
+  for (int d = 0; d < SP_MAX_DEVICES; ++d) {
+    t->device_ms[d] += s->device_ms[d];
+    t->device_units[d] += s->device_units[d];
+  }
+  t->units += s->units;
+  t->visited += s->visited;
+  t->launches += s->launches;
+  if (s->devices > t->devices) t->devices = s->devices;
+  t->path = s->path;
+  t->tile_log2 = s->tile_log2;
+}
+
+static double run_leaf(reduce_ctx *cx, sp_matrix *m) {
+  double rv[64], cv[64];
+  const int n = m->nov;
+  int rc;
+  /* threshold 0 = automatic: merged columns carry products of entries, which unbalances the row sums
+   * and costs the Ryser sum up to ~1e-6 of relative accuracy in FP64 (measured: tests/
+   * test_host_reduce.py); one Sinkhorn sweep to row sums 1 restores ~1e-13.  Untouched matrices are
+   * not scaled (SkipPer's exact-zero skipping depends on the values). */
+  const double threshold = cx->threshold > 0 ? cx->threshold : (cx->threshold == 0 && cx->altered) ? 1.0 : -1.0;
+  if (threshold > 0 && n > 1) {
+    if (n > 64) { sp_set_error("exact paths support n <= 64 (got %d)", n); cx->failed = SP_ELIMIT; return NAN; }
+    rc = sp_matrix_scale(m, threshold, rv, cv);
+    if (rc < 0) { cx->failed = rc; return NAN; }
+  }
+  sp_stats st;
+  double perman;
+  if (!cx->sparse) {
+    perman = sp_dense_ryser(m->mat, n, cx->algo_id, cx->gpu_num, 0, cx->threads, &st);
+  } else {
+    rc = sp_matrix_compress(m, cx->preprocessing);
+    if (rc != SP_OK) { cx->failed = rc; return NAN; }
+    if (cx->algo_id == 7 || cx->algo_id == 8)
+      perman = sp_skipper(m->mat, m->rptrs, m->cols, m->cptrs, m->rows, m->cvals, n, cx->algo_id, cx->gpu_num, 0,
+                          cx->threads, &st);
+    else
+      perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, n, cx->algo_id, cx->gpu_num, 0, cx->threads, &st);
+  }
+  if (isnan(perman) && st.error) { cx->failed = st.error; return NAN; }
+  stats_add(&cx->total, &st);
+  ++cx->leaves;
+  if (threshold > 0 && n > 1) {                 /* main.cpp:1143-1149 */
+    for (int i = 0; i < n; ++i) perman /= cv[i];
+    for (int i = 0; i < n; ++i) perman /= rv[i];
+  }
+  return perman;
+}
+
+/* consumes m */
+static double recurse(reduce_ctx *cx, sp_matrix *m) {
+  double factor = 1.0, result;
+  for (;;) {
+    if (cx->failed) { result = NAN; break; }
+    const int mind = sp_matrix_min_degree(m);
+    if (mind == 0) { result = 0.0; break; }
+    if (!(mind < 5 && m->nov > cx->leaf_nov)) { result = run_leaf(cx, m); break; }
+    if (mind <= 2) {
+      /* one d1 / d2 step (main.cpp:1010-1028); the d1 entry goes to `factor`, not into row 0 */
+      int rc = (mind == 1) ? step_d1(m->mat, &m->nov, &factor) : step_d2(m->mat, &m->nov);
+      if (rc <= 0) { sp_set_error("degree compression found no candidate"); cx->failed = SP_EINVAL; result = NAN; break; }
+      cx->altered = 1;
+      continue;
+    }
+    sp_matrix second;
+    int rc = sp_matrix_split34(m, mind, &second);
+    if (rc <= 0) { cx->failed = rc < 0 ? rc : SP_EINVAL; result = NAN; break; }
+    cx->altered = 1;
+    sp_matrix first = *m;                       /* ownership moves into the two recursive calls */
+    memset(m, 0, sizeof(*m));
+    const double p1 = recurse(cx, &first);
+    const double p2 = recurse(cx, &second);
+    return factor * (p1 + p2);
+  }
+  sp_matrix_free(m);
+  return factor * result;
+}
+
+double sp_permanent_compressed(const double *mat, int nov, int sparse, int preprocessing, int algo_id, int gpu_num,
+                               int threads, double scaling_threshold, int leaf_nov, sp_stats *stats) {
+  const double t0 = sp_now_ms();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  reduce_ctx cx;
+  memset(&cx, 0, sizeof(cx));
+  cx.sparse = sparse; cx.preprocessing = preprocessing; cx.algo_id = algo_id; cx.gpu_num = gpu_num;
+  cx.threads = threads; cx.threshold = scaling_threshold;
+  /* `densemat->nov > 30`, main.cpp:1008; leaf_nov < 0: no compression at all (scaling only) */
+  cx.leaf_nov = leaf_nov > 0 ? leaf_nov : leaf_nov == 0 ? 30 : SP_MAX_NOV;
+  sp_matrix m;
+  int rc = sp_matrix_from_dense(mat, nov, &m);
+  if (rc != SP_OK) { if (stats) stats->error = rc; return NAN; }
+  double factor = 1.0;
+  rc = leaf_nov < 0 ? 0 : sp_matrix_reduce(&m, &factor);
+  if (rc < 0) { sp_matrix_free(&m); if (stats) stats->error = rc; return NAN; }
+  cx.altered = rc > 0;
+  double perman = (factor == 0.0) ? (sp_matrix_free(&m), 0.0) : factor * recurse(&cx, &m);
+  if (stats) {
+    *stats = cx.total;
+    stats->chunks = cx.leaves;
+    stats->wall_ms = sp_now_ms() - t0;
+    stats->error = cx.failed;
+  }
+  return cx.failed ? NAN : perman;
+}

@@ -246,3 +246,77 @@ class Reference:
 
 def have_reference() -> bool:
     return os.path.exists(REF_SO)
+
+
+REF_REVISED_SO = os.path.join(ORACLE_DIR, "_ref", "libref_revised.so")
+
+
+def have_revised_reference() -> bool:
+    return os.path.exists(REF_REVISED_SO)
+
+
+class RevisedReference:
+    """The structural preprocessing of the reference's revised front-end (revised_perman/util.h)
+    behind oracle/_ref/libref_revised.so."""
+
+    def __init__(self):
+        if not os.path.exists(REF_REVISED_SO):
+            raise FileNotFoundError(REF_REVISED_SO)
+        self.lib = L = C.CDLL(REF_REVISED_SO)
+        L.rev_min_nnz.restype = C.c_int
+        L.rev_min_nnz.argtypes = [_dp, C.c_int]
+        for name in ("rev_d1compress", "rev_d2compress"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [_dp, C.c_int]
+        L.rev_d34compress.restype = C.c_int
+        L.rev_d34compress.argtypes = [_dp, C.c_int, _dp, C.c_int]
+        L.rev_scalesk.restype = None
+        L.rev_scalesk.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, C.c_double, _dp, _dp]
+
+    def min_nnz(self, mat) -> int:
+        a = _d(mat)
+        return self.lib.rev_min_nnz(_pd(a), a.shape[0])
+
+    def _step(self, fn, mat):
+        a = _d(mat).copy(); n = a.shape[0]
+        flat = a.reshape(-1).copy()
+        k = fn(_pd(flat), n)
+        return flat[:k * k].reshape(k, k).copy()
+
+    def d1compress(self, mat):
+        return self._step(self.lib.rev_d1compress, mat)
+
+    def d2compress(self, mat):
+        return self._step(self.lib.rev_d2compress, mat)
+
+    def d34compress(self, mat, min_deg):
+        a = _d(mat).copy(); n = a.shape[0]
+        flat = a.reshape(-1).copy()
+        other = np.zeros(n * n, dtype=np.float64)
+        k = self.lib.rev_d34compress(_pd(flat), n, _pd(other), min_deg)
+        if k == n:
+            return None
+        return flat[:k * k].reshape(k, k).copy(), other[:k * k].reshape(k, k).copy()
+
+    def scalesk(self, mat, threshold):
+        """(rv, cv) from the CRS/CCS of mat in natural order"""
+        a = _d(mat); n = a.shape[0]
+        rptrs = [0]; cols = []; rvals = []
+        for i in range(n):
+            for j in range(n):
+                if a[i, j] > 0:
+                    cols.append(j); rvals.append(a[i, j])
+            rptrs.append(len(cols))
+        cptrs = [0]; rows = []; cvals = []
+        for j in range(n):
+            for i in range(n):
+                if a[i, j] > 0:
+                    rows.append(i); cvals.append(a[i, j])
+            cptrs.append(len(rows))
+        cptrs, rows, rptrs, cols = _i(cptrs), _i(rows), _i(rptrs), _i(cols)
+        cvals, rvals = _d(cvals), _d(rvals)
+        rv = np.zeros(n); cv = np.zeros(n)
+        self.lib.rev_scalesk(n, len(rows), _pi(cptrs), _pi(rows), _pd(cvals), _pi(rptrs), _pi(cols), _pd(rvals),
+                             float(threshold), _pd(rv), _pd(cv))
+        return rv, cv

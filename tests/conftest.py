@@ -28,6 +28,14 @@ def reference():
 
 
 @pytest.fixture(scope="session")
+def revised():
+    from _oracle import RevisedReference, have_revised_reference
+    if not have_revised_reference():
+        pytest.skip("oracle/_ref/libref_revised.so not built (reference tree absent)")
+    return RevisedReference()
+
+
+@pytest.fixture(scope="session")
 def sp():
     import superman_b200
     return superman_b200

@@ -1,0 +1,138 @@
+"""sp_permanent_compressed (the revised front-end's -o / -u path: degree compression, d34 splits,
+Sinkhorn scaling; host/sp_reduce.c) on the GPU engine against the CPU oracle.  The truth for n > 30
+is the same recursion evaluated with the long-double oracle at small leaves (pinned against the
+direct long-double permanent on the CPU in tests/test_host_reduce.py)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_host_reduce import sparse_matrix
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PERMAN = os.path.join(ROOT, "superman_b200", "perman")
+
+
+def oracle_compressed(sp, oracle, a, leaf_nov=14):
+    def leaf(m, f):
+        if m.nov == 1:
+            return f * m.mat[0, 0]
+        rv, cv, _ = m.scale(1.0)
+        p = oracle.perm_ld(m.mat)
+        for v in cv:
+            p /= v
+        for v in rv:
+            p /= v
+        return f * p
+
+    def total(a):
+        m = sp.Matrix.from_dense(a)
+        f = m.reduce()
+        if f == 0.0:
+            return 0.0
+        d = m.min_degree()
+        if m.nov > leaf_nov and d in (3, 4):
+            other = m.split34(d)
+            return f * (total(m.mat) + total(other.mat))
+        assert m.nov <= 24, "oracle leaf too large"
+        return leaf(m, f)
+
+    return total(a)
+
+
+def banded(rng, n, weights):
+    """rows with 3-4 entries near the diagonal: every reduction step applies somewhere"""
+    a = np.zeros((n, n))
+    for i in range(n):
+        for j in {i, (i + 1) % n, (i + int(rng.integers(2, 5))) % n, (i + n - 1) % n if rng.random() < 0.5 else i}:
+            a[i, j] = float(rng.integers(1, 4)) if weights == "int" else round(float(rng.uniform(0.2, 3.0)), 6)
+    return a
+
+
+@pytest.mark.parametrize("n,weights,sparse,algo,pre", [
+    (33, "real", False, 4, 0), (34, "int", True, 4, 1), (36, "real", True, 7, 2), (38, "int", False, 4, 0),
+    (40, "real", True, 4, 1)])
+def test_compressed_matches_oracle(sp, oracle, n, weights, sparse, algo, pre):
+    rng = np.random.default_rng(100 + n)
+    a = banded(rng, n, weights)
+    want = oracle_compressed(sp, oracle, a)
+    st = sp.SpStats()
+    got = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, stats=st)
+    assert got == pytest.approx(want, rel=1e-9), (got, want)
+    assert st.chunks >= 1 and st.error == 0
+    # explicit threshold (-u 4) and no scaling at all agree too (looser without scaling)
+    got_u = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, scaling_threshold=4.0)
+    assert got_u == pytest.approx(want, rel=1e-9)
+    got_plain = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, scaling_threshold=-1.0)
+    assert got_plain == pytest.approx(want, rel=1e-4)
+    # a deeper recursion (more, smaller leaves) gives the same permanent
+    st2 = sp.SpStats()
+    got_deep = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, leaf_nov=20, stats=st2)
+    assert got_deep == pytest.approx(want, rel=1e-9)
+    assert st2.chunks >= st.chunks
+
+
+def test_compressed_equals_direct_on_a_matrix_without_structure(sp, oracle):
+    rng = np.random.default_rng(9)
+    n = 20
+    a = (rng.random((n, n)) < 0.6) * rng.uniform(0.5, 2.0, (n, n))
+    a[np.arange(n), np.arange(n)] = 1.0
+    assert (a != 0).sum(axis=0).min() >= 5 and (a != 0).sum(axis=1).min() >= 5
+    st = sp.SpStats()
+    got = sp.permanent_compressed(a, stats=st)
+    assert st.chunks == 1
+    assert got == sp.dense_ryser(a)                       # untouched matrix: same kernel, same bits
+    assert got == pytest.approx(oracle.perm_ld(a), rel=1e-10)
+    # scaling only (leaf_nov < 0), as -u without -o
+    got_u = sp.permanent_compressed(a, scaling_threshold=2.0, leaf_nov=-1)
+    assert got_u == pytest.approx(oracle.perm_ld(a), rel=1e-10)
+
+
+def test_compressed_zero_and_tiny(sp):
+    z = np.ones((9, 9)); z[:, 4] = 0
+    assert sp.permanent_compressed(z) == 0.0
+    assert sp.permanent_compressed(np.eye(12) * 2.0) == 4096.0          # all d1 steps, 1x1 leaf
+    tri = np.triu(np.ones((10, 10)))
+    assert sp.permanent_compressed(tri, sparse=True, algo_id=4, preprocessing=1) == 1.0
+
+
+def write_matrix(path, a, kind):
+    n = a.shape[0]
+    nz = [(i, j) for i in range(n) for j in range(n) if a[i, j] != 0]
+    with open(path, "w") as f:
+        f.write(f"{n} {len(nz)} {kind}\n")
+        for i, j in nz:
+            f.write(f"{i} {j} {int(a[i, j]) if kind == 'int' else repr(float(a[i, j]))}\n")
+
+
+def run_cli(*args):
+    env = dict(os.environ, PERMAN_PRECISION="17")
+    r = subprocess.run([PERMAN, *args], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("Result17:")][-1]
+    return float(line.split()[2]), r.stdout
+
+
+def test_cli_compression_scaling_and_dm_flags(sp, oracle, tmp_path):
+    rng = np.random.default_rng(36)
+    a = banded(rng, 36, "int")
+    want = oracle_compressed(sp, oracle, a)
+    path = str(tmp_path / "banded36.txt")
+    write_matrix(path, a, "int")
+    for extra in (("-p", "4", "-o"), ("-s", "-p", "4", "-r", "1", "-o"), ("-s", "-p", "7", "-r", "2", "-o", "-u", "2"),
+                  ("-p", "4", "--reduce", "--dm")):
+        got, out = run_cli("-f", path, *extra)
+        assert got == pytest.approx(want, rel=1e-9), (extra, got, want)
+        assert "Compressed:" in out
+        if "--dm" in extra:
+            assert "DM: maximum matching 36 of 36" in out
+    # -u alone: Sinkhorn scaling, no compression -- on a small dense matrix
+    b = sparse_matrix(rng, 18, 8, 12, "real")
+    pathb = str(tmp_path / "dense18.txt")
+    write_matrix(pathb, b, "double")
+    got, out = run_cli("-f", pathb, "-p", "4", "-u", "3")
+    assert got == pytest.approx(oracle.perm_ld(b), rel=1e-10)
+    assert "Compressed: 1 leaf" in out
