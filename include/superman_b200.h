@@ -107,6 +107,10 @@ int  sp_matrix_grid(int m, int n, sp_matrix *out);
  *   perm(before) = perm(m) + perm(second).  Returns 1, or 0 when no row / column has that degree.
  * sp_matrix_scale: scalesk + scaleMatrix (util.h:1445-1593), rv / cv receive the nov row / column
  *   factors; perm(original) = perm(scaled) / prod(cv) / prod(rv).  Returns the number of sweeps.
+ * sp_matrix_balance: Sinkhorn-Knopp to convergence (every column sum within 0.1 % of threshold after
+ *   the row pass, <= 1000 sweeps); same outputs as sp_matrix_scale.  What sp_permanent_compressed
+ *   uses: upstream's stopping rule (mean sums only) ends after one sweep, which leaves the matrices
+ *   produced by the degree compression too unbalanced for a Ryser sum in FP64.
  * sp_matrix_dm: Dulmage-Mendelsohn fine decomposition (util.h:309): erases the entries that lie on no
  *   perfect matching (they cannot contribute to the permanent); *matching receives the size of a
  *   maximum matching (< nov: the permanent is 0, nothing erased).  Returns the entries erased. */
@@ -115,14 +119,16 @@ int  sp_matrix_reduce_step(sp_matrix *m, double *factor);
 int  sp_matrix_reduce(sp_matrix *m, double *factor);
 int  sp_matrix_split34(sp_matrix *m, int min_deg, sp_matrix *second);
 int  sp_matrix_scale(sp_matrix *m, double threshold, double *rv, double *cv);
+int  sp_matrix_balance(sp_matrix *m, double threshold, double *rv, double *cv);
 int  sp_matrix_dm(sp_matrix *m, int *matching);
 /* compress_singleton_and_then_recurse + compress_and_calculate_recursive + scale_and_calculate
  * (revised_perman/main.cpp:993-1260) on the GPU engine: degree-1/2 compression, then -- while the
  * smallest degree is < 5 and nov > leaf_nov (0: upstream's 30; < 0: no compression at all, scaling
- * only) -- d1 / d2 steps and d34 splits; every leaf is Sinkhorn-scaled to row / column sums
- * scaling_threshold when that is > 0 (upstream's -u), to 1 when it is 0 and the compression changed
- * the matrix (merged columns unbalance the row sums and cost FP64 Ryser ~1e-6 of accuracy), not at
- * all when it is < 0 (upstream's default), then computed
+ * only) -- d1 / d2 steps and d34 splits; every leaf is reduced to its total support (sp_matrix_dm)
+ * and Sinkhorn-balanced (sp_matrix_balance) to row / column sums scaling_threshold when that is > 0
+ * (upstream's -u), to 1 when it is 0 and the compression changed the matrix (without it FP64 Ryser
+ * on the merged matrices can be off by tens of percent), not at all when it is < 0 (upstream's
+ * default), then computed
  * with sp_dense_ryser (sparse == 0; algo_id 0-6) or, after sp_matrix_compress(preprocessing),
  * sp_sparse_ryser (algo_id 1-6) / sp_skipper (7, 8).  mat is the row-major nov x nov matrix as read
  * (not reordered).  stats: sums over the leaves, chunks = number of leaves. */

@@ -119,6 +119,7 @@ _sig("sp_matrix_reduce_step", C.c_int, [_mp, _dp])
 _sig("sp_matrix_min_degree", C.c_int, [_mp])
 _sig("sp_matrix_split34", C.c_int, [_mp, C.c_int, _mp])
 _sig("sp_matrix_scale", C.c_int, [_mp, C.c_double, _dp, _dp])
+_sig("sp_matrix_balance", C.c_int, [_mp, C.c_double, _dp, _dp])
 _sig("sp_matrix_dm", C.c_int, [_mp, C.POINTER(C.c_int)])
 _sig("sp_permanent_compressed", C.c_double,
      [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(SpStats)])

@@ -13,7 +13,7 @@ from ._ffi import SpStats, lib
 
 __all__ = [
     "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
-    "dense_ryser", "dense_ryser_range", "DenseHandle",
+    "SpStats", "dense_ryser", "dense_ryser_range", "DenseHandle", "permanent_compressed",
     "sparse_ryser", "skipper", "sparse_ryser_range",
     "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense",
     "gpu_perman64_rasmussen_sparse", "gpu_perman64_rasmussen_multigpucpu_chunks_sparse",
@@ -133,12 +133,12 @@ class Matrix:
         other._live = True
         return other
 
-    def scale(self, threshold: float):
-        """scalesk + scaleMatrix; returns (rv, cv, sweeps)"""
+    def scale(self, threshold: float, converge: bool = False):
+        """scalesk + scaleMatrix (converge=True: Sinkhorn to convergence, sp_matrix_balance); returns (rv, cv, sweeps)"""
         n = self._m.nov
         rv = np.zeros(n, dtype=np.float64)
         cv = np.zeros(n, dtype=np.float64)
-        rc = lib.sp_matrix_scale(C.byref(self._m), float(threshold), rv.ctypes.data_as(_ffi._dp),
+        rc = (lib.sp_matrix_balance if converge else lib.sp_matrix_scale)(C.byref(self._m), float(threshold), rv.ctypes.data_as(_ffi._dp),
                                  cv.ctypes.data_as(_ffi._dp))
         if rc < 0:
             raise SupermanError(rc, _ffi.last_error())

@@ -10,6 +10,8 @@ import os
 import numpy as np
 import pytest
 
+from _compressed import banded, oracle_compressed
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "revised.json")
 
 
@@ -123,44 +125,50 @@ def test_scalesk_matches_reference_live(sp, revised):
 
 
 def test_reduce_then_split_keeps_the_permanent(sp, oracle):
-    """the whole recursion of sp_permanent_compressed with the CPU oracle at the leaves: reduce, then
-    split while the smallest degree is 3 or 4; leaves are Sinkhorn-scaled as the driver does.  Without
-    the scaling the merged columns unbalance the row sums and even a long-double Ryser sum loses
-    digits (1e-10 here; ~1e-6 in FP64), which is why the driver scales altered matrices by default."""
+    """the whole recursion of sp_permanent_compressed with the CPU oracle at the leaves (reduce, then
+    split while the smallest degree is 3 or 4) reproduces the permanent of the original matrix --
+    provided the leaves are Sinkhorn-balanced to convergence.  Merged columns carry products of
+    entries: without balancing, or with the single sweep upstream's stopping rule amounts to, the Ryser
+    sum cancels catastrophically even in long double."""
     rng = np.random.default_rng(7)
-
-    def leaf(m, f, scaled):
-        if m.nov == 1:
-            return f * m.mat[0, 0]
-        if not scaled:
-            return f * oracle.perm_ld(m.mat)
-        rv, cv, _ = m.scale(1.0)
-        p = oracle.perm_ld(m.mat)
-        for v in cv:
-            p /= v
-        for v in rv:
-            p /= v
-        return f * p
-
-    def total(a, scaled):
-        m = sp.Matrix.from_dense(a)
-        f = m.reduce()
-        if f == 0.0:
-            return 0.0
-        d = m.min_degree()
-        if m.nov > 6 and d in (3, 4):
-            other = m.split34(d)
-            return f * (total(m.mat, scaled) + total(other.mat, scaled))
-        return leaf(m, f, scaled)
-
-    worst_plain = 0.0
     for trial in range(25):
         n = int(rng.integers(8, 15))
         a = sparse_matrix(rng, n, 2, 4, "int" if trial % 2 else "real")
+        assert oracle_compressed(sp, oracle, a, leaf_nov=6) == pytest.approx(oracle.perm_ld(a), rel=1e-13), trial
+    worst = {"none": 0.0, "one": 0.0, "full": 0.0}
+    for n, seed in ((22, 2), (24, 0), (24, 8)):
+        a = banded(np.random.default_rng(seed * 100 + n), n, "real" if seed % 2 else "int")
         want = oracle.perm_ld(a)
-        assert total(a, True) == pytest.approx(want, rel=1e-13), trial
-        worst_plain = max(worst_plain, abs(total(a, False) / want - 1))
-    assert worst_plain < 1e-8
+        for leaf in (6, 8, 10):
+            for mode in worst:
+                got = oracle_compressed(sp, oracle, a, leaf_nov=leaf, mode=mode)
+                worst[mode] = max(worst[mode], abs(got / want - 1))
+    assert worst["full"] < 1e-13
+    assert worst["one"] > 1e-5 and worst["none"] > 1.0        # the reason sp_matrix_balance exists
+
+
+def test_balance_converges_and_keeps_the_permanent(sp, oracle):
+    rng = np.random.default_rng(12)
+    for trial in range(20):
+        n = int(rng.integers(4, 13))
+        base = sparse_matrix(rng, n, 1, 4, "real")
+        rs, cs = np.exp(rng.uniform(-12, 12, n)), np.exp(rng.uniform(-12, 12, n))
+        a = base * rs[:, None] * cs[None, :]          # badly scaled: a direct Ryser sum loses ~1e-5 here
+        want = oracle.perm_ld(base) * np.prod(rs) * np.prod(cs)
+        m = sp.Matrix.from_dense(a)
+        m.dm()
+        support = m.mat.copy()
+        thr = float(rng.choice([1.0, 3.0]))
+        rv, cv, sweeps = m.scale(thr, converge=True)
+        assert 1 <= sweeps < 1000
+        b = m.mat
+        assert np.allclose(b.sum(axis=1), thr, rtol=1e-12) and np.allclose(b.sum(axis=0), thr, rtol=2e-3)
+        assert np.allclose(b, support * rv[:, None] * cv[None, :], rtol=1e-15)
+        p = oracle.perm_ld(b)
+        for i in range(n):
+            p /= cv[i]
+            p /= rv[i]
+        assert p == pytest.approx(want, rel=1e-12), trial
 
 
 def test_dm_erases_exactly_the_entries_on_no_perfect_matching(sp, oracle):
