@@ -7,8 +7,10 @@
 //   hot rows (level < B): X in registers, in B*S fixed slots, S per level (the host packs the rows
 //     into slots; free slots hold the neutral row x = 1, entries 0).  A level-L slot takes only
 //     2^(B-L) distinct values inside a block, so it costs 2^(B-L) updates and multiplies into its
-//     level's 2^(B-L) running products PL[L][.] instead of 2^B of each; the 2^B terms of a block are
-//     recombined as  term_u = PL[0][u] * PL[1][u>>1] * ... * PL[B-1][u>>(B-1)] * Q.
+//     level's 2^(B-L) running products PL[L][.] instead of 2^B of each.  The 2^B terms of a block,
+//     term_u = PL[0][u] * PL[1][u>>1] * ... * PL[B-1][u>>(B-1)] * Q, are summed with their signs by
+//     pairing bottom-up: E_0[w] = PL0[2w] - PL0[2w+1], E_L[w] = PL_L[2w] E_{L-1}[2w] + PL_L[2w+1]
+//     E_{L-1}[2w+1], sum = Q * E_{B-1}[0] -- 2^B + B - 1 instructions instead of 3 * 2^B - 2.
 //     Everything here is compile-time structured: straight-line code, no runtime branch.
 //   register-cold rows: the R cold rows of lowest level (the ones refreshed most often) also stay
 //     in registers: one update and one multiply per block, in straight-line code.
@@ -16,7 +18,9 @@
 //     Their product Q is kept as suffix products SP[i] = prod(rows of level >= B+i): the block that
 //     flips high column k only touches the rows of level <= k, refreshes SP[k-B .. 0] and reuses
 //     SP[k-B+1].  Half of the blocks flip column B, a quarter column B+1, ...: the expected number
-//     of cold rows touched per block is small.
+//     of cold rows touched per block is small.  Levels without rows share one SP slot with the
+//     next level that has some (s_grp), and every row knows the slot it closes (s_slot, a dummy
+//     slot for most rows), so the refresh is ONE flat loop over the touched rows.
 //
 // SkipPer (SKIP = true): terms with a zero cold row are exact zeros (Q == 0).  Tiles whose
 // tile-constant rows (level >= c) contain a zero are dropped by a warp-wide filter (ballot +
@@ -28,6 +32,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "ryser_reg.cuh"
+
 
 namespace spb {
 
@@ -55,8 +60,8 @@ struct LevelLayout {
   static constexpr int LB = B + (B & 1);
 };
 
-// dynamic shared memory (doubles):  colT_hot | lowR | dcold | xb_hot | xb_cold | Xc[NC][T] | SP[c-B+1][T]
-// then ints: cold_start
+// dynamic shared memory (doubles):  colT_hot | lowR | dcold | xb_hot | xb_cold | Xc[NC][T] | SP[c-B+2][T]
+// then ints: cold_start[n-B+2] | grp[c-B+1] | slot[NC]
 template <int B, int S, int R, int THREADS, int MINBLOCKS, bool SKIP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 level_reg_kernel(const LevelArgs a) {
@@ -71,8 +76,10 @@ level_reg_kernel(const LevelArgs a) {
   double* s_xbh = s_dcold + (size_t)(n - 1) * NCP;
   double* s_xbc = s_xbh + HSP;
   double* s_X = s_xbc + NCP;                    // [NC][THREADS]
-  double* s_SP = s_X + (size_t)NC * THREADS;    // [nseg + 1][THREADS]
-  int* s_cs = reinterpret_cast<int*>(s_SP + (size_t)(nseg + 1) * THREADS);
+  double* s_SP = s_X + (size_t)NC * THREADS;    // [nseg + 2][THREADS]: one per group of levels + a dummy
+  int* s_cs = reinterpret_cast<int*>(s_SP + (size_t)(nseg + 2) * THREADS);
+  int* s_grp = s_cs + (n - B + 2);              // [nseg + 1]  SP slot of segment seg
+  int* s_slot = s_grp + (nseg + 1);             // [NC]        SP slot closed by cold row jc (or the dummy)
   __shared__ double warp_part[WARPS];
   __shared__ unsigned long long warp_vis[WARPS];
   __shared__ unsigned long long queue[WARPS][64];
@@ -83,6 +90,20 @@ level_reg_kernel(const LevelArgs a) {
   for (int e = threadIdx.x; e < HT; e += THREADS) s_xbh[e] = a.xb_hot[e];
   for (int e = threadIdx.x; e < NC; e += THREADS) s_xbc[e] = a.xb_cold[e];
   for (int e = threadIdx.x; e < n - B + 2; e += THREADS) s_cs[e] = a.cold_start[e];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // segments with the same first row (levels without rows) share a slot
+    int g = 0;
+    s_grp[0] = 0;
+    for (int seg = 1; seg <= nseg; ++seg) {
+      if (s_cs[seg] != s_cs[seg - 1]) ++g;
+      s_grp[seg] = g;
+    }
+    const int dummy = g + 1;
+    for (int jc = 0; jc < NC; ++jc) s_slot[jc] = dummy;
+    for (int seg = 0; seg <= nseg; ++seg)
+      if (s_cs[seg] < NC) s_slot[s_cs[seg]] = s_grp[seg];
+  }
   __syncthreads();
 
   const uint32_t sm_colT = (uint32_t)__cvta_generic_to_shared(s_colT);
@@ -145,20 +166,15 @@ level_reg_kernel(const LevelArgs a) {
     {
       // cold rows, from the last (highest level) to the first, building the suffix products
       double run = 1.0;
-      int seg = n - B;                           // segment of the row being visited
+      if (tc_first == NC) mySP[s_grp[nseg] * THREADS] = 1.0;     // no tile-constant rows: empty product
       for (int jc = NC - 1; jc >= 0; --jc) {
-        while (jc < s_cs[seg]) {                 // crossed into a lower segment: close the upper ones
-          if (seg <= nseg) mySP[seg * THREADS] = run;
-          --seg;
-        }
         double x = s_xbc[jc];
         for (int k = c - 1; k < n - 1; ++k)
           x = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], x);
         myX[jc * THREADS] = x;
         run *= x;
+        mySP[s_slot[jc] * THREADS] = run;
       }
-      for (; seg >= 0; --seg)
-        if (seg <= nseg) mySP[seg * THREADS] = run;
     }
 
     double tile_acc = 0.0;
@@ -173,26 +189,26 @@ level_reg_kernel(const LevelArgs a) {
       const double sg = (blk != 0) ? (up ? -1.0 : 1.0) : 0.0;
       const double sg_top = (blk & 1) ? -1.0 : 1.0;
 
+      const uint32_t hi_addr = sm_colT + (uint32_t)(k * HSP * 8);
       // ---- cold rows of level <= k: update, refresh SP[z .. 0] ----
       double Q;
       if (blk != 0) {
-        double run = mySP[(z + 1) * THREADS];
+        double run = mySP[s_grp[z + 1] * THREADS];
         const double* dk = s_dcold + k * NCP;
-        for (int seg = z; seg >= 0; --seg) {
-          const int lo = s_cs[seg];
-          for (int jc = s_cs[seg + 1] - 1; jc >= lo; --jc) {
-            const double x = fma(sg, dk[jc], myX[jc * THREADS]);
-            myX[jc * THREADS] = x;
-            run *= x;
-          }
-          mySP[seg * THREADS] = run;
+        double* px = myX + (size_t)s_cs[z + 1] * THREADS;
+        int jc = s_cs[z + 1] - 1;
+        for (; jc >= 0; --jc) {
+          px -= THREADS;
+          const double x = fma(sg, dk[jc], *px);
+          *px = x;
+          run *= x;
+          mySP[s_slot[jc] * THREADS] = run;
         }
         Q = run;
       } else {
         Q = mySP[0];
       }
 
-      const uint32_t hi_addr = sm_colT + (uint32_t)(k * HSP * 8);
       // ---- register-cold rows: one update, one multiply ----
       if (R > 0) {
         double r0 = 1.0, r1 = 1.0;
@@ -210,52 +226,73 @@ level_reg_kernel(const LevelArgs a) {
         // exact zeros: only the block's net effect on the hot slots (high column + column B-1)
 #pragma unroll
         for (int i = 0; i < HS; ++i) {
-          double d, mt;
-          lds_f64(hi_addr + (uint32_t)(i * 8), d);
+          double mt;
           lds_f64(sm_lowR + (uint32_t)((i * LB + (B - 1)) * 8), mt);
+          double d;
+          lds_f64(hi_addr + (uint32_t)(i * 8), d);
           xh[i] = fma(sg_top, mt, fma(sg, d, xh[i]));
         }
       } else {
-        // ---- hot slots: level L = slot / S takes 2^(B-L) values ----
+        // ---- hot slots: level L takes 2^(B-L) values; the slots of a level advance together, CH
+        // independent chains at a time, and multiply into the level's running products PL[L][w] ----
+        constexpr int CH = (B * S + R > 20) ? 1 : (S % 3 == 0) ? 3 : (S % 2 == 0) ? 2 : 1;   // register budget
         double PL[2 * NB];
         // layout: level L occupies indices [off(L), off(L) + 2^(B-L)), off(L) = 2*NB - 2*(NB >> L)
 #pragma unroll
-        for (int i = 0; i < HS; ++i) {
-          const int L = i / S;                   // compile-time after unrolling
+        for (int L = 0; L < B; ++L) {
           const int off = 2 * NB - 2 * (NB >> L);
           const int cnt = NB >> L;
-          double m[LB];
 #pragma unroll
-          for (int qq = 0; qq < LB; qq += 2) lds_f64x2(sm_lowR + (uint32_t)((i * LB + qq) * 8), m[qq], m[qq + 1]);
-          double d;
-          lds_f64(hi_addr + (uint32_t)(i * 8), d);
-          double v = fma(sg, d, xh[i]);
-          const bool first = (i % S) == 0;       // first slot of its level initialises the products
-          PL[off] = first ? v : PL[off] * v;
+          for (int t0 = 0; t0 < S; t0 += CH) {
+            double v[CH], m[CH][LB];
 #pragma unroll
-          for (int w = 1; w < cnt; ++w) {
-            const int u = w << L;
-            const int K = ctz_c(u);
-            if (K == B - 1) v = fma(sg_top, m[K], v);
-            else if (((u >> (K + 1)) & 1) == 0) v += m[K];
-            else v -= m[K];
-            PL[off + w] = first ? v : PL[off + w] * v;
+            for (int t = 0; t < CH; ++t) {
+              const int i = L * S + t0 + t;
+#pragma unroll
+              for (int qq = (L & ~1); qq < LB; qq += 2)       // only columns >= L flip inside this level
+                lds_f64x2(sm_lowR + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
+              double d;
+              lds_f64(hi_addr + (uint32_t)(i * 8), d);
+              v[t] = fma(sg, d, xh[i]);
+            }
+            {
+              double pr = v[0];
+#pragma unroll
+              for (int t = 1; t < CH; ++t) pr *= v[t];
+              PL[off] = (t0 == 0) ? pr : PL[off] * pr;
+            }
+#pragma unroll
+            for (int w = 1; w < cnt; ++w) {
+              const int u = w << L;
+              const int K = ctz_c(u);
+#pragma unroll
+              for (int t = 0; t < CH; ++t) {
+                if (K == B - 1) v[t] = fma(sg_top, m[t][K], v[t]);
+                else if (((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
+                else v[t] -= m[t][K];
+              }
+              double pr = v[0];
+#pragma unroll
+              for (int t = 1; t < CH; ++t) pr *= v[t];
+              PL[off + w] = (t0 == 0) ? pr : PL[off + w] * pr;
+            }
+#pragma unroll
+            for (int t = 0; t < CH; ++t) xh[L * S + t0 + t] = v[t];
           }
-          xh[i] = v;
         }
-        // ---- recombine: T_L[w] = PL[L][w] * T_{L+1}[w >> 1], T_B = Q ----
+        // signed pair sums bottom-up: E_0[w] = PL0[2w] - PL0[2w+1],
+        // E_L[w] = PL_L[2w] E_{L-1}[2w] + PL_L[2w+1] E_{L-1}[2w+1]
+        double E[NB / 2];
 #pragma unroll
-        for (int L = B - 1; L >= 0; --L) {
+        for (int w = 0; w < NB / 2; ++w) E[w] = PL[2 * w] - PL[2 * w + 1];          // off(0) = 0
+#pragma unroll
+        for (int L = 1; L < B; ++L) {
           const int off = 2 * NB - 2 * (NB >> L);
-          const int offu = 2 * NB - 2 * (NB >> (L + 1));
-          const int cnt = NB >> L;
 #pragma unroll
-          for (int w = 0; w < cnt; ++w) PL[off + w] *= (L == B - 1) ? Q : PL[offu + (w >> 1)];
+          for (int w = 0; w < (NB >> (L + 1)); ++w)
+            E[w] = fma(PL[off + 2 * w], E[2 * w], PL[off + 2 * w + 1] * E[2 * w + 1]);
         }
-        double blk_sum = 0.0;
-#pragma unroll
-        for (int u = 0; u < NB; u += 2) blk_sum += (PL[u] - PL[u + 1]);    // off(0) = 0
-        tile_acc += blk_sum;
+        tile_acc = fma(Q, E[0], tile_acc);
         tile_vis += 1;
       }
     }

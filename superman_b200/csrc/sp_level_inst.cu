@@ -13,7 +13,7 @@ namespace spb {
 template <int B, int S, int R, bool SKIP>
 static int launch_level(cudaStream_t st, const LevelArgs& a, unsigned blocks, size_t smem) {
   // registers: X of the slots 2*(B*S + R), level products 2*(2^(B+1)-2): 128 registers up to 16 slots
-  constexpr int MB = (B * S + R <= 16) ? 4 : 3;
+  constexpr int MB = (B * S + R <= 16 && !(B == 4 && S == 4)) ? 4 : 3;
   auto kern = level_reg_kernel<B, S, R, SPB_REG_THREADS, MB, SKIP>;
   if (smem > 40 * 1024) {   // static shared memory (queue, partials) counts against the 48 KiB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

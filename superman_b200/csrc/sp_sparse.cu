@@ -227,8 +227,8 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
         la.n = n; la.NC = p->NC; la.NCP = p->NCP; la.HSP = p->HSP; la.c = c; la.tiles_per_warp = tiles_per_warp;
         const int HS = p->lvB * p->lvS, LBv = p->lvB + (p->lvB & 1);
         const size_t dbl = (size_t)(n - 1) * p->HSP + (size_t)HS * LBv + (size_t)(n - 1) * p->NCP + p->HSP + p->NCP +
-                           (size_t)p->NC * SPB_REG_THREADS + (size_t)(c - B + 1) * SPB_REG_THREADS;
-        const size_t smem = dbl * sizeof(double) + (size_t)(n - B + 2) * sizeof(int);
+                           (size_t)p->NC * SPB_REG_THREADS + (size_t)(c - B + 2) * SPB_REG_THREADS;
+        const size_t smem = dbl * sizeof(double) + (size_t)((n - B + 2) + (c - B + 1) + p->NC) * sizeof(int);
         if (smem > 220 * 1024) { set_error("level engine needs %zu B of shared memory", smem); return SPD_ELIMIT; }
         rc = level_launch(p->lvB, p->lvS, p->lvR, p->skip, L.stream, &la, (unsigned)blocks, smem);
         if (rc != SPD_OK) { if (rc == SPD_ELIMIT) set_error("no level kernel for B=%d S=%d R=%d", p->lvB, p->lvS, p->lvR); return rc; }
@@ -345,7 +345,7 @@ int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase
           if (!level_pack(n, B, s_opts[si], R, lvl, dmat_t, xbase, h, l, d, xh, xc, cs, &NC, &cost)) break;
           fits = true;
           cost *= 1.15;
-          if (B * s_opts[si] + R > 16) cost *= 1.1;      // 3 instead of 4 blocks per SM
+          if (B * s_opts[si] + R > 16 || (B == 4 && s_opts[si] == 4)) cost *= 1.1;      // 3 instead of 4 blocks per SM
           if (cost < p->lv_cost) {
             p->lv_cost = cost; p->lvB = B; p->lvS = s_opts[si]; p->lvR = R; p->NC = NC;
             bh.swap(h); bl.swap(l); bd.swap(d); bxh.swap(xh); bxc.swap(xc); bcs.swap(cs);

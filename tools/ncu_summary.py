@@ -22,3 +22,19 @@ for r in rows[2:]:
     for k in keys:
         if k in idx:
             print("%-70s %-12s %s" % (k, units[idx[k]], r[idx[k]]))
+    # top warp-stall reasons (warps stalled per issue-active cycle)
+    stalls = []
+    for h, i in idx.items():
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+            try:
+                stalls.append((float(r[i]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+            except ValueError:
+                pass
+    stalls.sort(reverse=True)
+    if stalls:
+        print("%-70s %s" % ("top stalls (warps per issue-active cycle)", ", ".join("%s %.2f" % (n, v) for v, n in stalls[:6])))
+    for k in ("smsp__inst_executed_pipe_alu.sum", "smsp__inst_executed_pipe_fma.sum", "smsp__inst_executed_pipe_lsu.sum",
+              "smsp__inst_executed_pipe_xu.sum", "smsp__inst_executed_pipe_fp64.sum", "smsp__warps_eligible.avg.per_cycle_active",
+              "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"):
+        if k in idx:
+            print("%-70s %-12s %s" % (k, units[idx[k]], r[idx[k]]))
