@@ -102,3 +102,22 @@ def test_cli_compression_scaling_and_dm_flags(sp, oracle, tmp_path):
     got, out = run_cli("-f", pathb, "-p", "4", "-u", "3")
     assert got == pytest.approx(oracle.perm_ld(b), rel=1e-10)
     assert "Compressed: 1 leaf" in out
+
+
+def test_compressed_on_the_reference_corpus(sp):
+    """the reference's own sparse files (tests/golden/corpus*.json: long-double permanents made by
+    tests/golden/make_golden.py): -o shrinks them and lands on the same permanent"""
+    import _golden
+    seen = 0
+    for name, entry in _golden.corpus().items():
+        if "_0.20_" not in name and "_0.30_" not in name:
+            continue
+        a = _golden.dense_from(entry)
+        n = entry["n"]
+        for sparse, algo, pre in ((True, 4, 1), (True, 7, 2), (False, 4, 0)):
+            st = sp.SpStats()
+            got = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, stats=st)
+            assert got == pytest.approx(entry["ld"], rel=1e-9), (name, sparse, algo, got, entry["ld"])
+            assert st.units < (1 << (n - 1)), (name, st.units)        # fewer Gray indices than the direct run
+        seen += 1
+    assert seen >= 3
