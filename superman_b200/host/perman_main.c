@@ -246,9 +246,9 @@ int main(int argc, char **argv) {
   int reduce = 0;                                    /* --reduce: not a reference flag, off by default */
 
   /* the reference's option string (main.cu:347) plus the revised front-end's extra letters
-   * (revised_perman/main.cpp:1298): -k reps, -l device id, -o degree compression, and the
-   * precision / launch-shape flags -h -w -q -v -e -u, which are accepted and ignored (this engine
-   * always computes in FP64 and sizes its own launches) */
+   * (revised_perman/main.cpp:1298): -k reps, -l device id, -o degree compression, -u <threshold>
+   * Sinkhorn scaling, and the precision / launch-shape flags -h -w -q -v -e, which are accepted and
+   * ignored (this engine always computes in FP64 and sizes its own launches) */
   static const char *short_options = "bsr:t:f:gd:cap:x:y:z:im:n:hwqk:e:ol:vu:";
   int reps = 1, first_device = 0, dm = 0;
   static const struct option long_options[] = {
