@@ -53,6 +53,8 @@ struct ApproxArgs {
   const int* rptrs; const int* cols;   // CRS pattern
   const int* cptrs; const int* rows;   // CCS pattern
   const double* rvals; const double* cvals;  // entry weights (dense twins) or nullptr
+  const unsigned short* ell_rows;      // [nov * W] rows of column j, CCS order, padded with nov (W > 0 only)
+  const unsigned short* ell_cols;      // [nov * W] columns of row i, CRS order, padded with nov
   double* partial_sum;                 // per block: sum of estimates
   double* partial_sq;                  // per block: sum of (estimate * sq_scale)^2
   unsigned long long trial_lo, trial_hi;
@@ -67,7 +69,11 @@ __device__ __forceinline__ bool bit_test(const unsigned* m, int i) { return (m[i
 
 // WEIGHTED: Sinkhorn sums use the entry values in double (dense twin, gpu_approximation_dense.cu:
 // 286-313); otherwise pattern only with float sums (gpu_approximation_sparse.cu:361-396).
-template <bool WEIGHTED>
+// W > 0 (pattern only, every row and column has at most W entries): the Sinkhorn sweeps read the
+// pattern in ELL form, W 16-bit indices per row / column padded with the index nov, whose scaling
+// factor is a constant 0 -- fixed trip count, no pointer loads, and adding the padding's exact
+// zeros after the real entries leaves every float sum bit-identical.
+template <bool WEIGHTED, int W>
 __global__ void __launch_bounds__(APX_THREADS)
 approx_kernel(const ApproxArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -80,9 +86,13 @@ approx_kernel(const ApproxArgs a) {
   int* s_rows = s_cols + nnz;
   size_t off = (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
   off = (off + 15) & ~(size_t)15;
+  unsigned short* s_ell_rows = reinterpret_cast<unsigned short*>(smraw + off);
+  unsigned short* s_ell_cols = s_ell_rows + (size_t)nov * W;
+  off += 2 * (size_t)nov * W * sizeof(unsigned short);
+  off = (off + 15) & ~(size_t)15;
   // per-warp state
   const int deg_bytes = (nov + 15) & ~15;
-  const size_t warp_bytes = (size_t)deg_bytes + 2 * (size_t)words * 4 + (a.scaling ? 2 * (size_t)nov * 4 : 0);
+  const size_t warp_bytes = (size_t)deg_bytes + 2 * (size_t)words * 4 + (a.scaling ? 2 * (size_t)(nov + 1) * 4 : 0);
   const size_t warp_stride = (warp_bytes + 15) & ~(size_t)15;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smraw + off + wib * warp_stride;
@@ -90,11 +100,13 @@ approx_kernel(const ApproxArgs a) {
   unsigned* rowx = reinterpret_cast<unsigned*>(wbase + deg_bytes);
   unsigned* colx = rowx + words;
   float* d_r = reinterpret_cast<float*>(colx + words);
-  float* d_c = d_r + nov;
+  float* d_c = d_r + (nov + 1);                 // d_r[nov] = d_c[nov] = 0: the ELL padding
   __shared__ double blk_sum[APX_WARPS], blk_sq[APX_WARPS];
 
   for (int e = threadIdx.x; e <= nov; e += APX_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
   for (int e = threadIdx.x; e < nnz; e += APX_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
+  if (W > 0)
+    for (int e = threadIdx.x; e < nov * W; e += APX_THREADS) { s_ell_rows[e] = a.ell_rows[e]; s_ell_cols[e] = a.ell_cols[e]; }
   __syncthreads();
 
   const unsigned long long total_warps = (unsigned long long)gridDim.x * APX_WARPS;
@@ -106,7 +118,10 @@ approx_kernel(const ApproxArgs a) {
     // ---- reset state ----
     for (int r = lane; r < nov; r += 32) deg[r] = (unsigned char)min(255, s_rptrs[r + 1] - s_rptrs[r]);
     for (int w = lane; w < words; w += 32) { rowx[w] = 0u; colx[w] = 0u; }
-    if (a.scaling) for (int i = lane; i < nov; i += 32) { d_r[i] = 1.0f; d_c[i] = 1.0f; }
+    if (a.scaling) {
+      for (int i = lane; i < nov; i += 32) { d_r[i] = 1.0f; d_c[i] = 1.0f; }
+      if (lane == 0) { d_r[nov] = 0.0f; d_c[nov] = 0.0f; }
+    }
     __syncwarp();
     double perm = 1.0;
     uint32_t rnd[4];
@@ -153,15 +168,22 @@ approx_kernel(const ApproxArgs a) {
               if (WEIGHTED) {
                 double cs = 0.0;
                 for (int t = s_cptrs[j]; t < s_cptrs[j + 1]; ++t) {
-                  const int r = s_rows[t];
-                  if (!bit_test(rowx, r)) cs += (double)d_r[r] * a.cvals[t];
+                  cs += (double)d_r[s_rows[t]] * a.cvals[t];          // extracted rows hold d_r = 0
                 }
                 if (cs == 0.0) zero = true; else d_c[j] = (float)(1.0 / cs);
+              } else if (W > 0) {
+                const ushort4* er = reinterpret_cast<const ushort4*>(s_ell_rows + j * W);
+                float cs = 0.0f;
+#pragma unroll
+                for (int q = 0; q < W / 4; ++q) {
+                  const ushort4 e4 = er[q];
+                  cs += d_r[e4.x]; cs += d_r[e4.y]; cs += d_r[e4.z]; cs += d_r[e4.w];
+                }
+                if (cs == 0.0f) zero = true; else d_c[j] = 1.0f / cs;
               } else {
                 float cs = 0.0f;
                 for (int t = s_cptrs[j]; t < s_cptrs[j + 1]; ++t) {
-                  const int r = s_rows[t];
-                  if (!bit_test(rowx, r)) cs += d_r[r];
+                  cs += d_r[s_rows[t]];                               // extracted rows hold d_r = 0
                 }
                 if (cs == 0.0f) zero = true; else d_c[j] = 1.0f / cs;
               }
@@ -173,15 +195,22 @@ approx_kernel(const ApproxArgs a) {
               if (WEIGHTED) {
                 double rs = 0.0;
                 for (int t = s_rptrs[i]; t < s_rptrs[i + 1]; ++t) {
-                  const int cc = s_cols[t];
-                  if (!bit_test(colx, cc)) rs += a.rvals[t] * (double)d_c[cc];
+                  rs += a.rvals[t] * (double)d_c[s_cols[t]];          // extracted columns hold d_c = 0
                 }
                 if (rs == 0.0) zero = true; else d_r[i] = (float)(1.0 / rs);
+              } else if (W > 0) {
+                const ushort4* ec = reinterpret_cast<const ushort4*>(s_ell_cols + i * W);
+                float rs = 0.0f;
+#pragma unroll
+                for (int q = 0; q < W / 4; ++q) {
+                  const ushort4 e4 = ec[q];
+                  rs += d_c[e4.x]; rs += d_c[e4.y]; rs += d_c[e4.z]; rs += d_c[e4.w];
+                }
+                if (rs == 0.0f) zero = true; else d_r[i] = 1.0f / rs;
               } else {
                 float rs = 0.0f;
                 for (int t = s_rptrs[i]; t < s_rptrs[i + 1]; ++t) {
-                  const int cc = s_cols[t];
-                  if (!bit_test(colx, cc)) rs += d_c[cc];
+                  rs += d_c[s_cols[t]];                               // extracted columns hold d_c = 0
                 }
                 if (rs == 0.0f) zero = true; else d_r[i] = 1.0f / rs;
               }
@@ -194,17 +223,13 @@ approx_kernel(const ApproxArgs a) {
         // ---- column with probability d_r[row]*d_c[c] / sum (all lanes compute the same) ----
         const float dr = d_r[row];
         double tot = 0.0;
-        for (int t = rb; t < re; ++t) {
-          const int cc = s_cols[t];
-          if (!bit_test(colx, cc)) tot += (double)(dr * d_c[cc]);
-        }
+        for (int t = rb; t < re; ++t) tot += (double)(dr * d_c[s_cols[t]]);   // + 0 for extracted columns
         if (tot == 0.0) { perm = 0.0; dead = true; break; }
         const double target = ((double)draw + 1.0) * (1.0 / 4294967296.0) * tot;
         double run = 0.0;
         for (int t = rb; t < re; ++t) {
           const int cc = s_cols[t];
-          if (bit_test(colx, cc)) continue;
-          const double s = (double)(dr * d_c[cc]);
+          const double s = (double)(dr * d_c[cc]);     // 0 for an extracted column: run does not move
           run += s;
           if (target <= run) { col = cc; perm /= (s / tot); break; }
         }
@@ -215,6 +240,9 @@ approx_kernel(const ApproxArgs a) {
       if (lane == 0) {
         rowx[row >> 5] |= 1u << (row & 31);
         colx[col >> 5] |= 1u << (col & 31);
+        // an extracted row / column keeps scaling factor 0: the Sinkhorn sums and the column pick
+        // add exact zeros for it instead of testing the bit sets per entry
+        if (a.scaling) { d_r[row] = 0.0f; d_c[col] = 0.0f; }
       }
       __syncwarp();
       for (int t = s_cptrs[col] + lane; t < s_cptrs[col + 1]; t += 32) {
@@ -595,6 +623,8 @@ struct spd_approx_plan {
   double *d_rvals = nullptr, *d_cvals = nullptr;
   size_t smem_bytes = 0;
   int blocks = 0;
+  int ellW = 0;                                  // 0: CSR sweeps; 4 or 8: ELL width (pattern-only scaling)
+  unsigned short *d_ell_rows = nullptr, *d_ell_cols = nullptr;
   // thread-per-trial engine (nov <= 64)
   bool small = false;
   unsigned long long *d_rowmask = nullptr, *d_colmask = nullptr;
@@ -608,6 +638,14 @@ struct spd_approx_plan {
   bool pending = false;
   spd_run_info info;
 };
+
+typedef void (*warp_kernel_t)(const ApproxArgs);
+static warp_kernel_t warp_kernel_of(const spd_approx_plan* p) {
+  if (p->weighted) return approx_kernel<true, 0>;
+  if (p->ellW == 4) return approx_kernel<false, 4>;
+  if (p->ellW == 8) return approx_kernel<false, 8>;
+  return approx_kernel<false, 0>;
+}
 
 template <typename K>
 static int small_prepare(spd_approx_plan* p, K kern) {
@@ -653,8 +691,19 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
   const int words = (nov + 31) / 32;
   size_t off = (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
   off = (off + 15) & ~(size_t)15;
+  // ELL form of the pattern for the Sinkhorn sweeps when every row and column has <= 8 entries
+  if (p->scaling && !p->weighted && env_int("SP_APPROX_ELL", 1) != 0) {
+    int maxdeg = 0;
+    for (int i = 0; i < nov; ++i) {
+      maxdeg = std::max(maxdeg, rptrs[i + 1] - rptrs[i]);
+      maxdeg = std::max(maxdeg, cptrs[i + 1] - cptrs[i]);
+    }
+    if (maxdeg <= 8) p->ellW = maxdeg <= 4 ? 4 : 8;
+  }
+  off += 2 * (size_t)nov * p->ellW * sizeof(unsigned short);
+  off = (off + 15) & ~(size_t)15;
   const size_t deg_bytes = ((size_t)nov + 15) & ~(size_t)15;
-  size_t warp_bytes = deg_bytes + 2 * (size_t)words * 4 + (scaling ? 2 * (size_t)nov * 4 : 0);
+  size_t warp_bytes = deg_bytes + 2 * (size_t)words * 4 + (scaling ? 2 * (size_t)(nov + 1) * 4 : 0);
   warp_bytes = (warp_bytes + 15) & ~(size_t)15;
   p->smem_bytes = off + APX_WARPS * warp_bytes;
   if (p->smem_bytes > 227 * 1024) {
@@ -682,9 +731,25 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     set_error("approx plan upload: %s", cudaGetErrorString(e));
     return fail(SPD_ECUDA);
   }
+  if (p->ellW) {
+    const int W = p->ellW;
+    std::vector<unsigned short> er((size_t)nov * W, (unsigned short)nov), ec((size_t)nov * W, (unsigned short)nov);
+    for (int i = 0; i < nov; ++i) {
+      for (int t = cptrs[i]; t < cptrs[i + 1]; ++t) er[(size_t)i * W + (t - cptrs[i])] = (unsigned short)rows[t];
+      for (int t = rptrs[i]; t < rptrs[i + 1]; ++t) ec[(size_t)i * W + (t - rptrs[i])] = (unsigned short)cols[t];
+    }
+    const size_t eb = er.size() * sizeof(unsigned short);
+    if ((rc = lane_arena_alloc(&L, eb, (void**)&p->d_ell_rows)) != SPD_OK) return fail(rc);
+    if ((rc = lane_arena_alloc(&L, eb, (void**)&p->d_ell_cols)) != SPD_OK) return fail(rc);
+    if ((e = cudaMemcpyAsync(p->d_ell_rows, er.data(), eb, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(p->d_ell_cols, ec.data(), eb, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(L.stream)) != cudaSuccess) {
+      set_error("approx plan upload: %s", cudaGetErrorString(e));
+      return fail(SPD_ECUDA);
+    }
+  }
   if (p->smem_bytes > 40 * 1024) {
-    e = p->weighted ? cudaFuncSetAttribute(approx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes)
-                    : cudaFuncSetAttribute(approx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    e = cudaFuncSetAttribute(warp_kernel_of(p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->smem_bytes, cudaGetErrorString(e)); return fail(SPD_ECUDA); }
   }
   // ---- thread-per-trial engine for nov <= 64: 64-bit pattern words ----
@@ -742,8 +807,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     }
   }
   int per_sm = 0;
-  e = p->weighted ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<true>, APX_THREADS, p->smem_bytes)
-                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approx_kernel<false>, APX_THREADS, p->smem_bytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel_of(p), APX_THREADS, p->smem_bytes);
   if (e != cudaSuccess || per_sm < 1) { set_error("approx kernel does not fit on an SM: %s", cudaGetErrorString(e)); return fail(SPD_ECUDA); }
   p->blocks = per_sm * L.sm_count;     // persistent grid: resident blocks x SM count
   if ((rc = lane_reserve_partials(&L, (size_t)2 * p->blocks + 16)) != SPD_OK) return fail(rc);
@@ -818,13 +882,13 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
   ApproxArgs a;
   a.rptrs = p->d_rptrs; a.cols = p->d_cols; a.cptrs = p->d_cptrs; a.rows = p->d_rows;
   a.rvals = p->d_rvals; a.cvals = p->d_cvals;
+  a.ell_rows = p->d_ell_rows; a.ell_cols = p->d_ell_cols;
   a.partial_sum = L.d_partials; a.partial_sq = L.d_partials + blocks;
   a.trial_lo = lo; a.trial_hi = hi; a.seed = p->seed; a.sq_scale = p->sq_scale;
   a.nov = p->nov; a.nnz = p->nnz; a.scaling = p->scaling;
   a.scale_intervals = p->y; a.scale_times = p->z;
   SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
-  if (p->weighted) approx_kernel<true><<<blocks, APX_THREADS, p->smem_bytes, L.stream>>>(a);
-  else approx_kernel<false><<<blocks, APX_THREADS, p->smem_bytes, L.stream>>>(a);
+  warp_kernel_of(p)<<<blocks, APX_THREADS, p->smem_bytes, L.stream>>>(a);
   SPB_CUDA(cudaGetLastError());
   int rc;
   if ((rc = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc;

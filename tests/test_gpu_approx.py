@@ -44,6 +44,28 @@ def test_random_sparse_patterns_bitwise(sp, oracle):
             assert s[t] == oracle.scaling_trial(m.rptrs, m.cols, m.cptrs, m.rows, n, 4, 5, 5, t)
 
 
+def test_banded_patterns_bitwise(sp, oracle):
+    """every row and column holds exactly `width` entries: the scaled estimator's sweeps read the
+    pattern in ELL form (width 4 or 8), wider patterns in CRS / CCS form -- same bits either way"""
+    for n, width in ((72, 3), (72, 6), (90, 8), (80, 11)):
+        pat = np.zeros((n, n))
+        for i in range(n):
+            for d in range(width):
+                pat[i, (i + d * d) % n] = 1.0           # distinct offsets 0, 1, 4, 9, ... (< n)
+        assert (pat.sum(axis=0) <= width).all() and (pat.sum(axis=1) >= width - 1).all()
+        m = sp.Matrix.from_dense(pat).compress(0)
+        s = sp.approx_trials_sparse(m.rptrs, m.cols, m.cptrs, m.rows, n, m.nnz, scaling=True, scale_intervals=3,
+                                    scale_times=4, seed=11, first=5, count=16)
+        r = sp.approx_trials_sparse(m.rptrs, m.cols, m.cptrs, m.rows, n, m.nnz, scaling=False, seed=11, first=5, count=16)
+        alive = 0
+        for t in range(16):
+            assert s[t] == oracle.scaling_trial(m.rptrs, m.cols, m.cptrs, m.rows, n, 3, 4, 11, 5 + t), (n, width, t)
+            assert r[t] == oracle.rasmussen_trial(m.rptrs, m.cols, n, 11, 5 + t), (n, width, t)
+            alive += s[t] != 0.0
+        if width >= 6:
+            assert alive > 0            # long trials: extracted rows / columns really take part in the sweeps
+
+
 def test_mean_is_sum_of_trials_and_split_invariant(sp, oracle):
     g = _grid(sp, 6, 6)
     N = 3000
