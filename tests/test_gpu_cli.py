@@ -115,12 +115,12 @@ def test_reduce_flag(files):
         for extra in ((), ("-s", "-r", "1", "-p", "4"), ("-s", "-r", "2", "-p", "7")):
             r = run("-f", path, "--reduce", *(extra or ("-p", "4")), env={"PERMAN_PRECISION": "17"})
             assert r.returncode == 0, r.stderr
-            assert re.search(r"^Reduced: nov %d -> \d+$" % e["n"], r.stdout, flags=re.M)
+            assert re.search(r"^Compressed: \d+ leaf matrix\(es\), \d+ Gray indices$", r.stdout, flags=re.M)
             assert result_of(r.stdout)[1] == pytest.approx(e["ld"], rel=1e-9)
 
 
 def test_revised_front_end_flags(files):
-    """-k reps / -l device / -o compression / ignored precision flags (revised_perman/main.cpp:1298-1325)"""
+    """-k reps / -l device / -o compression / -u scaling / ignored precision flags (revised_perman/main.cpp:1298-1325)"""
     path, e = files[6]
     r = run("-f", path, "-p", "4", "-k", "3", "-l", "0", "-h", "-w", "-q", "-v", "-e", "4", "-u", "2",
             env={"PERMAN_PRECISION": "17"})
@@ -129,6 +129,6 @@ def test_revised_front_end_flags(files):
     assert len(vals) == 3 and all(v == pytest.approx(e["ld"], rel=1e-9) for v in vals)
     assert vals[0] == vals[1] == vals[2]                  # bit-reproducible
     r = run("-f", path, "-s", "-p", "4", "-o", env={"PERMAN_PRECISION": "17"})
-    assert "Reduced: nov" in r.stdout and result_of(r.stdout)[1] == pytest.approx(e["ld"], rel=1e-9)
+    assert "Compressed: " in r.stdout and result_of(r.stdout)[1] == pytest.approx(e["ld"], rel=1e-9)
     r = run("-f", path, "-p", "4", "-l", "99")
     assert r.returncode == 1 and "device" in r.stderr
