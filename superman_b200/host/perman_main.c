@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "superman_b200.h"
 
@@ -61,6 +62,17 @@ static void result_both(const char *name, const char *try_prefix, double v, doub
   printf("Result: %s %2lf in %lf\n", name, v, secs);
   printf("%s: %s %g in %g\n", try_prefix, name, v, secs);
   extra_precision(name, v);
+}
+
+/* Everything is printed and the process owns nothing else: leave without the CUDA runtime's atexit
+ * teardown.  Destroying the contexts costs ~0.15 s per device (1.3 s of a 3.0 s `-p5 -d 8` process on
+ * an 8 x B200 box, profiles/r01_cli_configs_8xB200.log) and is not part of any algorithm.
+ * PERMAN_SLOW_EXIT=1 keeps the ordinary return path. */
+static int finish(int rc) {
+  fflush(stdout);
+  fflush(stderr);
+  if (!getenv("PERMAN_SLOW_EXIT")) _exit(rc);
+  return rc;
 }
 
 static int report_failure(void) {
@@ -344,7 +356,7 @@ int main(int argc, char **argv) {
     int rcg = 0;
     for (int r = 0; r < reps && rcg == 0; ++r)
       rcg = run_grid(gridm, gridn, perman_algo, gpu_num, number_of_times, scale_intervals, scale_times);
-    return rcg;
+    return finish(rcg);
   }
 
   sp_matrix m;
@@ -368,5 +380,5 @@ int main(int argc, char **argv) {
     rc = run_matrix(&m, perman_algo, gpu_num, threads, cpu, dense, approximation, number_of_times,
                     scale_intervals, scale_times);
   sp_matrix_free(&m);
-  return rc;
+  return finish(rc);
 }
