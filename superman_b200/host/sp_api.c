@@ -22,6 +22,8 @@ int sp_set_first_device(int device) {
   return SP_OK;
 }
 
+int sp_first_device(void) { return g_first_device; }
+
 int sp_device_count(void) {
   int n = spd_device_count();
   if (n < 0) sp_set_error("%s", spd_last_error());

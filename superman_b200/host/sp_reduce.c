@@ -24,6 +24,8 @@
 #include "sp_sched.h"
 
 #include <math.h>
+#include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -403,120 +405,266 @@ int sp_matrix_dm(sp_matrix *m, int *matching) {
 }
 
 /* ---- compress_singleton_and_then_recurse / compress_and_calculate_recursive / scale_and_calculate
- * (main.cpp:993-1260) on the GPU engine ---------------------------------------------------------- */
+ * (main.cpp:993-1260) on the GPU engine ----------------------------------------------------------
+ * The recursion only PREPARES leaves (reduce, split, total support, balance, -r ordering) and
+ * queues them with the product of the degree-1 factors along their path; the permanent is
+ *   sum over leaves, in the order the recursion meets them, of  coeff * perm(leaf) / prod(rv cv).
+ * Queued leaves are independent, so with a multi-device id (-p5 / -p6 / -p8) and at least as many
+ * pending leaves as devices each device takes whole leaves from a shared counter (no exchange, one
+ * double back per leaf); otherwise every leaf goes through the id's own entry point, which splits
+ * its Gray range over the devices.  The sum order is fixed, so the result does not depend on which
+ * device computed which leaf. */
+#define SP_LEAF_BATCH 1024
+
+typedef struct leaf {
+  sp_matrix m;                 /* owned; carries CRS / CCS for the sparse ids */
+  double coeff;                /* product of the degree-1 factors on the path to this leaf */
+  double rv[64], cv[64];       /* Sinkhorn factors when scaled */
+  int scaled;
+  int slot;                    /* device slot that computed it in a parallel flush, else -1 */
+  double value;                /* coeff * perm(leaf before scaling) */
+  sp_stats st;
+  int rc;
+  char err[200];
+} leaf;
+
 typedef struct reduce_ctx {
   int sparse, preprocessing, algo_id, gpu_num, threads, leaf_nov;
+  int multi;                   /* the id partitions over several devices */
+  int first_device;
   double threshold;
   sp_stats total;
+  double seq_ms, dev_ms[SP_MAX_DEVICES];
+  unsigned long long dev_units[SP_MAX_DEVICES];
   int leaves, failed, altered;
+  char err[200];
+  leaf *pend[SP_LEAF_BATCH];
+  int npend;
+  int next;                    /* shared leaf counter of a parallel flush */
+  double sum;
 } reduce_ctx;
 
-static void stats_add(sp_stats *t, const sp_stats *s) {
-  t->kernel_ms += s->kernel_ms;
-  for (int d = 0; d < SP_MAX_DEVICES; ++d) {
-    t->device_ms[d] += s->device_ms[d];
-    t->device_units[d] += s->device_units[d];
-  }
-  t->units += s->units;
-  t->visited += s->visited;
-  t->launches += s->launches;
-  if (s->devices > t->devices) t->devices = s->devices;
-  t->path = s->path;
-  t->tile_log2 = s->tile_log2;
+static void fail_ctx(reduce_ctx *cx, int code, const char *msg) {
+  if (cx->failed) return;
+  cx->failed = code;
+  snprintf(cx->err, sizeof(cx->err), "%s", msg);
 }
 
-static double run_leaf(reduce_ctx *cx, sp_matrix *m) {
-  double rv[64], cv[64];
+/* slot < 0: through the id's own entry point (which may split the leaf over the devices);
+ * slot >= 0: the whole leaf on device first_device + slot */
+static void run_leaf(const reduce_ctx *cx, leaf *lf, int slot) {
+  const int n = lf->m.nov;
+  double v;
+  memset(&lf->st, 0, sizeof(lf->st));
+  lf->rc = SP_OK;
+  lf->slot = slot;
+  if (n == 1) {
+    v = lf->m.mat[0];
+  } else if (slot < 0) {
+    if (!cx->sparse)
+      v = sp_dense_ryser(lf->m.mat, n, cx->algo_id, cx->gpu_num, 0, cx->threads, &lf->st);
+    else if (cx->algo_id == 7 || cx->algo_id == 8)
+      v = sp_skipper(lf->m.mat, lf->m.rptrs, lf->m.cols, lf->m.cptrs, lf->m.rows, lf->m.cvals, n, cx->algo_id,
+                     cx->gpu_num, 0, cx->threads, &lf->st);
+    else
+      v = sp_sparse_ryser(lf->m.mat, lf->m.cptrs, lf->m.rows, lf->m.cvals, n, cx->algo_id, cx->gpu_num, 0,
+                          cx->threads, &lf->st);
+  } else {
+    const long long end = 1ll << (n - 1);
+    const int device = cx->first_device + slot;
+    if (!cx->sparse)
+      v = sp_dense_ryser_range(lf->m.mat, n, device, 0, end, &lf->st);
+    else
+      v = sp_sparse_ryser_range(lf->m.mat, lf->m.cptrs, lf->m.rows, lf->m.cvals, n, cx->algo_id == 8, device, 0, end,
+                                &lf->st);
+    v *= sp_nw_factor(n);
+  }
+  if (isnan(v) && lf->st.error) {
+    lf->rc = lf->st.error;
+    snprintf(lf->err, sizeof(lf->err), "%s", sp_last_error());
+    return;
+  }
+  if (lf->scaled)                               /* main.cpp:1143-1149 */
+    for (int i = 0; i < n; ++i) { v /= lf->cv[i]; v /= lf->rv[i]; }
+  lf->value = lf->coeff * v;
+}
+
+typedef struct flush_arg { reduce_ctx *cx; int slot; } flush_arg;
+
+static void *flush_worker(void *p) {
+  flush_arg *fa = (flush_arg *)p;
+  reduce_ctx *cx = fa->cx;
+  for (;;) {
+    const int i = __atomic_fetch_add(&cx->next, 1, __ATOMIC_RELAXED);
+    if (i >= cx->npend) break;
+    run_leaf(cx, cx->pend[i], fa->slot);
+  }
+  return NULL;
+}
+
+static void flush_leaves(reduce_ctx *cx) {
+  if (cx->npend == 0) return;
+  int devices = 1;
+  if (cx->multi && !cx->failed) {
+    const int visible = sp_device_count() - cx->first_device;
+    devices = cx->gpu_num < visible ? cx->gpu_num : visible;
+    if (devices > SP_MAX_DEVICES) devices = SP_MAX_DEVICES;
+    if (devices < 1) devices = 1;
+  }
+  if (cx->failed) {
+    /* an earlier leaf failed: nothing more is computed */
+  } else if (devices > 1 && cx->npend >= devices) {
+    pthread_t th[SP_MAX_DEVICES];
+    flush_arg fa[SP_MAX_DEVICES];
+    int started[SP_MAX_DEVICES] = {0};
+    cx->next = 0;
+    for (int d = 1; d < devices; ++d) {
+      fa[d].cx = cx; fa[d].slot = d;
+      started[d] = pthread_create(&th[d], NULL, flush_worker, &fa[d]) == 0;
+    }
+    fa[0].cx = cx; fa[0].slot = 0;
+    flush_worker(&fa[0]);                        /* the first device on the caller's thread */
+    for (int d = 1; d < devices; ++d)
+      if (started[d]) pthread_join(th[d], NULL);
+    if (devices > cx->total.devices) cx->total.devices = devices;
+  } else {
+    for (int i = 0; i < cx->npend; ++i) {
+      run_leaf(cx, cx->pend[i], -1);
+      if (cx->pend[i]->rc != SP_OK) { fail_ctx(cx, cx->pend[i]->rc, cx->pend[i]->err); break; }
+    }
+  }
+  for (int i = 0; i < cx->npend; ++i) {
+    leaf *lf = cx->pend[i];
+    if (lf->rc != SP_OK) fail_ctx(cx, lf->rc, lf->err);
+    if (!cx->failed) {
+      cx->sum += lf->value;
+      cx->total.units += lf->st.units;
+      cx->total.visited += lf->st.visited;
+      cx->total.launches += lf->st.launches;
+      if (lf->st.devices > cx->total.devices) cx->total.devices = lf->st.devices;
+      cx->total.path = lf->st.path;
+      cx->total.tile_log2 = lf->st.tile_log2;
+      if (lf->slot >= 0) {
+        cx->dev_ms[lf->slot] += lf->st.kernel_ms;
+        cx->dev_units[lf->slot] += lf->st.units;
+      } else {
+        cx->seq_ms += lf->st.kernel_ms;
+      }
+      ++cx->leaves;
+    }
+    sp_matrix_free(&lf->m);
+    free(lf);
+  }
+  cx->npend = 0;
+}
+
+/* consumes m: total support, balancing, ordering; queues the leaf */
+static void queue_leaf(reduce_ctx *cx, sp_matrix *m, double coeff) {
   const int n = m->nov;
+  leaf *lf = NULL;
   int rc;
+  if (cx->failed) goto drop;
+  if (n > 64) { sp_set_error("exact paths support n <= 64 (got %d after compression)", n); fail_ctx(cx, SP_ELIMIT, sp_last_error()); goto drop; }
+  lf = (leaf *)calloc(1, sizeof(leaf));
+  if (!lf) { fail_ctx(cx, SP_ENOMEM, "out of memory"); goto drop; }
   /* threshold 0 = automatic: scale when the compression changed the matrix (see sp_matrix_balance for
    * why that is necessary); untouched matrices are not scaled -- SkipPer's exact-zero skipping depends
    * on the values.  Before scaling, entries on no perfect matching are erased (exact), which gives
    * the matrix total support; a leaf without a perfect matching has permanent 0 and needs no kernel. */
   const double threshold = cx->threshold > 0 ? cx->threshold : (cx->threshold == 0 && cx->altered) ? 1.0 : -1.0;
   if (threshold > 0 && n > 1) {
-    if (n > 64) { sp_set_error("exact paths support n <= 64 (got %d)", n); cx->failed = SP_ELIMIT; return NAN; }
     int matching = 0;
     rc = sp_matrix_dm(m, &matching);
-    if (rc < 0) { cx->failed = rc; return NAN; }
-    if (matching < n) { ++cx->leaves; return 0.0; }
-    rc = sp_matrix_balance(m, threshold, rv, cv);
-    if (rc < 0) { cx->failed = rc; return NAN; }
+    if (rc < 0) { fail_ctx(cx, rc, sp_last_error()); goto drop; }
+    if (matching < n) { ++cx->leaves; goto drop; }
+    rc = sp_matrix_balance(m, threshold, lf->rv, lf->cv);
+    if (rc < 0) { fail_ctx(cx, rc, sp_last_error()); goto drop; }
+    lf->scaled = 1;
   }
-  sp_stats st;
-  double perman;
-  if (!cx->sparse) {
-    perman = sp_dense_ryser(m->mat, n, cx->algo_id, cx->gpu_num, 0, cx->threads, &st);
-  } else {
+  if (cx->sparse && n > 1) {
     rc = sp_matrix_compress(m, cx->preprocessing);
-    if (rc != SP_OK) { cx->failed = rc; return NAN; }
-    if (cx->algo_id == 7 || cx->algo_id == 8)
-      perman = sp_skipper(m->mat, m->rptrs, m->cols, m->cptrs, m->rows, m->cvals, n, cx->algo_id, cx->gpu_num, 0,
-                          cx->threads, &st);
-    else
-      perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, n, cx->algo_id, cx->gpu_num, 0, cx->threads, &st);
+    if (rc != SP_OK) { fail_ctx(cx, rc, sp_last_error()); goto drop; }
   }
-  if (isnan(perman) && st.error) { cx->failed = st.error; return NAN; }
-  stats_add(&cx->total, &st);
-  ++cx->leaves;
-  if (threshold > 0 && n > 1) {                 /* main.cpp:1143-1149 */
-    for (int i = 0; i < n; ++i) { perman /= cv[i]; perman /= rv[i]; }
-  }
-  return perman;
+  lf->m = *m;                                   /* ownership moves into the leaf */
+  memset(m, 0, sizeof(*m));
+  lf->coeff = coeff;
+  cx->pend[cx->npend++] = lf;
+  if (cx->npend == SP_LEAF_BATCH) flush_leaves(cx);
+  return;
+drop:
+  free(lf);
+  sp_matrix_free(m);
 }
 
 /* consumes m */
-static double recurse(reduce_ctx *cx, sp_matrix *m) {
-  double factor = 1.0, result;
+static void recurse(reduce_ctx *cx, sp_matrix *m, double coeff) {
   for (;;) {
-    if (cx->failed) { result = NAN; break; }
+    if (cx->failed) break;
     const int mind = sp_matrix_min_degree(m);
-    if (mind == 0) { result = 0.0; break; }
-    if (!(mind < 5 && m->nov > cx->leaf_nov)) { result = run_leaf(cx, m); break; }
+    if (mind == 0) break;                       /* an empty row or column: this branch adds 0 */
+    if (!(mind < 5 && m->nov > cx->leaf_nov)) { queue_leaf(cx, m, coeff); return; }
     if (mind <= 2) {
-      /* one d1 / d2 step (main.cpp:1010-1028); the d1 entry goes to `factor`, not into row 0 */
-      int rc = (mind == 1) ? step_d1(m->mat, &m->nov, &factor) : step_d2(m->mat, &m->nov);
-      if (rc <= 0) { sp_set_error("degree compression found no candidate"); cx->failed = SP_EINVAL; result = NAN; break; }
+      /* one d1 / d2 step (main.cpp:1010-1028); the d1 entry goes to the coefficient, not into row 0 */
+      int rc = (mind == 1) ? step_d1(m->mat, &m->nov, &coeff) : step_d2(m->mat, &m->nov);
+      if (rc <= 0) { fail_ctx(cx, SP_EINVAL, "degree compression found no candidate"); break; }
       cx->altered = 1;
       continue;
     }
     sp_matrix second;
     int rc = sp_matrix_split34(m, mind, &second);
-    if (rc <= 0) { cx->failed = rc < 0 ? rc : SP_EINVAL; result = NAN; break; }
+    if (rc <= 0) { fail_ctx(cx, rc < 0 ? rc : SP_EINVAL, rc < 0 ? sp_last_error() : "d34 split found no candidate"); break; }
     cx->altered = 1;
     sp_matrix first = *m;                       /* ownership moves into the two recursive calls */
     memset(m, 0, sizeof(*m));
-    const double p1 = recurse(cx, &first);
-    const double p2 = recurse(cx, &second);
-    return factor * (p1 + p2);
+    recurse(cx, &first, coeff);
+    recurse(cx, &second, coeff);
+    return;
   }
   sp_matrix_free(m);
-  return factor * result;
 }
 
 double sp_permanent_compressed(const double *mat, int nov, int sparse, int preprocessing, int algo_id, int gpu_num,
                                int threads, double scaling_threshold, int leaf_nov, sp_stats *stats) {
   const double t0 = sp_now_ms();
   if (stats) memset(stats, 0, sizeof(*stats));
-  reduce_ctx cx;
-  memset(&cx, 0, sizeof(cx));
-  cx.sparse = sparse; cx.preprocessing = preprocessing; cx.algo_id = algo_id; cx.gpu_num = gpu_num;
-  cx.threads = threads; cx.threshold = scaling_threshold;
+  reduce_ctx *cx = (reduce_ctx *)calloc(1, sizeof(reduce_ctx));
+  if (!cx) { sp_set_error("out of memory"); if (stats) stats->error = SP_ENOMEM; return NAN; }
+  cx->sparse = sparse; cx->preprocessing = preprocessing; cx->algo_id = algo_id;
+  cx->gpu_num = gpu_num < 1 ? 1 : gpu_num;
+  cx->threads = threads; cx->threshold = scaling_threshold;
+  cx->multi = sparse ? (algo_id == 5 || algo_id == 6 || algo_id == 8) : (algo_id == 5 || algo_id == 6);
+  cx->first_device = sp_first_device();
   /* `densemat->nov > 30`, main.cpp:1008; leaf_nov < 0: no compression at all (scaling only) */
-  cx.leaf_nov = leaf_nov > 0 ? leaf_nov : leaf_nov == 0 ? 30 : SP_MAX_NOV;
+  cx->leaf_nov = leaf_nov > 0 ? leaf_nov : leaf_nov == 0 ? 30 : SP_MAX_NOV;
   sp_matrix m;
   int rc = sp_matrix_from_dense(mat, nov, &m);
-  if (rc != SP_OK) { if (stats) stats->error = rc; return NAN; }
+  if (rc != SP_OK) { free(cx); if (stats) stats->error = rc; return NAN; }
   double factor = 1.0;
   rc = leaf_nov < 0 ? 0 : sp_matrix_reduce(&m, &factor);
-  if (rc < 0) { sp_matrix_free(&m); if (stats) stats->error = rc; return NAN; }
-  cx.altered = rc > 0;
-  double perman = (factor == 0.0) ? (sp_matrix_free(&m), 0.0) : factor * recurse(&cx, &m);
-  if (stats) {
-    *stats = cx.total;
-    stats->chunks = cx.leaves;
-    stats->wall_ms = sp_now_ms() - t0;
-    stats->error = cx.failed;
+  if (rc < 0) { sp_matrix_free(&m); free(cx); if (stats) stats->error = rc; return NAN; }
+  cx->altered = rc > 0;
+  if (factor == 0.0) {
+    sp_matrix_free(&m);
+  } else {
+    recurse(cx, &m, factor);
+    flush_leaves(cx);
   }
-  return cx.failed ? NAN : perman;
+  const int failed = cx->failed;
+  const double perman = cx->sum;
+  if (failed) sp_set_error("%s", cx->err);
+  if (stats) {
+    *stats = cx->total;
+    double par = 0.0;
+    for (int d = 0; d < SP_MAX_DEVICES; ++d) {
+      stats->device_ms[d] = cx->dev_ms[d];
+      stats->device_units[d] = cx->dev_units[d];
+      if (cx->dev_ms[d] > par) par = cx->dev_ms[d];
+    }
+    stats->kernel_ms = cx->seq_ms + par;
+    stats->chunks = cx->leaves;
+    stats->wall_ms = sp_now_ms() - t0;
+    stats->error = failed;
+  }
+  free(cx);
+  return failed ? NAN : perman;
 }

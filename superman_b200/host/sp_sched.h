@@ -41,6 +41,7 @@ unsigned long long sp_sched_boundary(unsigned long long lo, unsigned long long h
                                      unsigned long long parts, unsigned long long idx, int align_log2);
 
 void sp_set_error(const char *fmt, ...);
+int sp_first_device(void);            /* what sp_set_first_device stored (sp_api.c) */
 double sp_now_ms(void);
 
 #endif

@@ -121,3 +121,28 @@ def test_compressed_on_the_reference_corpus(sp):
             assert st.units < (1 << (n - 1)), (name, st.units)        # fewer Gray indices than the direct run
         seen += 1
     assert seen >= 3
+
+
+def test_leaves_are_spread_over_the_devices(sp, oracle):
+    """multi-device ids (-p5 / -p6 / -p8): with at least as many pending leaves as devices every device
+    computes whole leaves; the sum runs in leaf order, so the result does not depend on the split"""
+    g = sp.device_count()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    a = banded(np.random.default_rng(140), 40, "real")
+    want = oracle_compressed(sp, oracle, a)
+    one = sp.permanent_compressed(a, sparse=False, algo_id=4, leaf_nov=24)
+    assert one == pytest.approx(want, rel=1e-9)
+    for sparse, algo, pre in ((False, 5, 0), (False, 6, 0), (True, 5, 1), (True, 8, 2)):
+        st = sp.SpStats()
+        got = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, gpu_num=g, leaf_nov=24, stats=st)
+        assert got == pytest.approx(want, rel=1e-9), (sparse, algo)
+        assert st.chunks >= g and st.devices == g
+        used = [d for d in range(g) if st.device_units[d] > 0]
+        assert len(used) == g, (sparse, algo, used)              # every device took leaves
+        again = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, gpu_num=g, leaf_nov=24)
+        assert again == got                                       # whichever device took which leaf
+    # fewer leaves than devices: each leaf is split over the devices by the id's own entry point
+    st = sp.SpStats()
+    few = sp.permanent_compressed(a, sparse=False, algo_id=5, gpu_num=g, leaf_nov=39, stats=st)
+    assert few == pytest.approx(want, rel=1e-9)
