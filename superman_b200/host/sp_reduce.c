@@ -409,11 +409,12 @@ int sp_matrix_dm(sp_matrix *m, int *matching) {
  * The recursion only PREPARES leaves (reduce, split, total support, balance, -r ordering) and
  * queues them with the product of the degree-1 factors along their path; the permanent is
  *   sum over leaves, in the order the recursion meets them, of  coeff * perm(leaf) / prod(rv cv).
- * Queued leaves are independent, so with a multi-device id (-p5 / -p6 / -p8) and at least as many
- * pending leaves as devices each device takes whole leaves from a shared counter (no exchange, one
- * double back per leaf); otherwise every leaf goes through the id's own entry point, which splits
- * its Gray range over the devices.  The sum order is fixed, so the result does not depend on which
- * device computed which leaf. */
+ * Queued leaves are independent: when at least as many leaves are pending as the id has devices
+ * (one device for the single-GPU ids, gpu_num for -p5 / -p6 / -p8), host threads -- two per device,
+ * so one leaf's plan upload and result read-back overlap the other's kernel -- take whole leaves
+ * from a shared counter (no exchange, one double back per leaf); otherwise every leaf goes through
+ * the id's own entry point, which splits its Gray range over the devices.  The sum order is fixed,
+ * so the result does not depend on which device computed which leaf. */
 #define SP_LEAF_BATCH 1024
 
 typedef struct leaf {
@@ -421,7 +422,7 @@ typedef struct leaf {
   double coeff;                /* product of the degree-1 factors on the path to this leaf */
   double rv[64], cv[64];       /* Sinkhorn factors when scaled */
   int scaled;
-  int slot;                    /* device slot that computed it in a parallel flush, else -1 */
+  int slot;                    /* host thread that computed it in a parallel flush (device = slot % devices), else -1 */
   double value;                /* coeff * perm(leaf before scaling) */
   sp_stats st;
   int rc;
@@ -434,8 +435,10 @@ typedef struct reduce_ctx {
   int first_device;
   double threshold;
   sp_stats total;
-  double seq_ms, dev_ms[SP_MAX_DEVICES];
-  unsigned long long dev_units[SP_MAX_DEVICES];
+#define SP_LEAF_THREADS_PER_DEVICE 2
+  double seq_ms, thr_ms[SP_MAX_DEVICES * SP_LEAF_THREADS_PER_DEVICE];   /* sums of CUDA-event times */
+  unsigned long long thr_units[SP_MAX_DEVICES * SP_LEAF_THREADS_PER_DEVICE];
+  int par_devices;             /* devices of the parallel flushes */
   int leaves, failed, altered;
   char err[200];
   leaf *pend[SP_LEAF_BATCH];
@@ -451,8 +454,8 @@ static void fail_ctx(reduce_ctx *cx, int code, const char *msg) {
 }
 
 /* slot < 0: through the id's own entry point (which may split the leaf over the devices);
- * slot >= 0: the whole leaf on device first_device + slot */
-static void run_leaf(const reduce_ctx *cx, leaf *lf, int slot) {
+ * slot >= 0: the whole leaf on device first_device + slot % devices */
+static void run_leaf(const reduce_ctx *cx, leaf *lf, int slot, int devices) {
   const int n = lf->m.nov;
   double v;
   memset(&lf->st, 0, sizeof(lf->st));
@@ -471,7 +474,7 @@ static void run_leaf(const reduce_ctx *cx, leaf *lf, int slot) {
                           cx->threads, &lf->st);
   } else {
     const long long end = 1ll << (n - 1);
-    const int device = cx->first_device + slot;
+    const int device = cx->first_device + slot % devices;
     if (!cx->sparse)
       v = sp_dense_ryser_range(lf->m.mat, n, device, 0, end, &lf->st);
     else
@@ -489,7 +492,7 @@ static void run_leaf(const reduce_ctx *cx, leaf *lf, int slot) {
   lf->value = lf->coeff * v;
 }
 
-typedef struct flush_arg { reduce_ctx *cx; int slot; } flush_arg;
+typedef struct flush_arg { reduce_ctx *cx; int slot; int devices; } flush_arg;
 
 static void *flush_worker(void *p) {
   flush_arg *fa = (flush_arg *)p;
@@ -497,7 +500,7 @@ static void *flush_worker(void *p) {
   for (;;) {
     const int i = __atomic_fetch_add(&cx->next, 1, __ATOMIC_RELAXED);
     if (i >= cx->npend) break;
-    run_leaf(cx, cx->pend[i], fa->slot);
+    run_leaf(cx, cx->pend[i], fa->slot, fa->devices);
   }
   return NULL;
 }
@@ -513,23 +516,26 @@ static void flush_leaves(reduce_ctx *cx) {
   }
   if (cx->failed) {
     /* an earlier leaf failed: nothing more is computed */
-  } else if (devices > 1 && cx->npend >= devices) {
-    pthread_t th[SP_MAX_DEVICES];
-    flush_arg fa[SP_MAX_DEVICES];
-    int started[SP_MAX_DEVICES] = {0};
+  } else if (cx->npend >= 2 && cx->npend >= devices) {
+    pthread_t th[SP_MAX_DEVICES * SP_LEAF_THREADS_PER_DEVICE];
+    flush_arg fa[SP_MAX_DEVICES * SP_LEAF_THREADS_PER_DEVICE];
+    int started[SP_MAX_DEVICES * SP_LEAF_THREADS_PER_DEVICE] = {0};
+    int nthreads = devices * SP_LEAF_THREADS_PER_DEVICE;
+    if (nthreads > cx->npend) nthreads = cx->npend;
     cx->next = 0;
-    for (int d = 1; d < devices; ++d) {
-      fa[d].cx = cx; fa[d].slot = d;
-      started[d] = pthread_create(&th[d], NULL, flush_worker, &fa[d]) == 0;
+    for (int t = 1; t < nthreads; ++t) {
+      fa[t].cx = cx; fa[t].slot = t; fa[t].devices = devices;   /* thread t drives device t % devices */
+      started[t] = pthread_create(&th[t], NULL, flush_worker, &fa[t]) == 0;
     }
-    fa[0].cx = cx; fa[0].slot = 0;
-    flush_worker(&fa[0]);                        /* the first device on the caller's thread */
-    for (int d = 1; d < devices; ++d)
-      if (started[d]) pthread_join(th[d], NULL);
+    fa[0].cx = cx; fa[0].slot = 0; fa[0].devices = devices;
+    flush_worker(&fa[0]);                        /* the caller's thread works too */
+    for (int t = 1; t < nthreads; ++t)
+      if (started[t]) pthread_join(th[t], NULL);
     if (devices > cx->total.devices) cx->total.devices = devices;
+    if (devices > cx->par_devices) cx->par_devices = devices;
   } else {
     for (int i = 0; i < cx->npend; ++i) {
-      run_leaf(cx, cx->pend[i], -1);
+      run_leaf(cx, cx->pend[i], -1, 1);
       if (cx->pend[i]->rc != SP_OK) { fail_ctx(cx, cx->pend[i]->rc, cx->pend[i]->err); break; }
     }
   }
@@ -545,8 +551,8 @@ static void flush_leaves(reduce_ctx *cx) {
       cx->total.path = lf->st.path;
       cx->total.tile_log2 = lf->st.tile_log2;
       if (lf->slot >= 0) {
-        cx->dev_ms[lf->slot] += lf->st.kernel_ms;
-        cx->dev_units[lf->slot] += lf->st.units;
+        cx->thr_ms[lf->slot] += lf->st.kernel_ms;
+        cx->thr_units[lf->slot] += lf->st.units;
       } else {
         cx->seq_ms += lf->st.kernel_ms;
       }
@@ -654,11 +660,13 @@ double sp_permanent_compressed(const double *mat, int nov, int sparse, int prepr
   if (failed) sp_set_error("%s", cx->err);
   if (stats) {
     *stats = cx->total;
+    /* a device's two host threads overlap their kernels: its time is the longer of the two sums */
     double par = 0.0;
-    for (int d = 0; d < SP_MAX_DEVICES; ++d) {
-      stats->device_ms[d] = cx->dev_ms[d];
-      stats->device_units[d] = cx->dev_units[d];
-      if (cx->dev_ms[d] > par) par = cx->dev_ms[d];
+    for (int t = 0; cx->par_devices > 0 && t < cx->par_devices * SP_LEAF_THREADS_PER_DEVICE; ++t) {
+      const int d = t % cx->par_devices;
+      if (cx->thr_ms[t] > stats->device_ms[d]) stats->device_ms[d] = cx->thr_ms[t];
+      stats->device_units[d] += cx->thr_units[t];
+      if (cx->thr_ms[t] > par) par = cx->thr_ms[t];
     }
     stats->kernel_ms = cx->seq_ms + par;
     stats->chunks = cx->leaves;
