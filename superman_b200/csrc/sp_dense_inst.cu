@@ -29,8 +29,11 @@ template <int N, int B>
 static int launch_nb(cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
                      unsigned long long group_first, unsigned long long n_groups, int gpb, int c,
                      unsigned* blocks_out) {
-  // from the ptxas -v survey of every (N, B, MB): the largest occupancy with zero spill bytes
-  constexpr int MB = (N > 54) ? 2 : (B == 4) ? ((N <= 39 && N != 33) ? 4 : 3) : (N <= 43 ? 4 : 3);
+  // blocks per SM from the ptxas -v survey of every (N, B, MB) and a timing of every order
+  // (profiles/r01_ptxas_spill_survey_dense.txt, r01_dense_frac_vs_n.log): the largest occupancy without
+  // spills, except where a spill of <= 60 bytes outside the inner product loop measured faster than the
+  // next lower occupancy (n = 33, 40: 4 blocks; n = 55..59: 3 blocks)
+  constexpr int MB = (B == 4) ? ((N <= 40) ? 4 : (N <= 59) ? 3 : 2) : ((N > 54) ? 2 : (N <= 43 ? 4 : 3));
   return launch_one<N, B, MB>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out);
 }
 

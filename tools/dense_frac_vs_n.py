@@ -11,7 +11,8 @@ import superman_b200 as sp
 peak = max(sp.fp64_peak(0, 200) for _ in range(3))
 print("# measured FP64 issue peak %.4e thread-instr/s" % peak)
 rows = []
-for n in range(13, 65):
+NS = [int(x) for x in os.environ["NS"].split(",")] if os.environ.get("NS") else range(13, 65)
+for n in NS:
     A = bench.synthetic_matrix(n, 0.5)
     hi = min(1 << (n - 1), 1 << 33)
     with sp.DenseHandle(A, n) as h:
