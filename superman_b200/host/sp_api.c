@@ -286,12 +286,34 @@ static void sparse_close(void *plan) { spd_sparse_plan_destroy((spd_sparse_plan 
 
 static const sp_job_ops g_sparse_ops = {sparse_open, sparse_launch, sparse_wait, sparse_close};
 
+/* SkipPer skips where some row's X is exactly 0 (gpu_exact_sparse.cu:644-666), i.e. where the selected
+ * entries of that row cancel its Nijenhuis-Wilf shift exactly: common for 0/1 and small-integer rows,
+ * essentially impossible for generic reals (the reference's own CPU SkipPer takes
+ * 0.31 s on -b, 6.9 s on int/, 26.7 s on double/ input).  A row can only cancel if all its entries are
+ * dyadic rationals; when no row qualifies, the skip bookkeeping (tile filter, block votes) cannot
+ * pay and the same engine runs without it -- the sum is identical, skipped terms being exact zeros.
+ * SP_SKIP_ALWAYS=1 keeps the skip engine on whatever the values. */
+static int some_row_can_cancel(const double *mat, int nov) {
+  const char *force = getenv("SP_SKIP_ALWAYS");
+  if (force && force[0] == '1') return 1;
+  for (int j = 0; j < nov; ++j) {
+    int dyadic = 1;
+    for (int k = 0; k < nov && dyadic; ++k) {
+      const double v = mat[j * nov + k] * 1024.0;
+      if (v != floor(v) || fabs(v) > 9007199254740992.0) dyadic = 0;
+    }
+    if (dyadic) return 1;
+  }
+  return 0;
+}
+
 static double sparse_common(const double *mat, const int *cptrs, const int *rows, const double *cvals,
                             int nov, int skip, int mode, int gpu_num, sp_stats *stats) {
   const double t0 = sp_now_ms();
   if (!mat || !cptrs || !rows || !cvals) { sp_set_error("null argument"); return fail(stats, SP_EINVAL); }
   if (nov < 1 || nov > 64) { sp_set_error("sparse Ryser supports 1 <= n <= 64 (got %d)", nov); return fail(stats, SP_ELIMIT); }
   if (gpu_num < 1) gpu_num = 1;
+  if (skip && !some_row_can_cancel(mat, nov)) skip = 0;
   if (nov == 1) {
     if (spd_device_count() <= 0) { sp_set_error("no CUDA device: %s", spd_last_error()); return fail(stats, SP_ENODEV); }
     return mat[0];
