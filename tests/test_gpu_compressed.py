@@ -146,3 +146,25 @@ def test_leaves_are_spread_over_the_devices(sp, oracle):
     st = sp.SpStats()
     few = sp.permanent_compressed(a, sparse=False, algo_id=5, gpu_num=g, leaf_nov=39, stats=st)
     assert few == pytest.approx(want, rel=1e-9)
+
+
+def test_compressed_random_matrices_against_the_direct_permanent(sp, oracle):
+    """end to end: C recursion + GPU leaves against the long-double permanent of the ORIGINAL matrix
+    (no recursion on the oracle side), small leaves so that every kind of step happens many times"""
+    rng = np.random.default_rng(2026)
+    kinds = 0
+    for trial in range(36):
+        n = int(rng.integers(14, 25))
+        if trial % 3 == 0:
+            a = banded(rng, n, "int" if trial % 2 else "real")
+        else:
+            a = sparse_matrix(rng, n, 1 + trial % 3, 3 + trial % 3, "int" if trial % 2 else "real")
+        if trial % 5 == 0:
+            a = a.T.copy()
+        want = oracle.perm_ld(a)
+        sparse, algo, pre = ((False, 4, 0), (True, 4, 1), (True, 7, 2))[trial % 3]
+        st = sp.SpStats()
+        got = sp.permanent_compressed(a, sparse=sparse, preprocessing=pre, algo_id=algo, leaf_nov=int(rng.integers(6, 12)), stats=st)
+        assert got == pytest.approx(want, rel=1e-9, abs=1e-9), (trial, n, got, want)
+        kinds += st.chunks > 1
+    assert kinds >= 10          # the recursion really split
