@@ -49,5 +49,10 @@ def corpus():
     return out
 
 
+def corpus_wide():
+    """a wider slice of the reference corpus (n = 30, 31; all three types; densities 0.1 ... 0.9)"""
+    return _load("corpus_wide.json") or {}
+
+
 def real():
     return _load("real.json") or {}

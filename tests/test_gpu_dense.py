@@ -118,6 +118,35 @@ def test_golden_corpus(sp):
             assert gotb == pytest.approx(e["ld_binary"], rel=REL), name
 
 
+def test_golden_corpus_wide(sp, tmp_path):
+    """30 more files of the reference corpus (int/, float/, double/; n = 30, 31; densities 0.1 ... 0.9),
+    read back through the library's own reader: dense Ryser, SpaRyser + SortOrder and SkipPer +
+    SkipOrder against the long-double oracle values of tests/golden/corpus_wide.json"""
+    c = _golden.corpus_wide()
+    assert len(c) >= 20
+    for name, e in sorted(c.items()):
+        p = tmp_path / name.replace("/", "_")
+        _golden.write_matrix_file(e, p)
+        n = e["n"]
+        want = e["ld"]
+        m = sp.Matrix.read(str(p))
+        assert m.nov == n and m.type == e["type"]
+        # a file without a perfect matching (density 0.1) has permanent 0: every method returns rounding
+        # noise of its 2^(n-1) Ryser terms, the long-double oracle included -- bound it by the term size
+        _, matching = sp.Matrix.read(str(p)).dm()
+        if matching < n:
+            a = np.abs(m.mat)
+            noise = (1 << (n - 1)) * n * 1.2e-16 * float(np.prod(a.sum(axis=1) / 2 + a.max(axis=1)))
+            check = lambda v: abs(v) <= noise and abs(want) <= noise
+        else:
+            check = lambda v: v == pytest.approx(want, rel=REL)
+        assert check(sp.dense_ryser(m.mat, n, 4)), name
+        m1 = sp.Matrix.read(str(p)).compress(1)
+        assert check(sp.sparse_ryser(m1.mat, m1.cptrs, m1.rows, m1.cvals, n, 4)), name
+        m2 = sp.Matrix.read(str(p)).compress(2)
+        assert check(sp.skipper(m2.mat, m2.rptrs, m2.cols, m2.cptrs, m2.rows, m2.cvals, n, 7)), name
+
+
 def test_small_golden_files_via_reader(sp, tmp_path):
     for idx, e in enumerate(_golden.small()):
         p = tmp_path / ("g%d.txt" % idx)

@@ -193,3 +193,22 @@ def test_cli_argument_errors():
     assert r.returncode == 1 and "CPU-only" in r.stderr
     r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)
     assert r.returncode == 1
+
+
+def test_wide_corpus_files_read_back_exactly(sp, tmp_path):
+    """30 files of the reference corpus (tests/golden/corpus_wide.json) through the reader and the
+    three orderings: values, type, nnz and CRS/CCS sizes as the file says"""
+    c = _golden.corpus_wide()
+    assert len(c) >= 20
+    for name, e in sorted(c.items()):
+        p = tmp_path / name.replace("/", "_")
+        _golden.write_matrix_file(e, p)
+        A = _golden.dense_from(e)
+        for pre in (0, 1, 2):
+            m = sp.Matrix.read(str(p)).compress(pre)
+            assert m.nov == e["n"] and m.type == e["type"] and m.header_nnz == e["header_nnz"]
+            assert m.nnz == int((A > 0).sum()) == len(m.rows) == len(m.cols)
+            if pre == 0:
+                assert np.array_equal(m.mat, A)
+            else:   # a row / column permutation of the same entries
+                assert np.array_equal(np.sort(m.mat, axis=None), np.sort(A, axis=None))
