@@ -54,5 +54,10 @@ def corpus_wide():
     return _load("corpus_wide.json") or {}
 
 
+def erdos():
+    """the 12 Erdos-Renyi matrices of the reference's SkipPer kit with the authors' recorded permanents"""
+    return _load("erdos.json") or {}
+
+
 def real():
     return _load("real.json") or {}

@@ -149,3 +149,43 @@ def test_reference_real_matrices(sp):
     m2 = sp.Matrix.from_dense(A).compress(2)
     assert sp.sparse_ryser(m1.mat, m1.cptrs, m1.rows, m1.cvals, n, 4) == pytest.approx(d, rel=REL)
     assert sp.skipper(m2.mat, m2.rptrs, m2.cols, m2.cptrs, m2.rows, m2.cvals, n, 7) == pytest.approx(d, rel=REL)
+
+
+def test_permanents_recorded_by_the_reference_authors(sp):
+    """known-answer vectors: the twelve 32x32 Erdos-Renyi 0/1 matrices of the reference's SkipPer kit
+    (revised_perman/sparyser/ErdosRenyi) with the permanents its authors recorded in
+    revised_perman/sparyser/Results/*.out for seven algorithm / ordering variants each
+    (tests/golden/erdos.json, made by tests/golden/make_erdos_golden.py).  The recorded variants agree
+    with each other to ~1e-10; every exact engine here must land inside that band and on the
+    long-double oracle value.  (For p = 0.40 and 0.50 the kit printed 0: those permanents exceed 2^64 and
+    its integer conversion overflowed -- only the long-double value is checked there.)"""
+    import _golden
+    c = _golden.erdos()
+    assert len(c) == 12
+    known = 0
+    for name, e in sorted(c.items()):
+        n = e["n"]
+        A = _golden.dense_from(e)
+        rec = sorted(float(v) for v in e["recorded"].values() if float(v) > 0)
+        if rec:
+            assert len(rec) >= 5 and rec[-1] == pytest.approx(rec[0], rel=1e-9), name
+            known += 1
+        else:
+            assert e["ld"] > 2.0 ** 64, name              # the kit's integer print overflowed
+            rec = [e["ld"]]
+        mid = rec[len(rec) // 2]
+        m1 = sp.Matrix.from_dense(A).compress(1)
+        m2 = sp.Matrix.from_dense(A).compress(2)
+        st = sp.SpStats()
+        results = {
+            "dense": sp.dense_ryser(A, n, 4),
+            "sparyser+sort": sp.sparse_ryser(m1.mat, m1.cptrs, m1.rows, m1.cvals, n, 4),
+            "skipper+skiporder": sp.skipper(m2.mat, m2.rptrs, m2.cols, m2.cptrs, m2.rows, m2.cvals, n, 7, stats=st),
+            "compressed": sp.permanent_compressed(A, sparse=True, preprocessing=1, algo_id=4),
+        }
+        assert st.visited < st.units                      # 0/1 rows: SkipPer really skips
+        for how, got in results.items():
+            assert got == pytest.approx(mid, rel=1e-9), (name, how, got, mid)
+            assert got == pytest.approx(e["ld"], rel=1e-9), (name, how)
+            assert rec[0] - 1e-9 * mid <= got <= rec[-1] + 1e-9 * mid, (name, how)
+    assert known == 6

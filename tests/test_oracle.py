@@ -147,3 +147,26 @@ def test_against_reference_live(oracle, reference):
                 assert np.array_equal(co[k], cr[k]), (n, pre, k)
     for m, k in ((4, 4), (5, 6), (6, 7)):
         assert np.array_equal(oracle.grid_graph(m, k)[0], reference.grid_graph(m, k)[0])
+
+
+def test_oracle_lands_on_the_permanents_recorded_by_the_reference_authors():
+    """tests/golden/erdos.json: the long-double oracle value of each 32x32 Erdos-Renyi matrix of the
+    reference's SkipPer kit lies inside the band of the seven permanents its authors recorded for that
+    matrix (revised_perman/sparyser/Results/*.out); the oracle ran at fixture-generation time
+    (tests/golden/make_erdos_golden.py, ~50 s per matrix), this test only reads the JSON"""
+    import _golden
+    c = _golden.erdos()
+    assert len(c) == 12
+    known = 0
+    for name, e in sorted(c.items()):
+        rec = sorted(float(v) for v in e["recorded"].values() if float(v) > 0)
+        if not rec:
+            assert e["ld"] > 2.0 ** 64          # the kit's integer print overflowed to 0
+            continue
+        known += 1
+        assert len(rec) >= 5
+        spread = (rec[-1] - rec[0]) / rec[0]
+        assert spread < 1e-9
+        assert rec[0] * (1 - 1e-12) <= e["ld"] <= rec[-1] * (1 + 1e-12), name
+        assert abs(e["ld"] - round(e["ld"])) < 0.01 or e["ld"] > 2.0 ** 53   # a 0/1 permanent is an integer
+    assert known == 6
