@@ -59,5 +59,11 @@ def erdos():
     return _load("erdos.json") or {}
 
 
+def known_perman():
+    """real-world pattern matrices (chesapeake 39x39, will57 57x57) with the permanents recorded by the
+    reference's SkipPer kit and, when generated, the CPU long-double recursion value"""
+    return _load("known_perman.json") or {}
+
+
 def real():
     return _load("real.json") or {}

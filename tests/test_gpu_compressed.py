@@ -168,3 +168,56 @@ def test_compressed_random_matrices_against_the_direct_permanent(sp, oracle):
         assert got == pytest.approx(want, rel=1e-9, abs=1e-9), (trial, n, got, want)
         kinds += st.chunks > 1
     assert kinds >= 10          # the recursion really split
+
+
+def test_real_matrices_with_recorded_permanents(sp):
+    """chesapeake (39x39, 340 entries) and will57 (57x57, 281 entries) from
+    revised_perman/elektrik_matrices/known_perman, with the permanents the reference's SkipPer kit
+    recorded (revised_perman/sparyser/RealResults/*.out, 260-1600 s of CPU time each) and the CPU
+    long-double recursion value of tests/golden/make_known_perman_ld.py when present.
+
+    What the numbers say (profiles/r01_real_known_perman.log): on chesapeake the kit's five variants
+    spread over 1e-5, and so do the DIRECT FP64 Ryser runs here (dense 2.4e-6, SpaRyser 3.6e-7 away) --
+    a 0/1 permanent of 1.3e13 is what is left of 2^38 terms of size up to 1e25, whoever sums them.  The
+    -o path (balanced leaves of order <= 30) is the well-conditioned one: it returns the same value to
+    14 digits for ten different reduction trees (transpose, permutations, leaf sizes).  will57 is only
+    reachable through -o (2^56 indices directly): ~2300 leaves, 2 s on one B200, the same value to 15
+    digits over ten reduction trees; the kit's two recorded values disagree with each other by 6 % and
+    are 6.5-6.9 times larger."""
+    import _golden
+    d = _golden.known_perman()
+    assert set(d) >= {"chesapeake", "will57"}
+
+    e = d["chesapeake"]
+    a = _golden.dense_from(e)
+    n = e["n"]
+    assert n == 39 and int((a != 0).sum()) == 340
+    rec = sorted(float(r["perman"]) for r in e["recorded"].values())
+    st = sp.SpStats()
+    trees = [sp.permanent_compressed(a, sparse=True, preprocessing=1, algo_id=4, stats=st),
+             sp.permanent_compressed(a, sparse=False, algo_id=4, leaf_nov=28),
+             sp.permanent_compressed(a.T.copy(), sparse=True, preprocessing=1, algo_id=4, leaf_nov=33)]
+    assert st.chunks > 100
+    ref = trees[0]
+    for v in trees:
+        assert v == pytest.approx(ref, rel=1e-12)
+    assert abs(ref - round(ref)) < 0.5                          # a 0/1 permanent below 2^53
+    assert rec[0] * (1 - 2e-5) <= ref <= rec[-1] * (1 + 2e-5), (ref, rec)
+    m1 = sp.Matrix.from_dense(a).compress(1)
+    direct = sp.sparse_ryser(m1.mat, m1.cptrs, m1.rows, m1.cvals, n, 4)
+    assert direct == pytest.approx(ref, rel=1e-5)              # direct FP64 Ryser: conditioning, see above
+    if "ld_recursion" in e:
+        assert ref == pytest.approx(e["ld_recursion"], rel=1e-11)
+
+    e = d["will57"]
+    a = _golden.dense_from(e)
+    assert e["n"] == 57 and int((a != 0).sum()) == 281
+    st = sp.SpStats()
+    v1 = sp.permanent_compressed(a, sparse=True, preprocessing=1, algo_id=4, stats=st)
+    v2 = sp.permanent_compressed(a, sparse=False, algo_id=4, leaf_nov=27)
+    v3 = sp.permanent_compressed(a.T.copy(), sparse=True, preprocessing=2, algo_id=7, leaf_nov=32)
+    assert st.chunks > 1000 and st.error == 0
+    assert v2 == pytest.approx(v1, rel=1e-12) and v3 == pytest.approx(v1, rel=1e-12)
+    assert v1 == pytest.approx(1.070536592880585e18, rel=1e-12)
+    if "ld_recursion" in e:
+        assert v1 == pytest.approx(e["ld_recursion"], rel=1e-11)
