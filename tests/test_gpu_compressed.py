@@ -206,6 +206,9 @@ def test_real_matrices_with_recorded_permanents(sp):
     m1 = sp.Matrix.from_dense(a).compress(1)
     direct = sp.sparse_ryser(m1.mat, m1.cptrs, m1.rows, m1.cvals, n, 4)
     assert direct == pytest.approx(ref, rel=1e-5)              # direct FP64 Ryser: conditioning, see above
+    # -u alone (Sinkhorn-balance the whole matrix, no compression) repairs the direct sum
+    scaled = sp.permanent_compressed(a, sparse=True, preprocessing=1, algo_id=4, scaling_threshold=1.0, leaf_nov=-1)
+    assert scaled == pytest.approx(ref, rel=1e-9)
     if "ld_recursion" in e:
         assert ref == pytest.approx(e["ld_recursion"], rel=1e-11)
 
