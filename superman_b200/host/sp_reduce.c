@@ -478,8 +478,9 @@ static void run_leaf(const reduce_ctx *cx, leaf *lf, int slot, int devices) {
     if (!cx->sparse)
       v = sp_dense_ryser_range(lf->m.mat, n, device, 0, end, &lf->st);
     else
-      v = sp_sparse_ryser_range(lf->m.mat, lf->m.cptrs, lf->m.rows, lf->m.cvals, n, cx->algo_id == 8, device, 0, end,
-                                &lf->st);
+      /* a balanced leaf has no exact zeros left to skip (sp_api.c: some_row_can_cancel) */
+      v = sp_sparse_ryser_range(lf->m.mat, lf->m.cptrs, lf->m.rows, lf->m.cvals, n,
+                                (cx->algo_id == 7 || cx->algo_id == 8) && !lf->scaled, device, 0, end, &lf->st);
     v *= sp_nw_factor(n);
   }
   if (isnan(v) && lf->st.error) {
