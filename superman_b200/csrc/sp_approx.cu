@@ -651,7 +651,7 @@ template <typename K>
 static int small_prepare(spd_approx_plan* p, K kern) {
   cudaError_t e;
   if (p->small_smem > 40 * 1024) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->small_smem);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->small_smem, cudaGetErrorString(e)); return SPD_ECUDA; }
   }
   int per_sm = 0;
@@ -706,7 +706,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
   size_t warp_bytes = deg_bytes + 2 * (size_t)words * 4 + (scaling ? 2 * (size_t)(nov + 1) * 4 : 0);
   warp_bytes = (warp_bytes + 15) & ~(size_t)15;
   p->smem_bytes = off + APX_WARPS * warp_bytes;
-  if (p->smem_bytes > 227 * 1024) {
+  if (p->smem_bytes > SPB_SMEM_OPTIN_BYTES) {
     set_error("pattern too large for shared memory (%zu B needed)", p->smem_bytes);
     return fail(SPD_ELIMIT);
   }
@@ -749,7 +749,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     }
   }
   if (p->smem_bytes > 40 * 1024) {
-    e = cudaFuncSetAttribute(warp_kernel_of(p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    e = cudaFuncSetAttribute(warp_kernel_of(p), cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", p->smem_bytes, cudaGetErrorString(e)); return fail(SPD_ECUDA); }
   }
   // ---- thread-per-trial engine for nov <= 64: 64-bit pattern words ----
@@ -794,7 +794,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     const size_t state = (size_t)(WD + WG + WC) * 4 * APM_THREADS;
     p->mid_smem = shared_part + state;
     if (p->mid_smem <= 220 * 1024) {
-      e = cudaFuncSetAttribute(rasmussen_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->mid_smem);
+      e = cudaFuncSetAttribute(rasmussen_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);
       int per = 0;
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rasmussen_mid_kernel, APM_THREADS, p->mid_smem);
       if (e == cudaSuccess && per >= 1) {

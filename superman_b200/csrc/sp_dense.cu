@@ -135,7 +135,7 @@ int enqueue_smem_range(Lane* L, const double* d_mat_t, const double* d_xbase, in
 int smem_kernel_prepare(int n) {
   const size_t smem_bytes = ((size_t)n * n + (size_t)n * SMEMK_THREADS) * sizeof(double);
   if (smem_bytes > 40 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ryser_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(ryser_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", smem_bytes, cudaGetErrorString(e)); return SPD_ECUDA; }
   }
   return SPD_OK;

@@ -6,6 +6,13 @@
 #include <stdint.h>
 #include "superman_b200_device.h"
 
+// Opt-in size for kernels that need more than the default 48 KiB of dynamic shared memory.  The
+// attribute is per function and per context -- shared by every host thread that launches the kernel
+// on that device -- so it is always set to the same constant (the 227 KiB opt-in maximum minus room
+// for the kernels' static shared memory), never to the size one particular launch needs: two
+// threads preparing launches of different sizes cannot lower it under each other's feet.
+#define SPB_SMEM_OPTIN_BYTES (227 * 1024 - 4096)
+
 namespace spb {
 
 void set_error(const char* fmt, ...);

@@ -16,7 +16,7 @@ static int launch_level(cudaStream_t st, const LevelArgs& a, unsigned blocks, si
   constexpr int MB = (B * S + R <= 16 && !(B == 4 && S == 4)) ? 4 : 3;
   auto kern = level_reg_kernel<B, S, R, SPB_REG_THREADS, MB, SKIP>;
   if (smem > 40 * 1024) {   // static shared memory (queue, partials) counts against the 48 KiB default too
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);
     if (e != cudaSuccess) { set_error("smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return SPD_ECUDA; }
   }
   kern<<<blocks, SPB_REG_THREADS, smem, st>>>(a);
