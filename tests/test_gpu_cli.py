@@ -132,3 +132,22 @@ def test_revised_front_end_flags(files):
     assert "Compressed: " in r.stdout and result_of(r.stdout)[1] == pytest.approx(e["ld"], rel=1e-9)
     r = run("-f", path, "-p", "4", "-l", "99")
     assert r.returncode == 1 and "device" in r.stderr
+
+
+def test_matrixmarket_real_matrix_through_the_cli(tmp_path):
+    """will57 (57x57 pattern matrix of revised_perman/elektrik_matrices/known_perman) written back as a
+    MatrixMarket file: `perman -s -p4 -r1 -o` reads it, compresses it and prints the permanent the
+    library returns for ten different reduction trees (tests/test_gpu_compressed.py)"""
+    e = _golden.known_perman()["will57"]
+    p = tmp_path / "will57.mtx"
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate pattern general\n% written by the test\n")
+        f.write("%d %d %d\n" % (e["n"], e["n"], len(e["triples"])))
+        for i, j, _ in e["triples"]:
+            f.write("%d %d\n" % (i + 1, j + 1))
+    r = run("-f", str(p), "-s", "-p", "4", "-r", "1", "-o", env={"PERMAN_PRECISION": "17"})
+    assert r.returncode == 0, r.stderr
+    assert re.search(r"^Compressed: \d{4,} leaf matrix\(es\)", r.stdout, flags=re.M)
+    name, v = result_of(r.stdout)
+    assert name == "gpu_perman64_xshared_coalescing_mshared_sparse"
+    assert v == pytest.approx(1.070536592880585e18, rel=1e-12)
