@@ -488,9 +488,12 @@ static void run_leaf(const reduce_ctx *cx, leaf *lf, int slot, int devices) {
     snprintf(lf->err, sizeof(lf->err), "%s", sp_last_error());
     return;
   }
-  if (lf->scaled)                               /* main.cpp:1143-1149 */
-    for (int i = 0; i < n; ++i) { v /= lf->cv[i]; v /= lf->rv[i]; }
-  lf->value = lf->coeff * v;
+  /* undo the scaling (main.cpp:1143-1149) in long double: the factors of a badly scaled leaf can be
+   * far apart (rv huge, cv tiny) and must not overflow on the way to a representable result */
+  long double lv = (long double)v;
+  if (lf->scaled)
+    for (int i = 0; i < n; ++i) { lv /= (long double)lf->cv[i]; lv /= (long double)lf->rv[i]; }
+  lf->value = (double)((long double)lf->coeff * lv);
 }
 
 typedef struct flush_arg { reduce_ctx *cx; int slot; int devices; } flush_arg;

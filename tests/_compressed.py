@@ -28,11 +28,13 @@ def leaf_perm(oracle, mat, mode):
     if mode == "none":
         return oracle.perm_ld(mat)
     b, rv, cv = sinkhorn(mat, sweeps=1 if mode == "one" else 2000)
-    p = oracle.perm_ld(b)
+    # without total support the factors drift apart (rv -> huge, cv -> tiny): undo them in long double,
+    # whose exponent range cannot overflow on the way
+    p = np.longdouble(oracle.perm_ld(b))
     for i in range(n):
-        p /= cv[i]
-        p /= rv[i]
-    return p
+        p /= np.longdouble(cv[i])
+        p /= np.longdouble(rv[i])
+    return float(p)
 
 
 def oracle_compressed(sp, oracle, a, leaf_nov=14, mode="full", max_leaf=24):
