@@ -128,8 +128,9 @@ int  sp_matrix_dm(sp_matrix *m, int *matching);
  * and Sinkhorn-balanced (sp_matrix_balance) to row / column sums scaling_threshold when that is > 0
  * (upstream's -u), to 1 when it is 0 and the compression changed the matrix (without it FP64 Ryser
  * on the merged matrices can be off by tens of percent), not at all when it is < 0 (upstream's
- * default), then computed
- * with sp_dense_ryser (sparse == 0; algo_id 0-6) or, after sp_matrix_compress(preprocessing),
+ * default); with scaling on, the input is balanced once before the first compression step as well
+ * (upstream's -u before -o, main.cpp:1637) and all factors are divided out in long double.  Leaves
+ * are computed with sp_dense_ryser (sparse == 0; algo_id 0-6) or, after sp_matrix_compress(preprocessing),
  * sp_sparse_ryser (algo_id 1-6) / sp_skipper (7, 8).  mat is the row-major nov x nov matrix as read
  * (not reordered).  stats: sums over the leaves, chunks = number of leaves. */
 double sp_permanent_compressed(const double *mat, int nov, int sparse, int preprocessing, int algo_id,

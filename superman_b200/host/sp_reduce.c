@@ -649,18 +649,46 @@ double sp_permanent_compressed(const double *mat, int nov, int sparse, int prepr
   sp_matrix m;
   int rc = sp_matrix_from_dense(mat, nov, &m);
   if (rc != SP_OK) { free(cx); if (stats) stats->error = rc; return NAN; }
+  /* With scaling on, balance the matrix once BEFORE compressing it, as upstream does (-u then -o,
+   * main.cpp:1637-1641): the d2 / d34 merges multiply entries, which must not overflow or drown on a
+   * badly scaled input.  Automatic mode (threshold 0) does it only when a first step applies -- an
+   * untouched matrix stays as it is. */
+  double *pre_rv = NULL, *pre_cv = NULL;
+  int structurally_zero = 0;
+  if (leaf_nov >= 0 && nov > 1) {
+    const int mind = sp_matrix_min_degree(&m);
+    const int will_alter = mind <= 2 || (mind < 5 && nov > cx->leaf_nov);
+    const double thr0 = scaling_threshold > 0 ? scaling_threshold : (scaling_threshold == 0 && will_alter) ? 1.0 : -1.0;
+    if (thr0 > 0 && mind > 0) {
+      int matching = 0;
+      rc = sp_matrix_dm(&m, &matching);
+      if (rc >= 0 && matching < nov) structurally_zero = 1;
+      if (rc >= 0 && !structurally_zero) {
+        pre_rv = (double *)malloc(2 * (size_t)nov * sizeof(double));
+        if (!pre_rv) { sp_set_error("out of memory"); rc = SP_ENOMEM; }
+        else { pre_cv = pre_rv + nov; rc = sp_matrix_balance(&m, thr0, pre_rv, pre_cv); }
+      }
+      if (rc < 0) { free(pre_rv); sp_matrix_free(&m); free(cx); if (stats) stats->error = rc; return NAN; }
+    }
+  }
   double factor = 1.0;
-  rc = leaf_nov < 0 ? 0 : sp_matrix_reduce(&m, &factor);
-  if (rc < 0) { sp_matrix_free(&m); free(cx); if (stats) stats->error = rc; return NAN; }
+  rc = (leaf_nov < 0 || structurally_zero) ? 0 : sp_matrix_reduce(&m, &factor);
+  if (rc < 0) { free(pre_rv); sp_matrix_free(&m); free(cx); if (stats) stats->error = rc; return NAN; }
   cx->altered = rc > 0;
-  if (factor == 0.0) {
+  if (factor == 0.0 || structurally_zero) {
     sp_matrix_free(&m);
   } else {
     recurse(cx, &m, factor);
     flush_leaves(cx);
   }
   const int failed = cx->failed;
-  const double perman = cx->sum;
+  double perman = cx->sum;
+  if (pre_rv) {
+    long double t = (long double)perman;
+    for (int i = 0; i < nov; ++i) { t /= (long double)pre_cv[i]; t /= (long double)pre_rv[i]; }
+    perman = (double)t;
+    free(pre_rv);
+  }
   if (failed) sp_set_error("%s", cx->err);
   if (stats) {
     *stats = cx->total;

@@ -224,3 +224,22 @@ def test_real_matrices_with_recorded_permanents(sp):
     assert v1 == pytest.approx(1.070536592880585e18, rel=1e-12)
     if "ld_recursion" in e:
         assert v1 == pytest.approx(e["ld_recursion"], rel=1e-11)
+
+
+def test_extreme_row_and_column_scales(sp, oracle):
+    """rows scaled by 1e+-120 and columns by 1e+-80: the direct Ryser sum overflows, the balanced one
+    (-u, or -o on a matrix the compression touches) does not -- its Sinkhorn factors are undone in long
+    double on the host"""
+    rng = np.random.default_rng(77)
+    n = 16
+    base = sparse_matrix(rng, n, 4, 7, "real")
+    rs = np.array([1e120 if i % 2 else 1e-120 for i in range(n)])
+    cs = np.array([1e-80 if j % 2 else 1e80 for j in range(n)])
+    a = base * rs[:, None] * cs[None, :]
+    want = float(np.longdouble(oracle.perm_ld(base)) * np.prod(rs.astype(np.longdouble)) * np.prod(cs.astype(np.longdouble)))
+    assert np.isfinite(want) and want > 0
+    assert not np.isfinite(sp.dense_ryser(a)) or sp.dense_ryser(a) != pytest.approx(want, rel=1e-6)   # direct: hopeless
+    got = sp.permanent_compressed(a, scaling_threshold=1.0, leaf_nov=-1)
+    assert got == pytest.approx(want, rel=1e-10)
+    got = sp.permanent_compressed(a, sparse=True, preprocessing=1, algo_id=4, scaling_threshold=2.0, leaf_nov=8)
+    assert got == pytest.approx(want, rel=1e-10)
