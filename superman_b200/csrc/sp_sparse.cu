@@ -184,7 +184,9 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
     const int forced = env_int("SP_SPARSE_LOWCOLS", 0);
     if (forced == 3 || forced == 4) B = forced;
     if (use_level) B = p->lvB;
-    const int tiles_log2 = env_int("SP_SPARSE_TILES_LOG2", 21);
+    // tile size: SpaRyser is fastest with 2^12-index tiles at n = 33 (less start-up work per index),
+    // SkipPer with 2^11 (its tile filter drops more when tiles are finer): 2^20 resp. 2^21 tiles per launch
+    const int tiles_log2 = env_int("SP_SPARSE_TILES_LOG2", p->skip ? 21 : 20);
     c = env_int("SP_SPARSE_TILE_LOG2", 0);
     if (c <= 0) {
       c = ilog2_ull(len) - tiles_log2;
