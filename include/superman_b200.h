@@ -186,7 +186,9 @@ double sp_sparse_ryser(const double *mat, const int *cptrs, const int *rows, con
 /* Replaces gpu_perman64_xshared_coalescing_mshared_skipper (gpu_exact_sparse.cu:1123; id 7: one
  * device) and _mshared_multigpucpu_chunks_skipper (:1192; id 8: dynamic chunks).  rptrs/cols are
  * accepted for signature parity: the skip test here needs only the column structure.
- * stats->visited reports how many Gray indices were actually evaluated. */
+ * stats->visited reports how many Gray indices were actually evaluated.  A row can only reach X = 0
+ * when all its entries are dyadic rationals; if no row qualifies (generic real values) the same engine
+ * runs without the skip bookkeeping (identical sum, visited == units; SP_SKIP_ALWAYS=1 overrides). */
 double sp_skipper(const double *mat, const int *rptrs, const int *cols, const int *cptrs,
                   const int *rows, const double *cvals, int nov, int algo_id, int gpu_num, int use_cpu,
                   int threads, sp_stats *stats);
