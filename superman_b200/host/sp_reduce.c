@@ -637,6 +637,14 @@ double sp_permanent_compressed(const double *mat, int nov, int sparse, int prepr
                                int threads, double scaling_threshold, int leaf_nov, sp_stats *stats) {
   const double t0 = sp_now_ms();
   if (stats) memset(stats, 0, sizeof(*stats));
+  /* a matrix that compresses all the way (triangular, diagonal, structurally singular) needs no
+   * kernel, but this is a GPU entry point like the others: without a device it fails, it does not
+   * quietly become a CPU implementation */
+  if (sp_device_count() <= 0) {
+    sp_set_error("no CUDA device (libsuperman_b200 has no CPU fallback)");
+    if (stats) stats->error = SP_ENODEV;
+    return NAN;
+  }
   reduce_ctx *cx = (reduce_ctx *)calloc(1, sizeof(reduce_ctx));
   if (!cx) { sp_set_error("out of memory"); if (stats) stats->error = SP_ENOMEM; return NAN; }
   cx->sparse = sparse; cx->preprocessing = preprocessing; cx->algo_id = algo_id;

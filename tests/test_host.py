@@ -169,6 +169,10 @@ def test_no_cpu_fallback(sp):
         sp.rasmussen_sparse(m.rptrs, m.cols, m.cptrs, m.rows, 4, m.nnz, 10)
     with pytest.raises(sp.SupermanError):
         sp.fp64_peak(0, 10)
+    # the -o driver too, even for matrices that compress away completely on the host
+    for a in (np.eye(6) * 2.0, np.triu(np.ones((7, 7))), np.ones((5, 5))):
+        with pytest.raises(sp.SupermanError):
+            sp.permanent_compressed(a)
 
 
 def test_product_does_not_link_the_oracle():
