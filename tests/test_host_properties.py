@@ -71,3 +71,35 @@ def test_partition_covers_the_range_exactly_once(sp, lo, length, parts, align):
     assert b[0] == lo and b[-1] == hi
     assert all(x <= y for x, y in zip(b, b[1:]))
     assert sum(y - x for x, y in zip(b, b[1:])) == length
+
+
+@settings(**SET)
+@given(st.data())
+def test_dm_split_and_balance_keep_the_permanent(sp, oracle, data):
+    """Dulmage-Mendelsohn erasure, the d34 split and Sinkhorn balancing are exact for ANY matrix"""
+    A = _matrix(data.draw, nmin=5, nmax=8)
+    n = A.shape[0]
+    want = oracle.perm_ld(A)
+    # DM: never changes the permanent; with a perfect matching the result has total support
+    m = sp.Matrix.from_dense(A)
+    erased, matching = m.dm()
+    assert 0 <= matching <= n and erased >= 0
+    if matching < n:
+        assert want == pytest.approx(0.0, abs=1e-9) and np.array_equal(m.mat, A)
+    else:
+        assert oracle.perm_ld(m.mat) == pytest.approx(want, rel=1e-12, abs=1e-9)
+        assert (m.mat <= A).all() and erased == int((A != 0).sum() - (m.mat != 0).sum())
+        # balancing the total support: row sums exact, permanent recovered from the factors
+        rv, cv, sweeps = m.scale(1.0, converge=True)
+        assert sweeps >= 1 and np.allclose(m.mat.sum(axis=1), 1.0, rtol=1e-12)
+        p = np.longdouble(oracle.perm_ld(m.mat))
+        for i in range(n):
+            p /= np.longdouble(cv[i]); p /= np.longdouble(rv[i])
+        assert float(p) == pytest.approx(want, rel=1e-10, abs=1e-9)
+    # d34 split on the smallest degree, when it is 3 or 4
+    m = sp.Matrix.from_dense(A)
+    d = m.min_degree()
+    if d in (3, 4):
+        other = m.split34(d)
+        assert other is not None and m.nov == other.nov == n - 1
+        assert oracle.perm_ld(m.mat) + oracle.perm_ld(other.mat) == pytest.approx(want, rel=1e-12, abs=1e-9)
