@@ -20,7 +20,11 @@ CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(BUILD)/sp_level_inst_b3s0.o $(BUILD)/sp_l
 C_SRCS  := sp_sched sp_api sp_matrix sp_reduce sp_connector
 C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
 
-all: $(LIB) $(CLI)
+all: $(LIB) $(CLI) profiles/resource_usage.txt
+
+# registers / stack (spills) / shared memory of every shipped kernel, regenerated from the linked library
+profiles/resource_usage.txt: $(LIB) tools/resource_report.py
+	python3 tools/resource_report.py $(LIB) $@
 
 $(BUILD):
 	mkdir -p $(BUILD)

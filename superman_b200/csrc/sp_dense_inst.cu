@@ -11,36 +11,61 @@
 
 namespace spb {
 
+// resident blocks per SM of one instantiation (occupancy query; also forces the lazily loaded
+// kernel into the context, so the first timed launch does not pay the module load)
+template <int N, int B, int MB>
+static int blocks_per_sm() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MB;
+  static int cached[64];
+  if (cached[dev] > 0) return cached[dev];
+  using L = DenseLayout<N, B>;
+  constexpr size_t dyn = L::DYN ? sizeof(double) * L::TOTAL : 0;
+  if (L::DYN && cudaFuncSetAttribute(ryser_reg_kernel<N, B, SPB_REG_THREADS, MB>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return MB;
+  }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, ryser_reg_kernel<N, B, SPB_REG_THREADS, MB>,
+                                                    SPB_REG_THREADS, dyn) != cudaSuccess || v < 1) {
+    (void)cudaGetLastError();
+    return MB;
+  }
+  cached[dev] = v;
+  return v;
+}
+
 template <int N, int B, int MB>
 static int launch_one(cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
-                      unsigned long long group_first, unsigned long long n_groups, int gpb, int c,
-                      unsigned* blocks_out) {
-  const unsigned long long blocks = (n_groups + (unsigned)gpb - 1) / (unsigned)gpb;
-  if (blocks == 0 || blocks > 0x7fffffffull) return SPD_EINVAL;
+                      unsigned long long group_first, unsigned int n_groups, unsigned int* queue, int c,
+                      int sm_count, unsigned* blocks_out) {
+  if (n_groups == 0) return SPD_EINVAL;
+  if (!mat_t) { *blocks_out = (unsigned)blocks_per_sm<N, B, MB>(); return SPD_OK; }   // prepare only
+  // persistent grid: resident blocks only, groups are pulled from queue[0]
+  unsigned blocks = (unsigned)sm_count * (unsigned)blocks_per_sm<N, B, MB>();
+  if (blocks > n_groups) blocks = n_groups;
+  using L = DenseLayout<N, B>;
   ryser_reg_kernel<N, B, SPB_REG_THREADS, MB>
-      <<<(unsigned)blocks, SPB_REG_THREADS, 0, st>>>(mat_t, xbase, partials, group_first, n_groups, gpb, c);
-  *blocks_out = (unsigned)blocks;
+      <<<blocks, SPB_REG_THREADS, L::DYN ? sizeof(double) * L::TOTAL : 0, st>>>(mat_t, xbase, partials, group_first, n_groups, queue, c);
+  *blocks_out = blocks;
   return SPD_OK;
 }
 
 // Registers: X is 2N, the 2^B running products 2^(B+1); 4 blocks of 128 threads per SM leave 128
-// registers per thread, 3 blocks 168, 2 blocks 255 (ptxas -v: zero spills for every entry below).
+// registers per thread, 3 blocks 168, 2 blocks 255.  The build regenerates
+// profiles/ptxas_dense_resource_usage.txt from the shipped library (make resource-report).
 template <int N, int B>
 static int launch_nb(cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
-                     unsigned long long group_first, unsigned long long n_groups, int gpb, int c,
-                     unsigned* blocks_out) {
-  // blocks per SM from the ptxas -v survey of every (N, B, MB) and a timing of every order
-  // (profiles/r01_ptxas_spill_survey_dense.txt, r01_dense_frac_vs_n.log): the largest occupancy without
-  // spills, except where a spill of <= 60 bytes outside the inner product loop measured faster than the
-  // next lower occupancy (n = 33, 40: 4 blocks; n = 55..59: 3 blocks)
-  constexpr int MB = (B == 4) ? ((N <= 40) ? 4 : (N <= 59) ? 3 : 2) : ((N > 54) ? 2 : (N <= 43 ? 4 : 3));
-  return launch_one<N, B, MB>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out);
+                     unsigned long long group_first, unsigned int n_groups, unsigned int* queue, int c,
+                     int sm_count, unsigned* blocks_out) {
+  constexpr int MB = (B == 4) ? ((N <= 40) ? 4 : (N <= 59) ? 3 : 2) : ((N <= 43) ? 4 : 3);
+  return launch_one<N, B, MB>(st, mat_t, xbase, partials, group_first, n_groups, queue, c, sm_count, blocks_out);
 }
 
 #define SPB_CASE(N)                                                                          \
   case N:                                                                                    \
-    if (B == 3) return launch_nb<N, 3>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out); \
-    if (B == 4) return launch_nb<N, 4>(st, mat_t, xbase, partials, group_first, n_groups, gpb, c, blocks_out); \
+    if (B == 3) return launch_nb<N, 3>(st, mat_t, xbase, partials, group_first, n_groups, queue, c, sm_count, blocks_out); \
+    if (B == 4) return launch_nb<N, 4>(st, mat_t, xbase, partials, group_first, n_groups, queue, c, sm_count, blocks_out); \
     return SPD_ELIMIT;
 
 #define SPB_GLUE2(a, b) a##b
@@ -48,7 +73,8 @@ static int launch_nb(cudaStream_t st, const double* mat_t, const double* xbase, 
 
 extern "C" int SPB_GLUE(spb_reg_launch_g, SPB_GROUP)(
     int n, int B, cudaStream_t st, const double* mat_t, const double* xbase, double* partials,
-    unsigned long long group_first, unsigned long long n_groups, int gpb, int c, unsigned* blocks_out) {
+    unsigned long long group_first, unsigned int n_groups, unsigned int* queue, int c, int sm_count,
+    unsigned* blocks_out) {
   switch (n) {
 #if SPB_GROUP == 0
     SPB_CASE(16) SPB_CASE(24) SPB_CASE(32) SPB_CASE(40) SPB_CASE(48) SPB_CASE(56) SPB_CASE(64)

@@ -40,6 +40,8 @@ static int lane_create(int device, Lane* lane) {
   SPB_CUDA(cudaEventCreate(&lane->ev1));
   SPB_CUDA(cudaMallocHost(&lane->h_result, 8 * sizeof(double)));
   SPB_CUDA(cudaMalloc(&lane->d_result, 8 * sizeof(double)));
+  SPB_CUDA(cudaMalloc(&lane->d_queue, 16 * sizeof(unsigned int)));
+  SPB_CUDA(cudaMemset(lane->d_queue, 0, 16 * sizeof(unsigned int)));
   lane->arena_cap = 4u << 20;
   SPB_CUDA(cudaMalloc(&lane->d_arena, lane->arena_cap));
   SPB_CUDA(cudaDeviceGetAttribute(&lane->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -53,6 +55,7 @@ static void lane_destroy(Lane* lane) {
   if (lane->d_partials) cudaFree(lane->d_partials);
   if (lane->d_arena) cudaFree(lane->d_arena);
   if (lane->d_aux) cudaFree(lane->d_aux);
+  if (lane->d_queue) cudaFree(lane->d_queue);
   if (lane->d_result) cudaFree(lane->d_result);
   if (lane->h_result) cudaFreeHost(lane->h_result);
   if (lane->ev0) cudaEventDestroy(lane->ev0);

@@ -38,6 +38,7 @@ struct Lane {
   size_t partials_cap = 0;      // in doubles
   unsigned long long* d_aux = nullptr;   // per-block integer counters (visited blocks)
   size_t aux_cap = 0;
+  unsigned int* d_queue = nullptr;       // {next work item, blocks done} of the persistent kernels; 0 between launches
   char* d_arena = nullptr;      // plan inputs (matrix, CRS/CCS, ...) live here
   size_t arena_cap = 0, arena_used = 0;
   int sm_count = 0;
