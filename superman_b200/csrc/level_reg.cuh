@@ -4,13 +4,16 @@
 // walks it in aligned blocks of 2^B), but the work per index follows the STRUCTURE of the matrix:
 // a row whose lowest non-zero column is L ("level" L) can only change when a column >= L flips.
 //
-//   hot rows (level < B): X in registers, in B*S fixed slots, S per level (the host packs the rows
-//     into slots; free slots hold the neutral row x = 1, entries 0).  A level-L slot takes only
+//   hot rows (level < B): X in registers, in fixed slots: S0 for level 0 (the most expensive level:
+//     2^B values per block) and S for each other level (the host packs the rows into slots; free
+//     slots hold the neutral row x = 1, entries 0).  A level-L slot takes only
 //     2^(B-L) distinct values inside a block, so it costs 2^(B-L) updates and multiplies into its
-//     level's 2^(B-L) running products PL[L][.] instead of 2^B of each.  The 2^B terms of a block,
-//     term_u = PL[0][u] * PL[1][u>>1] * ... * PL[B-1][u>>(B-1)] * Q, are summed with their signs by
-//     pairing bottom-up: E_0[w] = PL0[2w] - PL0[2w+1], E_L[w] = PL_L[2w] E_{L-1}[2w] + PL_L[2w+1]
-//     E_{L-1}[2w+1], sum = Q * E_{B-1}[0] -- 2^B + B - 1 instructions instead of 3 * 2^B - 2.
+//     level's 2^(B-L) products PL_L[.] instead of 2^B of each.  The 2^B terms of a block,
+//     term_u = PL_0[u] * PL_1[u>>1] * ... * PL_{B-1}[u>>(B-1)] * Q, are summed with their signs by
+//     pairing bottom-up: T_0[w] = PL_0[2w] - PL_0[2w+1], T_L[w] = PL_L[2w] T_{L-1}[2w] + PL_L[2w+1]
+//     T_{L-1}[2w+1], sum = Q * T_{B-1}[0] -- 2^B + B - 1 instructions instead of 3 * 2^B - 2.  Every
+//     product is folded into T the moment it exists, so at most 2^(B-1) partial sums are alive and
+//     the register file has room for the register-cold rows below.
 //     Everything here is compile-time structured: straight-line code, no runtime branch.
 //   register-cold rows: the R cold rows of lowest level (the ones refreshed most often) also stay
 //     in registers: one update and one multiply per block, in straight-line code.
@@ -22,6 +25,14 @@
 //     next level that has some (s_grp), and every row knows the slot it closes (s_slot, a dummy
 //     slot for most rows), so the refresh is ONE flat loop over the touched rows.
 //
+// As in the dense kernel, the direction of a register row's update is not a +/-1.0 factor but a
+// choice between shared-memory images (D, -D, zeros; two low-column images), so the block loop's
+// addresses are block-uniform; the one update whose direction depends on the tile's parity (the
+// middle block of a tile) adds the column like an even tile, and odd tiles take it out twice first.
+//
+// Work distribution: a persistent grid; every warp pulls chunks of tiles from an atomic counter and
+// leaves one partial sum per chunk (bit-reproducible whichever warp took which chunk).
+//
 // SkipPer (SKIP = true): terms with a zero cold row are exact zeros (Q == 0).  Tiles whose
 // tile-constant rows (level >= c) contain a zero are dropped by a warp-wide filter (ballot +
 // shared-memory queue compaction, full warps only); blocks with Q == 0 in every lane skip the hot
@@ -31,10 +42,20 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "ryser_reg.cuh"
 
 
 namespace spb {
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
 
 struct LevelArgs {
   // packed device image (doubles unless noted), see sp_sparse.cu: level_pack()
@@ -44,48 +65,88 @@ struct LevelArgs {
   const double* xb_hot;      // [HS + R]
   const double* xb_cold;     // [NC]
   const int* cold_start;     // [n - B + 2]     first cold row of level >= B+i
-  double* partials;
-  unsigned long long* visited;
+  double* partials;          // [n_chunks]
+  unsigned long long* visited;   // [n_chunks]  blocks of 2^B indices evaluated
+  unsigned int* queue;       // {next chunk, warps that have left}; zero between launches
   unsigned long long tile_first, n_tiles;
+  unsigned int n_chunks;     // chunk = tiles_per_warp consecutive tiles
   int n, NC, NCP, HSP;
   int c;
   int tiles_per_warp;
 };
 
-template <int B, int S, int R>
+template <int B, int S0, int S, int R>
 struct LevelLayout {
-  static constexpr int HS = B * S;           // level slots
-  static constexpr int HT = HS + R;          // + register-cold rows
+  static constexpr int HS = S0 + (B - 1) * S;   // level slots: [0, S0) level 0, then S per level
+  static constexpr int HT = HS + R;             // + register-cold rows
   static constexpr int HSP = HT + (HT & 1);
   static constexpr int LB = B + (B & 1);
+  __host__ __device__ static constexpr int base(int L) { return L == 0 ? 0 : S0 + (L - 1) * S; }
+  __host__ __device__ static constexpr int count(int L) { return L == 0 ? S0 : S; }
 };
 
-// dynamic shared memory (doubles):  colT_hot | lowR | dcold | xb_hot | xb_cold | Xc[NC][T] | SP[c-B+2][T]
+// register-cold rows and resident blocks per SM that go with a slot configuration: 20 register rows fit
+// 128 registers (4 blocks of 128 threads per SM), about 30 fit 168 (3 blocks); the SkipPer variant needs a
+// few registers more (tile queue, votes) and gives up four register-cold rows at the edges
+__host__ __device__ constexpr int level_slots(int B, int S0, int S) { return S0 + (B - 1) * S; }
+__host__ __device__ constexpr int level_regcold(int B, int S0, int S, bool skip) {
+  const int hs = level_slots(B, S0, S);
+  int r = hs <= 12 ? 8 : hs <= 16 ? 4 : hs <= 24 ? 8 : 0;
+  if (skip && r >= 4 && (hs + r == 19 || hs + r == 20)) r -= 4;
+  return r;
+}
+__host__ __device__ constexpr int level_minblocks(int B, int S0, int S, bool skip) {
+  const int ht = level_slots(B, S0, S) + level_regcold(B, S0, S, skip);
+  return ht <= 20 ? 4 : (ht <= 30 || !skip) ? 3 : 2;
+}
+
+// bytes of dynamic shared memory the kernel needs (host and device agree through this one function)
+__host__ __device__ inline size_t level_smem_bytes(int n, int B, int HS, int HSP, int LB, int NC, int NCP, int c,
+                                                   int threads) {
+  const size_t dbl = 2 * (size_t)(n - 1) * HSP + HSP + 2 * (size_t)HS * LB + (size_t)(n - 1) * NCP + HSP + NCP +
+                     (size_t)(NC + 2) * threads + (size_t)(c - B + 2) * threads;
+  return dbl * sizeof(double) + (size_t)((n - B + 2) + (c - B + 1) + NC) * sizeof(int);
+}
+
+// dynamic shared memory (doubles):  colP | colN | zero | low0 | low1 | dcold | xb_hot | xb_cold | Xc[NC + 2][T] | SP[c-B+2][T]
+// (rows NC and NC+1 of Xc hold each thread's running sum and evaluated-block count for its current chunk: they
+// are kept out of the register file, which the block loop needs, and share the thread's X address register)
 // then ints: cold_start[n-B+2] | grp[c-B+1] | slot[NC]
-template <int B, int S, int R, int THREADS, int MINBLOCKS, bool SKIP>
+template <int B, int S0, int S, int R, int THREADS, int MINBLOCKS, bool SKIP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 level_reg_kernel(const LevelArgs a) {
-  using LL = LevelLayout<B, S, R>;
+  using LL = LevelLayout<B, S0, S, R>;
   constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
   extern __shared__ __align__(16) double dsm[];
   const int n = a.n, NC = a.NC, NCP = a.NCP, c = a.c;
   const int nseg = c - B;                       // SP[0 .. nseg]
-  double* s_colT = dsm;
-  double* s_lowR = s_colT + (size_t)(n - 1) * HSP;
-  double* s_dcold = s_lowR + HS * LB;
+  double* s_colP = dsm;                         //  D
+  double* s_colN = s_colP + (size_t)(n - 1) * HSP;   // -D
+  double* s_zero = s_colN + (size_t)(n - 1) * HSP;   //  0 (first block of a tile: X is already explicit)
+  double* s_low0 = s_zero + HSP;
+  double* s_low1 = s_low0 + HS * LB;            // column B-1 negated
+  double* s_dcold = s_low1 + HS * LB;
   double* s_xbh = s_dcold + (size_t)(n - 1) * NCP;
   double* s_xbc = s_xbh + HSP;
-  double* s_X = s_xbc + NCP;                    // [NC][THREADS]
-  double* s_SP = s_X + (size_t)NC * THREADS;    // [nseg + 2][THREADS]: one per group of levels + a dummy
+  double* s_X = s_xbc + NCP;                    // [NC + 2][THREADS]
+  double* s_SP = s_X + (size_t)(NC + 2) * THREADS;   // [nseg + 2][THREADS]: one per group of levels + a dummy
   int* s_cs = reinterpret_cast<int*>(s_SP + (size_t)(nseg + 2) * THREADS);
   int* s_grp = s_cs + (n - B + 2);              // [nseg + 1]  SP slot of segment seg
   int* s_slot = s_grp + (nseg + 1);             // [NC]        SP slot closed by cold row jc (or the dummy)
-  __shared__ double warp_part[WARPS];
-  __shared__ unsigned long long warp_vis[WARPS];
-  __shared__ unsigned long long queue[WARPS][64];
+  __shared__ unsigned long long tq[WARPS][64];  // surviving tiles of the warp's current chunk
+  __shared__ unsigned int s_chunk[WARPS];       // the chunk each warp is working on (same reason)
 
-  for (int e = threadIdx.x; e < (n - 1) * HSP; e += THREADS) s_colT[e] = a.colT_hot[e];
-  for (int e = threadIdx.x; e < HS * LB; e += THREADS) s_lowR[e] = a.lowR[e];
+  for (int e = threadIdx.x; e < (n - 1) * HSP; e += THREADS) {
+    const double v = a.colT_hot[e];
+    s_colP[e] = v;
+    s_colN[e] = -v;
+  }
+  for (int e = threadIdx.x; e < HSP; e += THREADS) s_zero[e] = 0.0;
+  for (int e = threadIdx.x; e < HS * LB; e += THREADS) {
+    const double v = a.lowR[e];
+    s_low0[e] = v;
+    s_low1[e] = (e % LB == B - 1) ? -v : v;
+  }
   for (int e = threadIdx.x; e < (n - 1) * NCP; e += THREADS) s_dcold[e] = a.dcold[e];
   for (int e = threadIdx.x; e < HT; e += THREADS) s_xbh[e] = a.xb_hot[e];
   for (int e = threadIdx.x; e < NC; e += THREADS) s_xbc[e] = a.xb_cold[e];
@@ -106,212 +167,231 @@ level_reg_kernel(const LevelArgs a) {
   }
   __syncthreads();
 
-  const uint32_t sm_colT = (uint32_t)__cvta_generic_to_shared(s_colT);
-  const uint32_t sm_lowR = (uint32_t)__cvta_generic_to_shared(s_lowR);
+  const uint32_t sm_colP = (uint32_t)__cvta_generic_to_shared(s_colP);
+  const uint32_t sm_low0 = (uint32_t)__cvta_generic_to_shared(s_low0);
+  const uint32_t neg_off = (uint32_t)((size_t)(n - 1) * HSP * 8);       // colN - colP
+  const uint32_t zero_off = 2u * neg_off;                              // zero - colP
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* myX = s_X + threadIdx.x;
   double* mySP = s_SP + threadIdx.x;
   const int tc_first = s_cs[nseg];              // cold rows >= this index are constant over a tile
+  const int nblk = 1 << (c - B);
 
-  const unsigned long long wg = (unsigned long long)blockIdx.x * WARPS + wib;
-  unsigned long long cand = wg * (unsigned long long)a.tiles_per_warp;
-  unsigned long long cand_hi = cand + (unsigned long long)a.tiles_per_warp;
-  if (cand_hi > a.n_tiles) cand_hi = a.n_tiles;
-
-  double acc = 0.0;
-  unsigned long long vis = 0;
-  int q = 0;
-  for (;;) {
-    // ---- refill: test 32 candidate tiles per trip until a full warp of survivors is queued ----
-    while (q < 32 && cand < cand_hi) {
-      const unsigned long long t = cand + lane;
-      bool alive = t < cand_hi;
-      if (SKIP && tc_first < NC) {
-        const unsigned long long s = (a.tile_first + (alive ? t : cand)) << c;
-        const unsigned long long g = s ^ (s >> 1);
-        for (int jc = tc_first; jc < NC; ++jc) {
-          double xr = s_xbc[jc];
-          for (int k = c; k < n - 1; ++k)
-            xr = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], xr);
-          alive = alive && (xr != 0.0);
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, alive);
-      if (alive) queue[wib][q + __popc(m & ((1u << lane) - 1u))] = t;
-      q += __popc(m);
-      cand += 32;
-    }
-    __syncwarp();
-    if (q == 0) break;
-    const int take = q < 32 ? q : 32;
-    const bool active = lane < take;
-    const unsigned long long my_tile = queue[wib][active ? lane : 0];
-    __syncwarp();
-    if (lane + 32 < q) queue[wib][lane] = queue[wib][lane + 32];
-    q -= take;
-    __syncwarp();
-
-    // ---- explicit X at the tile start (cf. gpu_exact_sparse.cu:497-503) -------------------------
-    const unsigned long long s = (a.tile_first + my_tile) << c;
-    const unsigned long long g = s ^ (s >> 1);
-    double xh[HT];
-#pragma unroll
-    for (int i = 0; i < HT; ++i) xh[i] = s_xbh[i];
-    for (int k = c - 1; k < n - 1; ++k) {
-      const double f = (double)((g >> k) & 1ull);
-      const double* col = s_colT + k * HSP;
-#pragma unroll
-      for (int i = 0; i < HT; ++i) xh[i] = fma(f, col[i], xh[i]);
-    }
-    {
-      // cold rows, from the last (highest level) to the first, building the suffix products
-      double run = 1.0;
-      if (tc_first == NC) mySP[s_grp[nseg] * THREADS] = 1.0;     // no tile-constant rows: empty product
-      for (int jc = NC - 1; jc >= 0; --jc) {
-        double x = s_xbc[jc];
-        for (int k = c - 1; k < n - 1; ++k)
-          x = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], x);
-        myX[jc * THREADS] = x;
-        run *= x;
-        mySP[s_slot[jc] * THREADS] = run;
-      }
-    }
-
-    double tile_acc = 0.0;
-    unsigned long long tile_vis = 0;
-    const int nblk = 1 << (c - B);
-    const int tile_odd = (int)((a.tile_first + my_tile) & 1ull);
 #pragma unroll 1
-    for (int blk = 0; blk < nblk; ++blk) {
-      const int z = (blk != 0) ? (__ffs(blk) - 1) : 0;     // k - B
-      const int k = B + z;
-      const int up = (k + 1 < c) ? ((blk >> (z + 1)) & 1) : tile_odd;
-      const double sg = (blk != 0) ? (up ? -1.0 : 1.0) : 0.0;
-      const double sg_top = (blk & 1) ? -1.0 : 1.0;
+  for (;;) {
+    // ---- next chunk of tiles for this warp ----
+    unsigned int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&a.queue[0], 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= a.n_chunks) break;
+    if (lane == 0) s_chunk[wib] = chunk;
+    unsigned long long cand = (unsigned long long)chunk * (unsigned long long)a.tiles_per_warp;
+    unsigned long long cand_hi = cand + (unsigned long long)a.tiles_per_warp;
+    if (cand_hi > a.n_tiles) cand_hi = a.n_tiles;
 
-      const uint32_t hi_addr = sm_colT + (uint32_t)(k * HSP * 8);
-      // ---- cold rows of level <= k: update, refresh SP[z .. 0] ----
-      double Q;
-      if (blk != 0) {
-        double run = mySP[s_grp[z + 1] * THREADS];
-        const double* dk = s_dcold + k * NCP;
-        double* px = myX + (size_t)s_cs[z + 1] * THREADS;
-        int jc = s_cs[z + 1] - 1;
-        for (; jc >= 0; --jc) {
-          px -= THREADS;
-          const double x = fma(sg, dk[jc], *px);
-          *px = x;
+    myX[(size_t)NC * THREADS] = 0.0;
+    reinterpret_cast<unsigned long long*>(myX)[(size_t)(NC + 1) * THREADS] = 0ull;
+    int q = 0;
+#pragma unroll 1
+    for (;;) {
+      // ---- refill: test 32 candidate tiles per trip until a full warp of survivors is queued ----
+      while (q < 32 && cand < cand_hi) {
+        const unsigned long long t = cand + lane;
+        bool alive = t < cand_hi;
+        if (SKIP && tc_first < NC) {
+          const unsigned long long s = (a.tile_first + (alive ? t : cand)) << c;
+          const unsigned long long g = s ^ (s >> 1);
+          for (int jc = tc_first; jc < NC; ++jc) {
+            double xr = s_xbc[jc];
+            for (int k = c; k < n - 1; ++k)
+              xr = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], xr);
+            alive = alive && (xr != 0.0);
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (alive) tq[wib][q + __popc(m & ((1u << lane) - 1u))] = t;
+        q += __popc(m);
+        cand += 32;
+      }
+      __syncwarp();
+      if (q == 0) break;
+      const int take = q < 32 ? q : 32;
+      const bool active = lane < take;
+      const unsigned long long my_tile = tq[wib][active ? lane : 0];
+      __syncwarp();
+      if (lane + 32 < q) tq[wib][lane] = tq[wib][lane + 32];
+      q -= take;
+      __syncwarp();
+
+      // ---- explicit X at the tile start (cf. gpu_exact_sparse.cu:497-503) -----------------------
+      const unsigned long long s = (a.tile_first + my_tile) << c;
+      const unsigned long long g = s ^ (s >> 1);
+      double xh[HT];
+#pragma unroll
+      for (int i = 0; i < HT; ++i) xh[i] = s_xbh[i];
+      for (int k = c - 1; k < n - 1; ++k) {
+        const double f = (double)((g >> k) & 1ull);
+        const double* col = s_colP + k * HSP;
+#pragma unroll
+        for (int i = 0; i < HT; ++i) xh[i] = fma(f, col[i], xh[i]);
+      }
+      {
+        // cold rows, from the last (highest level) to the first, building the suffix products
+        double run = 1.0;
+        if (tc_first == NC) mySP[s_grp[nseg] * THREADS] = 1.0;     // no tile-constant rows: empty product
+        for (int jc = NC - 1; jc >= 0; --jc) {
+          double x = s_xbc[jc];
+          for (int k = c - 1; k < n - 1; ++k)
+            x = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], x);
+          myX[jc * THREADS] = x;
           run *= x;
           mySP[s_slot[jc] * THREADS] = run;
         }
-        Q = run;
-      } else {
-        Q = mySP[0];
       }
 
-      // ---- register-cold rows: one update, one multiply ----
-      if (R > 0) {
-        double r0 = 1.0, r1 = 1.0;
+#pragma unroll 1
+      for (int blk = 0; blk < nblk; ++blk) {
+        // high column flipped at the block start: k = B + ctz(blk), the same for the whole grid; it is
+        // added when bit k+1 of the index is clear.  That bit is a bit of blk, except for the middle
+        // block of the tile (k = c-1), where it is the tile's parity: handled by the correction below.
+        const int z = (blk != 0) ? (__ffs(blk) - 1) : 0;     // k - B
+        const int k = B + z;
+        const int up = (k + 1 < c) ? ((blk >> (z + 1)) & 1) : 0;
+        const int tile_odd = (int)((a.tile_first + my_tile) & 1ull);
+        if (blk == (nblk >> 1)) {
+          const double f = -2.0 * (double)tile_odd;
+          const double* col = s_colP + (c - 1) * HSP;
 #pragma unroll
-        for (int i = HS; i < HT; ++i) {
-          double d;
-          lds_f64(hi_addr + (uint32_t)(i * 8), d);
-          xh[i] = fma(sg, d, xh[i]);
-          if (i & 1) r1 *= xh[i]; else r0 *= xh[i];
+          for (int i = 0; i < HT; ++i) xh[i] = fma(f, col[i], xh[i]);
         }
-        Q *= r0 * r1;
-      }
-      const bool skip_blk = SKIP && __all_sync(0xffffffffu, !active || Q == 0.0);
-      if (skip_blk) {
-        // exact zeros: only the block's net effect on the hot slots (high column + column B-1)
-#pragma unroll
-        for (int i = 0; i < HS; ++i) {
-          double mt;
-          lds_f64(sm_lowR + (uint32_t)((i * LB + (B - 1)) * 8), mt);
-          double d;
-          lds_f64(hi_addr + (uint32_t)(i * 8), d);
-          xh[i] = fma(sg_top, mt, fma(sg, d, xh[i]));
+        const uint32_t hi_addr = sm_colP + ((blk != 0) ? (uint32_t)(k * HSP * 8) + (up ? neg_off : 0u) : zero_off);
+        // column B-1 flips in the middle of the block; its direction is bit B of the index
+        const uint32_t low_addr = sm_low0 + (uint32_t)((blk & 1) * (HS * LB * 8));
+
+        // ---- cold rows of level <= k: update, refresh SP[z .. 0] (per-thread direction) ----
+        double Q;
+        if (blk != 0) {
+          const int upt = (k + 1 < c) ? up : tile_odd;
+          const double sg = upt ? -1.0 : 1.0;
+          double run = mySP[s_grp[z + 1] * THREADS];
+          const double* dk = s_dcold + k * NCP;
+          double* px = myX + (size_t)s_cs[z + 1] * THREADS;
+          int jc = s_cs[z + 1] - 1;
+          for (; jc >= 0; --jc) {
+            px -= THREADS;
+            const double x = fma(sg, dk[jc], *px);
+            *px = x;
+            run *= x;
+            mySP[s_slot[jc] * THREADS] = run;
+          }
+          Q = run;
+        } else {
+          Q = mySP[0];
         }
-      } else {
-        // ---- hot slots: level L takes 2^(B-L) values; the slots of a level advance together, CH
-        // independent chains at a time, and multiply into the level's running products PL[L][w] ----
-        constexpr int CH = (B * S + R > 20) ? 1 : (S % 3 == 0) ? 3 : (S % 2 == 0) ? 2 : 1;   // register budget
-        double PL[2 * NB];
-        // layout: level L occupies indices [off(L), off(L) + 2^(B-L)), off(L) = 2*NB - 2*(NB >> L)
+
+        // ---- register-cold rows: one update, one multiply ----
+        if (R > 0) {
+          double r0 = 1.0, r1 = 1.0;
 #pragma unroll
-        for (int L = 0; L < B; ++L) {
-          const int off = 2 * NB - 2 * (NB >> L);
-          const int cnt = NB >> L;
+          for (int i = HS; i < HT; ++i) {
+            double d;
+            lds_f64(hi_addr + (uint32_t)(i * 8), d);
+            xh[i] += d;
+            if (i & 1) r1 *= xh[i]; else r0 *= xh[i];
+          }
+          Q *= r0 * r1;
+        }
+        const bool skip_blk = SKIP && __all_sync(0xffffffffu, !active || Q == 0.0);
+        if (skip_blk) {
+          // exact zeros: only the block's net effect on the hot slots (high column + column B-1)
 #pragma unroll
-          for (int t0 = 0; t0 < S; t0 += CH) {
-            double v[CH], m[CH][LB];
-#pragma unroll
-            for (int t = 0; t < CH; ++t) {
-              const int i = L * S + t0 + t;
-#pragma unroll
-              for (int qq = (L & ~1); qq < LB; qq += 2)       // only columns >= L flip inside this level
-                lds_f64x2(sm_lowR + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
-              double d;
-              lds_f64(hi_addr + (uint32_t)(i * 8), d);
-              v[t] = fma(sg, d, xh[i]);
-            }
-            {
-              double pr = v[0];
-#pragma unroll
-              for (int t = 1; t < CH; ++t) pr *= v[t];
-              PL[off] = (t0 == 0) ? pr : PL[off] * pr;
-            }
-#pragma unroll
-            for (int w = 1; w < cnt; ++w) {
-              const int u = w << L;
-              const int K = ctz_c(u);
+          for (int i = 0; i < HS; ++i) {
+            double mt;
+            lds_f64(low_addr + (uint32_t)((i * LB + (B - 1)) * 8), mt);
+            double d;
+            lds_f64(hi_addr + (uint32_t)(i * 8), d);
+            xh[i] = (xh[i] + d) + mt;
+          }
+        } else {
+          // ---- hot slots: level L takes 2^(B-L) values; the slots of a level advance together, CH
+          // independent chains at a time; the product of the level's slots for value w is folded into
+          // the pair sums T as soon as the last chain group has contributed (all indices below are
+          // compile-time constants once the loops are unrolled) ----
+          double T[NB / 2];
+          static_for<0, B>([&](auto Lc) {
+            constexpr int L = decltype(Lc)::value;
+            constexpr int SL = LL::count(L), base = LL::base(L);
+            constexpr int NG = (SL + 2) / 3;        // chain groups of at most 3 slots, sizes as even as possible
+            constexpr int cnt = NB >> L;
+            double PL[NG > 1 ? cnt : 1];            // products across chain groups
+            double tmp = 0.0, prev = 0.0;
+            static_for<0, NG>([&](auto Gc) {
+              constexpr int gi = decltype(Gc)::value;
+              constexpr int t0 = gi * (SL / NG) + (gi < SL % NG ? gi : SL % NG);
+              constexpr int CH = SL / NG + (gi < SL % NG ? 1 : 0);
+              double v[CH], m[CH][LB];
 #pragma unroll
               for (int t = 0; t < CH; ++t) {
-                if (K == B - 1) v[t] = fma(sg_top, m[t][K], v[t]);
-                else if (((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
-                else v[t] -= m[t][K];
+                const int i = base + t0 + t;
+#pragma unroll
+                for (int qq = (L & ~1); qq < LB; qq += 2)       // only columns >= L flip inside this level
+                  lds_f64x2(low_addr + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
+                double d;
+                lds_f64(hi_addr + (uint32_t)(i * 8), d);
+                v[t] = xh[i] + d;
               }
-              double pr = v[0];
 #pragma unroll
-              for (int t = 1; t < CH; ++t) pr *= v[t];
-              PL[off + w] = (t0 == 0) ? pr : PL[off + w] * pr;
-            }
+              for (int w = 0; w < cnt; ++w) {
+                if (w > 0) {
+                  const int u = w << L;
+                  const int K = ctz_c(u);
 #pragma unroll
-            for (int t = 0; t < CH; ++t) xh[L * S + t0 + t] = v[t];
+                  for (int t = 0; t < CH; ++t) {
+                    if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
+                    else v[t] -= m[t][K];
+                  }
+                }
+                double pr = v[0];
+#pragma unroll
+                for (int t = 1; t < CH; ++t) pr *= v[t];
+                if constexpr (NG > 1) {
+                  if (gi > 0) pr *= PL[w];
+                  if (gi < NG - 1) { PL[w] = pr; continue; }
+                }
+                // fold: level 0 pairs up with alternating signs, level L combines the sums below it
+                if (L == 0) {
+                  if ((w & 1) == 0) prev = pr; else T[w >> 1] = prev - pr;
+                } else {
+                  if ((w & 1) == 0) tmp = pr * T[w]; else T[w >> 1] = fma(pr, T[w], tmp);
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < CH; ++t) xh[base + t0 + t] = v[t];
+            });
+          });
+          if (active) {                               // idle lanes of a last, partial round repeat lane 0's tile
+            myX[(size_t)NC * THREADS] = fma(Q, T[0], myX[(size_t)NC * THREADS]);
+            reinterpret_cast<unsigned long long*>(myX)[(size_t)(NC + 1) * THREADS] += 1ull;
           }
         }
-        // signed pair sums bottom-up: E_0[w] = PL0[2w] - PL0[2w+1],
-        // E_L[w] = PL_L[2w] E_{L-1}[2w] + PL_L[2w+1] E_{L-1}[2w+1]
-        double E[NB / 2];
-#pragma unroll
-        for (int w = 0; w < NB / 2; ++w) E[w] = PL[2 * w] - PL[2 * w + 1];          // off(0) = 0
-#pragma unroll
-        for (int L = 1; L < B; ++L) {
-          const int off = 2 * NB - 2 * (NB >> L);
-#pragma unroll
-          for (int w = 0; w < (NB >> (L + 1)); ++w)
-            E[w] = fma(PL[off + 2 * w], E[2 * w], PL[off + 2 * w + 1] * E[2 * w + 1]);
-        }
-        tile_acc = fma(Q, E[0], tile_acc);
-        tile_vis += 1;
       }
+      __syncwarp();
     }
-    if (active) { acc += tile_acc; vis += tile_vis; }
-    __syncwarp();
+
+    const double acc = warp_sum(myX[(size_t)NC * THREADS]);
+    unsigned long long vis = reinterpret_cast<unsigned long long*>(myX)[(size_t)(NC + 1) * THREADS];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vis += __shfl_down_sync(0xffffffffu, vis, o);
+    if (lane == 0) { const unsigned int ch = s_chunk[wib]; a.partials[ch] = acc; a.visited[ch] = vis; }
   }
 
-  acc = warp_sum(acc);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) vis += __shfl_down_sync(0xffffffffu, vis, o);
-  if (lane == 0) { warp_part[wib] = acc; warp_vis[wib] = vis; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double v = 0.0;
-    unsigned long long cnt = 0;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) { v += warp_part[w]; cnt += warp_vis[w]; }
-    a.partials[blockIdx.x] = v;
-    a.visited[blockIdx.x] = cnt;
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(&a.queue[1], 1u) == gridDim.x * WARPS - 1) {   // nobody will touch the counters any more
+      a.queue[0] = 0u;
+      a.queue[1] = 0u;
+      __threadfence();
+    }
   }
 }
 

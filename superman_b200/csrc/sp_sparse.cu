@@ -23,17 +23,19 @@ SPB_DECL(0) SPB_DECL(1) SPB_DECL(2) SPB_DECL(3) SPB_DECL(4) SPB_DECL(5) SPB_DECL
 }
 
 extern "C" {
-int spb_level_launch_b3_s0(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
-int spb_level_launch_b3_s1(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
-int spb_level_launch_b4_s0(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
-int spb_level_launch_b4_s1(int S, int R, cudaStream_t st, const spb::LevelArgs* a, unsigned blocks, size_t smem);
+// a->partials == NULL: no launch, *blocks_out = resident blocks per SM (and the kernel is loaded)
+int spb_level_launch_b3_s0(int S0, int S, cudaStream_t st, const spb::LevelArgs* a, int sm_count, size_t smem, unsigned* blocks_out);
+int spb_level_launch_b3_s1(int S0, int S, cudaStream_t st, const spb::LevelArgs* a, int sm_count, size_t smem, unsigned* blocks_out);
+int spb_level_launch_b4_s0(int S0, int S, cudaStream_t st, const spb::LevelArgs* a, int sm_count, size_t smem, unsigned* blocks_out);
+int spb_level_launch_b4_s1(int S0, int S, cudaStream_t st, const spb::LevelArgs* a, int sm_count, size_t smem, unsigned* blocks_out);
 }
 
 using namespace spb;
 
-static int level_launch(int B, int S, int R, int skip, cudaStream_t st, const LevelArgs* a, unsigned blocks, size_t smem) {
-  if (B == 3) return skip ? spb_level_launch_b3_s1(S, R, st, a, blocks, smem) : spb_level_launch_b3_s0(S, R, st, a, blocks, smem);
-  if (B == 4) return skip ? spb_level_launch_b4_s1(S, R, st, a, blocks, smem) : spb_level_launch_b4_s0(S, R, st, a, blocks, smem);
+static int level_launch(int B, int S0, int S, int skip, cudaStream_t st, const LevelArgs* a, int sm_count, size_t smem,
+                        unsigned* blocks_out) {
+  if (B == 3) return skip ? spb_level_launch_b3_s1(S0, S, st, a, sm_count, smem, blocks_out) : spb_level_launch_b3_s0(S0, S, st, a, sm_count, smem, blocks_out);
+  if (B == 4) return skip ? spb_level_launch_b4_s1(S0, S, st, a, sm_count, smem, blocks_out) : spb_level_launch_b4_s0(S0, S, st, a, sm_count, smem, blocks_out);
   return SPD_ELIMIT;
 }
 
@@ -58,7 +60,7 @@ struct spd_sparse_plan {
   double* d_xbase = nullptr;
   std::vector<int> level;      // sorted ascending: level[j] of the row now at position j
   // LevelRyser image (level_reg.cuh); lvB == 0 when the matrix does not fit its slots
-  int lvB = 0, lvS = 0, lvR = 0, NC = 0, NCP = 0, HSP = 0;
+  int lvB = 0, lvS0 = 0, lvS = 0, lvR = 0, NC = 0, NCP = 0, HSP = 0;
   double lv_cost = 1e300, hc_cost = 1e300;
   double *d_colT_hot = nullptr, *d_lowR = nullptr, *d_dcold = nullptr, *d_xb_hot = nullptr, *d_xb_cold = nullptr;
   int* d_cold_start = nullptr;
@@ -80,14 +82,16 @@ static double hotcold_cost(const spd_sparse_plan* p, int B) {
   return 2.0 * H + (2.0 * (n - H) + 8.0) / (double)(1 << B);
 }
 
-// Packs the rows into the LevelRyser layout for (B, S): S register slots per level < B, the other
-// rows cold, sorted by level.  lvl[] / dmat_t / xbase are in the ORIGINAL row order.  Returns
+// Packs the rows into the LevelRyser layout for (B, S0, S): S0 register slots for level 0, S for each other
+// level < B, the other rows cold, sorted by level.  lvl[] / dmat_t / xbase are in the ORIGINAL row order.  Returns
 // false when some level has more rows than the slots at or below it can take.
-static bool level_pack(int n, int B, int S, int R, const std::vector<int>& lvl, const double* dmat_t,
+static bool level_pack(int n, int B, int S0, int S, int R, const std::vector<int>& lvl, const double* dmat_t,
                        const double* xbase, std::vector<double>& colT_hot, std::vector<double>& lowR,
                        std::vector<double>& dcold, std::vector<double>& xb_hot, std::vector<double>& xb_cold,
                        std::vector<int>& cold_start, int* NC_out, double* cost_out) {
-  const int HS = B * S, HT = HS + R, HSP = HT + (HT & 1), LB = B + (B & 1);
+  const int HS = S0 + (B - 1) * S, HT = HS + R, HSP = HT + (HT & 1), LB = B + (B & 1);
+  auto base = [&](int L) { return L == 0 ? 0 : S0 + (L - 1) * S; };
+  auto count = [&](int L) { return L == 0 ? S0 : S; };
   std::vector<int> slot_row(HT, -1);
   std::vector<int> order(n);
   for (int j = 0; j < n; ++j) order[j] = j;
@@ -99,8 +103,8 @@ static bool level_pack(int n, int B, int S, int R, const std::vector<int>& lvl, 
     if (lvl[j] >= B) { cold.push_back(j); continue; }
     int placed = -1;
     for (int L = lvl[j]; L >= 0 && placed < 0; --L)
-      for (int t = 0; t < S; ++t)
-        if (slot_row[L * S + t] < 0) { placed = L * S + t; break; }
+      for (int t = 0; t < count(L); ++t)
+        if (slot_row[base(L) + t] < 0) { placed = base(L) + t; break; }
     if (placed < 0) return false;
     slot_row[placed] = j;
   }
@@ -139,10 +143,10 @@ static bool level_pack(int n, int B, int S, int R, const std::vector<int>& lvl, 
   }
   // cost per index: hot slots + recombination + expected cold refresh (x3: it runs from shared memory)
   double hot = 0.0;
-  for (int L = 0; L < B; ++L) hot += (double)S * 2.0 * (double)(1 << (B - L));
+  for (int L = 0; L < B; ++L) hot += (double)count(L) * 2.0 * (double)(1 << (B - L));
   double coldc = 0.0, w = 0.5;
   for (int z = 0; z < 16 && B + z <= n; ++z, w *= 0.5) coldc += w * 3.0 * (double)cold_start[(z + 1 <= n - B + 1) ? z + 1 : n - B + 1];
-  const double per_block = hot + 2.0 * R + (double)((2 << B) - 2) + (double)(1 << B) + coldc;
+  const double per_block = hot + 2.0 * R + (double)((1 << B) + B) + coldc;
   *cost_out = per_block / (double)(1 << B);
   *NC_out = NC;
   return true;
@@ -214,27 +218,45 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
     const unsigned long long max_blocks = 1ull << 20;
     bool first = true;
     while (tiles_left) {
+      if (use_level) {
+        // persistent grid: every warp pulls chunks of tiles_per_warp tiles from the lane's atomic queue and
+        // leaves one partial sum (and one visited count) per chunk; at most 2^20 chunks per launch
+        unsigned long long chunks = (tiles_left + (unsigned)tiles_per_warp - 1) / (unsigned)tiles_per_warp;
+        if (chunks > max_blocks) chunks = max_blocks;
+        unsigned long long nt = chunks * (unsigned)tiles_per_warp;
+        if (nt > tiles_left) nt = tiles_left;
+        if ((rc = lane_reserve_partials(&L, (size_t)chunks + 4096)) != SPD_OK) return rc;
+        if ((rc = lane_reserve_aux(&L, (size_t)chunks)) != SPD_OK) return rc;
+        LevelArgs la;
+        la.colT_hot = p->d_colT_hot; la.lowR = p->d_lowR; la.dcold = p->d_dcold;
+        la.xb_hot = p->d_xb_hot; la.xb_cold = p->d_xb_cold; la.cold_start = p->d_cold_start;
+        la.partials = L.d_partials; la.visited = L.d_aux; la.queue = L.d_queue;
+        la.tile_first = tile; la.n_tiles = nt; la.n_chunks = (unsigned)chunks;
+        la.n = n; la.NC = p->NC; la.NCP = p->NCP; la.HSP = p->HSP; la.c = c; la.tiles_per_warp = tiles_per_warp;
+        const int HS = p->lvS0 + (p->lvB - 1) * p->lvS, LBv = p->lvB + (p->lvB & 1);
+        const size_t smem = level_smem_bytes(n, p->lvB, HS, p->HSP, LBv, p->NC, p->NCP, c, SPB_REG_THREADS);
+        if (smem > 220 * 1024) { set_error("level engine needs %zu B of shared memory", smem); return SPD_ELIMIT; }
+        SPB_CUDA(cudaMemsetAsync(L.d_queue, 0, 2 * sizeof(unsigned int), L.stream));
+        unsigned nb = 0;
+        rc = level_launch(p->lvB, p->lvS0, p->lvS, p->skip, L.stream, &la, L.sm_count, smem, &nb);
+        if (rc != SPD_OK) { if (rc == SPD_ELIMIT) set_error("no level kernel for B=%d S0=%d S=%d", p->lvB, p->lvS0, p->lvS); return rc; }
+        SPB_CUDA(cudaGetLastError());
+        ++launches;
+        if ((rc = launch_reduce(L, L.d_partials, (size_t)chunks, L.d_result, 0, !first)) != SPD_OK) return rc;
+        if ((rc = launch_reduce_u64(L, L.d_aux, (size_t)chunks, L.d_result, 1, !first)) != SPD_OK) return rc;
+        launches += 2;
+        first = false;
+        have_visited = true;
+        tile += nt; tiles_left -= nt;
+        continue;
+      }
       unsigned long long blocks = (tiles_left + tiles_per_block - 1) / tiles_per_block;
       if (blocks > max_blocks) blocks = max_blocks;
       unsigned long long nt = blocks * tiles_per_block;
       if (nt > tiles_left) nt = tiles_left;
       if ((rc = lane_reserve_partials(&L, (size_t)blocks + 4096)) != SPD_OK) return rc;
       if ((rc = lane_reserve_aux(&L, (size_t)blocks)) != SPD_OK) return rc;
-      if (use_level) {
-        LevelArgs la;
-        la.colT_hot = p->d_colT_hot; la.lowR = p->d_lowR; la.dcold = p->d_dcold;
-        la.xb_hot = p->d_xb_hot; la.xb_cold = p->d_xb_cold; la.cold_start = p->d_cold_start;
-        la.partials = L.d_partials; la.visited = L.d_aux;
-        la.tile_first = tile; la.n_tiles = nt;
-        la.n = n; la.NC = p->NC; la.NCP = p->NCP; la.HSP = p->HSP; la.c = c; la.tiles_per_warp = tiles_per_warp;
-        const int HS = p->lvB * p->lvS, LBv = p->lvB + (p->lvB & 1);
-        const size_t dbl = (size_t)(n - 1) * p->HSP + (size_t)HS * LBv + (size_t)(n - 1) * p->NCP + p->HSP + p->NCP +
-                           (size_t)p->NC * SPB_REG_THREADS + (size_t)(c - B + 2) * SPB_REG_THREADS;
-        const size_t smem = dbl * sizeof(double) + (size_t)((n - B + 2) + (c - B + 1) + p->NC) * sizeof(int);
-        if (smem > 220 * 1024) { set_error("level engine needs %zu B of shared memory", smem); return SPD_ELIMIT; }
-        rc = level_launch(p->lvB, p->lvS, p->lvR, p->skip, L.stream, &la, (unsigned)blocks, smem);
-        if (rc != SPD_OK) { if (rc == SPD_ELIMIT) set_error("no level kernel for B=%d S=%d R=%d", p->lvB, p->lvS, p->lvR); return rc; }
-      } else {
+      {
         SparseArgs a;
         a.mat_t = p->d_mat_t; a.xbase = p->d_xbase;
         a.partials = L.d_partials; a.visited = L.d_aux;
@@ -330,34 +352,37 @@ int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase
     static const int s_opts[6] = {1, 2, 3, 4, 6, 8};
     std::vector<double> bh, bl, bd, bxh, bxc;
     std::vector<int> bcs;
-    const int forceB = env_int("SP_SPARSE_LOWCOLS", 0), forceS = env_int("SP_LEVEL_SLOTS", 0);
+    const int forceB = env_int("SP_SPARSE_LOWCOLS", 0), forceS = env_int("SP_LEVEL_SLOTS", 0), forceS0 = env_int("SP_LEVEL_SLOTS0", 0);
     for (int B = 3; B <= 4; ++B) {
       if (B + 2 > n - 1) continue;
       if (forceB && forceB != B) continue;
-      const int forceR = env_int("SP_LEVEL_REGCOLD", -1);
       for (int si = 0; si < 6; ++si) {
-        if (forceS && forceS != s_opts[si]) continue;
+        const int S = s_opts[si];
+        if (forceS && forceS != S) continue;
         bool fits = false;
-        for (int R = 0; R <= 8; R += 4) {
-          if (forceR >= 0 && forceR != R) continue;
+        // level 0 (2^B values per block, the most expensive level) may have up to two slots fewer
+        for (int S0 = std::max(1, S - 2); S0 <= S; ++S0) {
+          if (forceS0 && forceS0 != S0) continue;
+          const int R = level_regcold(B, S0, S, p->skip != 0);
           std::vector<double> h, l, d, xh, xc;
           std::vector<int> cs;
           int NC = 0;
           double cost = 0;
-          if (!level_pack(n, B, s_opts[si], R, lvl, dmat_t, xbase, h, l, d, xh, xc, cs, &NC, &cost)) break;
+          if (!level_pack(n, B, S0, S, R, lvl, dmat_t, xbase, h, l, d, xh, xc, cs, &NC, &cost)) continue;
           fits = true;
           cost *= 1.15;
-          if (B * s_opts[si] + R > 16 || (B == 4 && s_opts[si] == 4)) cost *= 1.1;      // 3 instead of 4 blocks per SM
+          if (level_minblocks(B, S0, S, p->skip != 0) < 4) cost *= 1.1;      // 3 instead of 4 blocks per SM
           if (cost < p->lv_cost) {
-            p->lv_cost = cost; p->lvB = B; p->lvS = s_opts[si]; p->lvR = R; p->NC = NC;
+            p->lv_cost = cost; p->lvB = B; p->lvS0 = S0; p->lvS = S; p->lvR = R; p->NC = NC;
             bh.swap(h); bl.swap(l); bd.swap(d); bxh.swap(xh); bxc.swap(xc); bcs.swap(cs);
           }
+          break;   // more level-0 slots for the same S only cost more
         }
         if (fits) break;   // a larger S for the same B only costs more
       }
     }
     if (p->lvB && (engine == 2 || p->lv_cost < p->hc_cost || n > SPB_SPARSE_NMAX)) {
-      const int HT = p->lvB * p->lvS + p->lvR;
+      const int HT = p->lvS0 + (p->lvB - 1) * p->lvS + p->lvR;
       p->HSP = HT + (HT & 1);
       p->NCP = (int)bxc.size();
       auto up = [&](const void* src, size_t bytes, void** dst) -> int {

@@ -12,7 +12,7 @@ namespace spb {
 
 template <int N, int B, bool SKIP>
 static int launch_sparse(cudaStream_t st, const SparseArgs& a, unsigned blocks) {
-  constexpr int MB = (B == 4) ? (N <= 30 ? 4 : 3) : (N <= 36 ? 4 : 3);
+  constexpr int MB = (B == 4) ? (N <= (SKIP ? 28 : 30) ? 4 : 3) : (N <= 36 ? 4 : 3);
   sparse_reg_kernel<N, B, SPB_REG_THREADS, MB, SKIP><<<blocks, SPB_REG_THREADS, 0, st>>>(a);
   return SPD_OK;
 }

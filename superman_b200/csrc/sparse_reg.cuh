@@ -49,6 +49,9 @@ sparse_reg_kernel(const SparseArgs a) {
   __shared__ double warp_part[WARPS];
   __shared__ unsigned long long warp_vis[WARPS];
   __shared__ unsigned long long queue[WARPS][64];
+  __shared__ unsigned long long s_cand[WARPS][2];   // the warp's next candidate tile and the end of its range
+  __shared__ double s_acc[THREADS];            // per-thread running sum and evaluated-block count: kept out of
+  __shared__ unsigned int s_vis[THREADS];      // the register file, which X and the running products fill
   // staging: consecutive threads write consecutive shared-memory words in both images (no bank
   // conflicts); the low-column image is gathered from global memory instead
   for (int e = threadIdx.x; e < N * N; e += THREADS) sm[L::COLT + (e / N) * NP + (e % N)] = a.mat_t[e];
@@ -64,16 +67,22 @@ sparse_reg_kernel(const SparseArgs a) {
   const int c = a.c;
   const int Hg = ((a.H + G - 1) / G) * G;
 
-  const unsigned long long wg = (unsigned long long)blockIdx.x * WARPS + wib;
-  unsigned long long cand = wg * (unsigned long long)a.tiles_per_warp;
-  unsigned long long cand_hi = cand + (unsigned long long)a.tiles_per_warp;
-  if (cand_hi > a.n_tiles) cand_hi = a.n_tiles;
+  if (lane == 0) {
+    const unsigned long long wg = (unsigned long long)blockIdx.x * WARPS + wib;
+    const unsigned long long c0 = wg * (unsigned long long)a.tiles_per_warp;
+    const unsigned long long c1 = c0 + (unsigned long long)a.tiles_per_warp;
+    s_cand[wib][0] = c0;
+    s_cand[wib][1] = c1 > a.n_tiles ? a.n_tiles : c1;
+  }
+  __syncwarp();
 
-  double acc = 0.0;
-  unsigned long long vis = 0;
+  s_acc[threadIdx.x] = 0.0;
+  s_vis[threadIdx.x] = 0u;
   int q = 0;   // live tiles waiting in queue[wib]
   for (;;) {
     // ---- refill: test 32 candidate tiles per trip until a full warp of survivors is queued ----
+    unsigned long long cand = s_cand[wib][0];
+    const unsigned long long cand_hi = s_cand[wib][1];
     while (q < 32 && cand < cand_hi) {
       const unsigned long long t = cand + lane;
       bool alive = t < cand_hi;
@@ -93,6 +102,7 @@ sparse_reg_kernel(const SparseArgs a) {
       cand += 32;
     }
     __syncwarp();
+    if (lane == 0) s_cand[wib][0] = cand;
     if (q == 0) break;
     const int take = q < 32 ? q : 32;
     const bool active = lane < take;
@@ -114,8 +124,6 @@ sparse_reg_kernel(const SparseArgs a) {
 #pragma unroll
       for (int j = 0; j < N; ++j) x[j] = fma(f, col[j], x[j]);
     }
-    double tile_acc = 0.0;
-    unsigned long long tile_vis = 0;
     const int nblk = 1 << (c - B);
     unsigned long long i0 = s;
 #pragma unroll 1
@@ -203,14 +211,16 @@ sparse_reg_kernel(const SparseArgs a) {
         double blk_sum = 0.0;
 #pragma unroll
         for (int u = 0; u < NB; u += 2) blk_sum += (P[u] - P[u + 1]);
-        tile_acc = fma(blk_sum, Q, tile_acc);
-        tile_vis += 1;
+        if (active) {                                   // inactive lanes run a placeholder tile
+          s_acc[threadIdx.x] = fma(blk_sum, Q, s_acc[threadIdx.x]);
+          s_vis[threadIdx.x] += 1u;
+        }
       }
     }
-    if (active) { acc += tile_acc; vis += tile_vis; }   // inactive lanes ran a placeholder tile
   }
 
-  acc = warp_sum(acc);
+  const double acc = warp_sum(s_acc[threadIdx.x]);
+  unsigned long long vis = s_vis[threadIdx.x];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vis += __shfl_down_sync(0xffffffffu, vis, o);
   if (lane == 0) { warp_part[wib] = acc; warp_vis[wib] = vis; }

@@ -1,4 +1,4 @@
-"""dev: LevelRyser parameter sweep (B, S, R through the SP_* environment knobs) on the config-3 matrix,
+"""dev: LevelRyser parameter sweep (B, S0, S through the SP_* environment knobs) on the config-3 matrix,
 next to the cost model's own choice.  Each configuration runs in a fresh process (the knobs are read
 at plan creation)."""
 import os, subprocess, sys
@@ -24,12 +24,12 @@ for _ in range(3):
 print("%%.3f ms  %%.12e" %% (best, v))
 ''' % R
 for B in (0, 3, 4):
-    for S in (0, 2, 3, 4, 6):
-        for Rc in (-1, 0, 4, 8):
-            if (B == 0) != (S == 0) or (B == 0) != (Rc == -1):
+    for S in (0, 3, 4, 6):
+        for S0 in (0, 1, 2, 3, 4):
+            if (B == 0) != (S == 0) or (B == 0) != (S0 == 0) or S0 > S or S0 < S - 2:
                 continue
             env = dict(os.environ)
             if B:
-                env.update(SP_SPARSE_LOWCOLS=str(B), SP_LEVEL_SLOTS=str(S), SP_LEVEL_REGCOLD=str(Rc), SP_SPARSE_ENGINE="2")
+                env.update(SP_SPARSE_LOWCOLS=str(B), SP_LEVEL_SLOTS=str(S), SP_LEVEL_SLOTS0=str(S0), SP_SPARSE_ENGINE="2")
             out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True).stdout.strip()
-            print("B=%d S=%d R=%d: %s" % (B, S, Rc, out), flush=True)
+            print("B=%d S0=%d S=%d: %s" % (B, S0, S, out), flush=True)
