@@ -50,6 +50,10 @@ typedef struct sp_stats {
   int path;                    /* SPD_PATH_* of the dominant kernel */
   int tile_log2;
   int error;                   /* SP_OK or SP_E* */
+  /* approximations: sum over all trials of (estimate * sq_scale)^2 and that scale, from which std_error
+   * is derived; `visited` counts the trials that reached the last step (the rest estimate 0) */
+  double sumsq_scaled;
+  double sq_scale;
 } sp_stats;
 
 const char *sp_last_error(void);
@@ -241,6 +245,17 @@ double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptr
 double sp_approx_trial_dense(const double *mat, int nov, int scaling, int scale_intervals, int scale_times,
                              unsigned long long seed, long long trial, int count, double *values,
                              sp_stats *stats);
+/* The same with each trial's record (count <= 65536, one launch): values[i] the estimate (0 for a dead
+ * end), steps[i] the steps completed (== nov when the trial reached the last step) and partial[i] the
+ * running product at that point.  On patterns where almost every trial dies (the 36 x 36 grid of BASELINE
+ * config 5) the estimates alone compare 0 with 0; steps and partial products do not.  Any output may be NULL. */
+double sp_approx_trace_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows, int nov, int nnz,
+                              int scaling, int scale_intervals, int scale_times, unsigned long long seed,
+                              long long trial, int count, double *values, int *steps, double *partial,
+                              sp_stats *stats);
+double sp_approx_trace_dense(const double *mat, int nov, int scaling, int scale_intervals, int scale_times,
+                             unsigned long long seed, long long trial, int count, double *values, int *steps,
+                             double *partial, sp_stats *stats);
 
 /* ---------------------------------------------------------------------------------------------
  * The reference's Python / MATLAB shim on the GPU engine (interface_connector.c:61-231,

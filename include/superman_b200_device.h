@@ -33,7 +33,8 @@ extern "C" {
 typedef struct spd_run_info {
   double kernel_ms;         /* CUDA-event time on the plan's stream around this run's launches */
   unsigned long long units; /* Gray indices covered (exact) or trials executed (approximations) */
-  unsigned long long visited; /* Skipper: indices actually evaluated; otherwise == units */
+  unsigned long long visited; /* Skipper: indices actually evaluated; approximations: trials that reached the
+                               * last step (the others hit a dead end and estimate 0); otherwise == units */
   int launches;             /* kernels launched by this run */
   int path;                 /* SPD_PATH_* of the dominant kernel */
   int tile_log2;            /* log2 of the per-thread tile (exact register paths), else 0 */
@@ -113,6 +114,11 @@ int  spd_approx_plan_run(spd_approx_plan *plan, unsigned long long lo, unsigned 
 int  spd_approx_plan_launch(spd_approx_plan *plan, unsigned long long lo, unsigned long long hi);
 int  spd_approx_plan_wait(spd_approx_plan *plan, double *sum, spd_run_info *info);
 int  spd_approx_plan_trial(spd_approx_plan *plan, unsigned long long trial, double *value);
+/* Trials [lo, hi) (at most 2^16) in one launch with their per-trial record: estimate[i] (0 for a dead end),
+ * steps[i] completed (== nov when the trial reached the last step) and the running product at that point.
+ * Any of the three output arrays may be NULL.  For parity tests against the oracle. */
+int  spd_approx_plan_trace(spd_approx_plan *plan, unsigned long long lo, unsigned long long hi,
+                           double *estimate, int *steps, double *partial);
 
 #ifdef __cplusplus
 }

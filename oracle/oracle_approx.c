@@ -68,15 +68,21 @@ static int min_degree_row(const int *rptrs, const int *cols, int nov, const unsi
   return row;
 }
 
-double orc_rasmussen_trial(const int *rptrs, const int *cols, int nov, u64 seed, u64 trial) {
+/* Every trial function also reports how far the trial got: *steps_out = steps completed (nov when it
+ * reached the last step) and *partial_out = the running product at that point; the estimate is 0 for a
+ * dead end and the full product otherwise.  (The reference only returns the estimate; the record lets a
+ * parity test say something on patterns where almost every trial dies.) */
+double orc_rasmussen_trace(const int *rptrs, const int *cols, int nov, u64 seed, u64 trial, int *steps_out,
+                           double *partial_out) {
   const int words = (nov + 31) / 32;
   unsigned *rowx = (unsigned *)calloc((size_t)words, sizeof(unsigned));
   unsigned *colx = (unsigned *)calloc((size_t)words, sizeof(unsigned));
   double perm = 1.0;
-  for (int step = 0; step < nov; ++step) {
+  int step = 0, dead = 0;
+  for (; step < nov; ++step) {
     int deg;
     const int row = min_degree_row(rptrs, cols, nov, rowx, colx, &deg);
-    if (deg == 0) { perm = 0.0; break; }
+    if (deg == 0) { dead = 1; break; }
     perm *= deg;
     int want = (int)(((uint64_t)draw_of(seed, trial, step) * (uint64_t)deg) >> 32);
     int col = -1;
@@ -90,14 +96,20 @@ double orc_rasmussen_trial(const int *rptrs, const int *cols, int nov, u64 seed,
     SETBIT(rowx, row);
   }
   free(rowx); free(colx);
-  return perm;
+  if (steps_out) *steps_out = step;
+  if (partial_out) *partial_out = perm;
+  return dead ? 0.0 : perm;
+}
+
+double orc_rasmussen_trial(const int *rptrs, const int *cols, int nov, u64 seed, u64 trial) {
+  return orc_rasmussen_trace(rptrs, cols, nov, seed, trial, NULL, NULL);
 }
 
 /* rvals / cvals == NULL: pattern-only sweeps with float sums (sparse kernel);
  * otherwise sums weighted by the entries, in double (dense kernel). */
-double orc_scaling_trial(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
+double orc_scaling_trace(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
                          const double *rvals, const double *cvals, int nov, int scale_intervals,
-                         int scale_times, u64 seed, u64 trial) {
+                         int scale_times, u64 seed, u64 trial, int *steps_out, double *partial_out) {
   const int words = (nov + 31) / 32;
   unsigned *rowx = (unsigned *)calloc((size_t)words, sizeof(unsigned));
   unsigned *colx = (unsigned *)calloc((size_t)words, sizeof(unsigned));
@@ -106,11 +118,11 @@ double orc_scaling_trial(const int *rptrs, const int *cols, const int *cptrs, co
   for (int i = 0; i < nov; ++i) { d_r[i] = 1.0f; d_c[i] = 1.0f; }
   const int weighted = (rvals != NULL && cvals != NULL);
   double perm = 1.0;
-  for (int step = 0; step < nov; ++step) {
+  int step = 0, dead = 0;
+  for (; step < nov; ++step) {
     int deg;
     const int row = min_degree_row(rptrs, cols, nov, rowx, colx, &deg);
-    if (deg == 0) { perm = 0.0; break; }   /* the sum below would be 0: same outcome */
-    int dead = 0;
+    if (deg == 0) { dead = 1; break; }   /* the sum below would be 0: same outcome */
     if (step % scale_intervals == 0) {
       for (int k = 0; k < scale_times && !dead; ++k) {
         for (int j = 0; j < nov && !dead; ++j) {
@@ -143,12 +155,12 @@ double orc_scaling_trial(const int *rptrs, const int *cols, const int *cptrs, co
         }
       }
     }
-    if (dead) { perm = 0.0; break; }
+    if (dead) break;
     const float dr = d_r[row];
     double tot = 0.0;
     for (int t = rptrs[row]; t < rptrs[row + 1]; ++t)
       if (!TESTBIT(colx, cols[t])) tot += (double)(dr * d_c[cols[t]]);
-    if (tot == 0.0) { perm = 0.0; break; }
+    if (tot == 0.0) { dead = 1; break; }
     const double target = ((double)draw_of(seed, trial, step) + 1.0) * (1.0 / 4294967296.0) * tot;
     double run = 0.0;
     int col = -1;
@@ -159,12 +171,21 @@ double orc_scaling_trial(const int *rptrs, const int *cols, const int *cptrs, co
       run += s;
       if (target <= run) { col = c; perm /= (s / tot); break; }
     }
-    if (col < 0) { perm = 0.0; break; }
+    if (col < 0) { dead = 1; break; }
     SETBIT(colx, col);
     SETBIT(rowx, row);
   }
   free(rowx); free(colx); free(d_r); free(d_c);
-  return perm;
+  if (steps_out) *steps_out = step;
+  if (partial_out) *partial_out = perm;
+  return dead ? 0.0 : perm;
+}
+
+double orc_scaling_trial(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
+                         const double *rvals, const double *cvals, int nov, int scale_intervals,
+                         int scale_times, u64 seed, u64 trial) {
+  return orc_scaling_trace(rptrs, cols, cptrs, rows, rvals, cvals, nov, scale_intervals, scale_times, seed, trial, NULL,
+                           NULL);
 }
 
 /* mean over trials [lo, hi), sequential sum in trial order */

@@ -30,6 +30,8 @@ class SpStats(C.Structure):
         ("path", C.c_int),
         ("tile_log2", C.c_int),
         ("error", C.c_int),
+        ("sumsq_scaled", C.c_double),
+        ("sq_scale", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -104,6 +106,8 @@ _sig("sp_scaling_dense", C.c_double, [_dp, C.c_int, C.c_longlong, C.c_int, C.c_i
 _sig("sp_approx_trial_sparse", C.c_double, [_ip, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, _dp, _sp])
 
 _sig("sp_approx_trial_dense", C.c_double, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, _dp, _sp])
+_sig("sp_approx_trace_sparse", C.c_double, [_ip, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, _dp, _ip, _dp, _sp])
+_sig("sp_approx_trace_dense", C.c_double, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, _dp, _ip, _dp, _sp])
 _sig("sp_connect", None, [])
 _sig("read_calculate_return", C.c_double, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int])
 _sig("matlab_calculate_return_int", C.c_double, [_ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int])

@@ -15,7 +15,7 @@ __all__ = [
     "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
     "SpStats", "dense_ryser", "dense_ryser_range", "DenseHandle", "permanent_compressed",
     "sparse_ryser", "skipper", "sparse_ryser_range",
-    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense",
+    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense", "approx_trace_sparse", "approx_trace_dense",
     "gpu_perman64_rasmussen_sparse", "gpu_perman64_rasmussen_multigpucpu_chunks_sparse",
     "gpu_perman64_approximation_sparse", "gpu_perman64_approximation_multigpucpu_chunks_sparse",
     "gpu_perman64_rasmussen", "gpu_perman64_rasmussen_multigpucpu_chunks",
@@ -357,6 +357,32 @@ def approx_trials_dense(mat, nov, scaling=False, scale_intervals=4, scale_times=
                                   _ptr(out), C.byref(st))
     _check(v, st)
     return out
+
+
+def approx_trace_sparse(rptrs, cols, cptrs, rows, nov, nnz, scaling=False, scale_intervals=4, scale_times=5, seed=1,
+                        first=0, count=1):
+    """(estimates, steps completed, running product) of trials [first, first+count), one launch."""
+    rp, co, cp, ro = _iarr(rptrs), _iarr(cols), _iarr(cptrs), _iarr(rows)
+    out = np.zeros(count, dtype=np.float64)
+    steps = np.zeros(count, dtype=np.int32)
+    part = np.zeros(count, dtype=np.float64)
+    st = SpStats()
+    v = lib.sp_approx_trace_sparse(_iptr(rp), _iptr(co), _iptr(cp), _iptr(ro), nov, nnz, int(scaling), scale_intervals,
+                                   scale_times, seed, first, count, _ptr(out), _iptr(steps), _ptr(part), C.byref(st))
+    _check(v, st)
+    return out, steps, part
+
+
+def approx_trace_dense(mat, nov, scaling=False, scale_intervals=4, scale_times=5, seed=1, first=0, count=1):
+    a = _dmat(mat, nov)
+    out = np.zeros(count, dtype=np.float64)
+    steps = np.zeros(count, dtype=np.int32)
+    part = np.zeros(count, dtype=np.float64)
+    st = SpStats()
+    v = lib.sp_approx_trace_dense(_ptr(a), nov, int(scaling), scale_intervals, scale_times, seed, first, count,
+                                  _ptr(out), _iptr(steps), _ptr(part), C.byref(st))
+    _check(v, st)
+    return out, steps, part
 
 
 # ---- reference wrapper names (gpu_approximation_sparse.cu:455,497,608,663; _dense.cu:373,411,527,573)

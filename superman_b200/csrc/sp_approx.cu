@@ -57,6 +57,8 @@ struct ApproxArgs {
   const unsigned short* ell_cols;      // [nov * W] columns of row i, CRS order, padded with nov
   double* partial_sum;                 // per block: sum of estimates
   double* partial_sq;                  // per block: sum of (estimate * sq_scale)^2
+  unsigned long long* partial_alive;   // per block: trials that reached the last step
+  double* trace;                       // tests only (else nullptr): per trial {steps completed, running product}
   unsigned long long trial_lo, trial_hi;
   unsigned long long seed;
   double sq_scale;
@@ -91,17 +93,18 @@ approx_kernel(const ApproxArgs a) {
   off += 2 * (size_t)nov * W * sizeof(unsigned short);
   off = (off + 15) & ~(size_t)15;
   // per-warp state
-  const int deg_bytes = (nov + 15) & ~15;
+  const int deg_bytes = (2 * nov + 15) & ~15;   // 16-bit degrees: a dense row may hold more than 255 entries
   const size_t warp_bytes = (size_t)deg_bytes + 2 * (size_t)words * 4 + (a.scaling ? 2 * (size_t)(nov + 1) * 4 : 0);
   const size_t warp_stride = (warp_bytes + 15) & ~(size_t)15;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smraw + off + wib * warp_stride;
-  unsigned char* deg = wbase;
+  unsigned short* deg = reinterpret_cast<unsigned short*>(wbase);
   unsigned* rowx = reinterpret_cast<unsigned*>(wbase + deg_bytes);
   unsigned* colx = rowx + words;
   float* d_r = reinterpret_cast<float*>(colx + words);
   float* d_c = d_r + (nov + 1);                 // d_r[nov] = d_c[nov] = 0: the ELL padding
   __shared__ double blk_sum[APX_WARPS], blk_sq[APX_WARPS];
+  __shared__ unsigned long long blk_alive[APX_WARPS];
 
   for (int e = threadIdx.x; e <= nov; e += APX_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
   for (int e = threadIdx.x; e < nnz; e += APX_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
@@ -112,11 +115,12 @@ approx_kernel(const ApproxArgs a) {
   const unsigned long long total_warps = (unsigned long long)gridDim.x * APX_WARPS;
   const unsigned long long wg = (unsigned long long)blockIdx.x * APX_WARPS + wib;
   double wsum = 0.0, wsq = 0.0;
+  unsigned long long walive = 0;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
 
   for (unsigned long long trial = a.trial_lo + wg; trial < a.trial_hi; trial += total_warps) {
     // ---- reset state ----
-    for (int r = lane; r < nov; r += 32) deg[r] = (unsigned char)min(255, s_rptrs[r + 1] - s_rptrs[r]);
+    for (int r = lane; r < nov; r += 32) deg[r] = (unsigned short)(s_rptrs[r + 1] - s_rptrs[r]);
     for (int w = lane; w < words; w += 32) { rowx[w] = 0u; colx[w] = 0u; }
     if (a.scaling) {
       for (int i = lane; i < nov; i += 32) { d_r[i] = 1.0f; d_c[i] = 1.0f; }
@@ -126,7 +130,8 @@ approx_kernel(const ApproxArgs a) {
     double perm = 1.0;
     uint32_t rnd[4];
     bool dead = false;
-    for (int step = 0; step < nov && !dead; ++step) {
+    int step = 0;                 // steps completed so far
+    for (; step < nov && !dead; ++step) {
       if ((step & 3) == 0)
         philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)(step >> 2), 0u, k0, k1, rnd);
       const int rw = step & 3;   // select, not index: keeps the four words in registers
@@ -138,7 +143,7 @@ approx_kernel(const ApproxArgs a) {
       best = __reduce_min_sync(0xffffffffu, best);
       const int row = (int)(best & 0xffffu);
       const int dmin = (int)(best >> 16);
-      if (dmin == 0) { perm = 0.0; dead = true; break; }
+      if (dmin == 0) { dead = true; break; }
       const int rb = s_rptrs[row], re = s_rptrs[row + 1];
       int col = -1;
       if (!a.scaling) {
@@ -218,13 +223,13 @@ approx_kernel(const ApproxArgs a) {
             if (__any_sync(0xffffffffu, zero)) { dead = true; break; }
             __syncwarp();
           }
-          if (dead) { perm = 0.0; break; }
+          if (dead) break;
         }
         // ---- column with probability d_r[row]*d_c[c] / sum (all lanes compute the same) ----
         const float dr = d_r[row];
         double tot = 0.0;
         for (int t = rb; t < re; ++t) tot += (double)(dr * d_c[s_cols[t]]);   // + 0 for extracted columns
-        if (tot == 0.0) { perm = 0.0; dead = true; break; }
+        if (tot == 0.0) { dead = true; break; }
         const double target = ((double)draw + 1.0) * (1.0 / 4294967296.0) * tot;
         double run = 0.0;
         for (int t = rb; t < re; ++t) {
@@ -233,7 +238,7 @@ approx_kernel(const ApproxArgs a) {
           run += s;
           if (target <= run) { col = cc; perm /= (s / tot); break; }
         }
-        if (col < 0) { perm = 0.0; dead = true; break; }   // cannot happen: run reaches tot exactly
+        if (col < 0) { dead = true; break; }   // cannot happen: run reaches tot exactly
       }
       // ---- extract row and column; lower the degree of the other rows of that column ----
       __syncwarp();
@@ -251,18 +256,27 @@ approx_kernel(const ApproxArgs a) {
       }
       __syncwarp();
     }
-    wsum += perm;
-    const double q = perm * a.sq_scale;
+    // a dead end estimates 0; `perm` is still the product over the `step` steps it completed
+    if (a.trace && lane == 0) {
+      a.trace[2 * (trial - a.trial_lo)] = (double)step;
+      a.trace[2 * (trial - a.trial_lo) + 1] = perm;
+    }
+    const double est = dead ? 0.0 : perm;
+    wsum += est;
+    const double q = est * a.sq_scale;
     wsq += q * q;
+    walive += dead ? 0ull : 1ull;
     __syncwarp();
   }
-  if (lane == 0) { blk_sum[wib] = wsum; blk_sq[wib] = wsq; }
+  if (lane == 0) { blk_sum[wib] = wsum; blk_sq[wib] = wsq; blk_alive[wib] = walive; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0, q = 0.0;
-    for (int w = 0; w < APX_WARPS; ++w) { s += blk_sum[w]; q += blk_sq[w]; }
+    unsigned long long al = 0;
+    for (int w = 0; w < APX_WARPS; ++w) { s += blk_sum[w]; q += blk_sq[w]; al += blk_alive[w]; }
     a.partial_sum[blockIdx.x] = s;
     a.partial_sq[blockIdx.x] = q;
+    a.partial_alive[blockIdx.x] = al;
   }
 }
 
@@ -283,6 +297,8 @@ struct SmallArgs {
   const double* wdense;                // [nov*nov] entry weights (scaled dense twin) or nullptr
   double* partial_sum;
   double* partial_sq;
+  unsigned long long* partial_alive;
+  double* trace;
   unsigned long long trial_lo, trial_hi;
   unsigned long long seed;
   double sq_scale;
@@ -302,6 +318,7 @@ approx_small_kernel(const SmallArgs a) {
   float* d_r = s_d + threadIdx.x;
   float* d_c = s_d + (size_t)nov * APS_THREADS + threadIdx.x;
   __shared__ double blk_sum[APS_THREADS / 32], blk_sq[APS_THREADS / 32];
+  __shared__ unsigned long long blk_alive[APS_THREADS / 32];
   for (int e = threadIdx.x; e < nov; e += APS_THREADS) { s_row[e] = a.rowmask[e]; s_col[e] = a.colmask[e]; }
   if (WEIGHTED) for (int e = threadIdx.x; e < nov * nov; e += APS_THREADS) s_w[e] = a.wdense[e];
   __syncthreads();
@@ -310,6 +327,7 @@ approx_small_kernel(const SmallArgs a) {
   unsigned long long trial = a.trial_lo + (unsigned long long)blockIdx.x * APS_THREADS + threadIdx.x;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
   double tsum = 0.0, tsq = 0.0, perm = 1.0;
+  unsigned long long talive = 0ull;
   unsigned long long rowx = 0ull, colx = 0ull;
   uint32_t rnd0 = 0, rnd1 = 0, rnd2 = 0, rnd3 = 0;
   int step = 0;
@@ -407,13 +425,18 @@ approx_small_kernel(const SmallArgs a) {
         }
       }
     }
-    if (dead) perm = 0.0;
-    else { rowx |= 1ull << row; colx |= 1ull << col; }
-    ++step;
+    if (!dead) { rowx |= 1ull << row; colx |= 1ull << col; ++step; }
     if (dead || step == nov) {
-      tsum += perm;
-      const double q = perm * a.sq_scale;
+      // a dead end estimates 0; `perm` is still the product over the `step` steps it completed
+      if (a.trace) {
+        a.trace[2 * (trial - a.trial_lo)] = (double)step;
+        a.trace[2 * (trial - a.trial_lo) + 1] = perm;
+      }
+      const double est = dead ? 0.0 : perm;
+      tsum += est;
+      const double q = est * a.sq_scale;
       tsq += q * q;
+      talive += dead ? 0ull : 1ull;
       trial += total;
       step = 0;
     }
@@ -422,14 +445,17 @@ approx_small_kernel(const SmallArgs a) {
   for (int o = 16; o > 0; o >>= 1) {
     tsum += __shfl_down_sync(0xffffffffu, tsum, o);
     tsq += __shfl_down_sync(0xffffffffu, tsq, o);
+    talive += __shfl_down_sync(0xffffffffu, talive, o);
   }
-  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; }
+  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; blk_alive[threadIdx.x >> 5] = talive; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double sv = 0.0, qv = 0.0;
-    for (int w = 0; w < APS_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; }
+    unsigned long long al = 0;
+    for (int w = 0; w < APS_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; al += blk_alive[w]; }
     a.partial_sum[blockIdx.x] = sv;
     a.partial_sq[blockIdx.x] = qv;
+    a.partial_alive[blockIdx.x] = al;
   }
 }
 
@@ -450,6 +476,8 @@ struct MidArgs {
   const int* rptrs; const int* cols; const int* cptrs; const int* rows;
   double* partial_sum;
   double* partial_sq;
+  unsigned long long* partial_alive;
+  double* trace;
   unsigned long long trial_lo, trial_hi;
   unsigned long long seed;
   double sq_scale;
@@ -481,6 +509,7 @@ rasmussen_mid_kernel(const MidArgs a) {
   unsigned* gmin = deg + (size_t)WD * APM_THREADS;
   unsigned* colx = gmin + (size_t)WG * APM_THREADS;
   __shared__ double blk_sum[APM_THREADS / 32], blk_sq[APM_THREADS / 32];
+  __shared__ unsigned long long blk_alive[APM_THREADS / 32];
 
   for (int e = threadIdx.x; e <= nov; e += APM_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
   for (int e = threadIdx.x; e < nnz; e += APM_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
@@ -511,6 +540,7 @@ rasmussen_mid_kernel(const MidArgs a) {
   unsigned long long trial = a.trial_lo + (unsigned long long)blockIdx.x * APM_THREADS + threadIdx.x;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
   double tsum = 0.0, tsq = 0.0, perm = 1.0;
+  unsigned long long talive = 0ull;
   uint32_t rnd0 = 0, rnd1 = 0, rnd2 = 0, rnd3 = 0;
   int step = 0;
 
@@ -583,12 +613,18 @@ rasmussen_mid_kernel(const MidArgs a) {
         if (d - 1u < cur) gmin[(g2 >> 2) * APM_THREADS] = (gw & ~(0xffu << (8 * (g2 & 3)))) | ((d - 1u) << (8 * (g2 & 3)));
       }
     }
-    if (dead) perm = 0.0;
-    ++step;
+    if (!dead) ++step;
     if (dead || step == nov) {
-      tsum += perm;
-      const double q = perm * a.sq_scale;
+      // a dead end estimates 0; `perm` is still the product over the `step` steps it completed
+      if (a.trace) {
+        a.trace[2 * (trial - a.trial_lo)] = (double)step;
+        a.trace[2 * (trial - a.trial_lo) + 1] = perm;
+      }
+      const double est = dead ? 0.0 : perm;
+      tsum += est;
+      const double q = est * a.sq_scale;
       tsq += q * q;
+      talive += dead ? 0ull : 1ull;
       trial += total;
       step = 0;
     }
@@ -597,14 +633,17 @@ rasmussen_mid_kernel(const MidArgs a) {
   for (int o = 16; o > 0; o >>= 1) {
     tsum += __shfl_down_sync(0xffffffffu, tsum, o);
     tsq += __shfl_down_sync(0xffffffffu, tsq, o);
+    talive += __shfl_down_sync(0xffffffffu, talive, o);
   }
-  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; }
+  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; blk_alive[threadIdx.x >> 5] = talive; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double sv = 0.0, qv = 0.0;
-    for (int w = 0; w < APM_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; }
+    unsigned long long al = 0;
+    for (int w = 0; w < APM_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; al += blk_alive[w]; }
     a.partial_sum[blockIdx.x] = sv;
     a.partial_sq[blockIdx.x] = qv;
+    a.partial_alive[blockIdx.x] = al;
   }
 }
 
@@ -635,6 +674,7 @@ struct spd_approx_plan {
   bool mid = false;
   size_t mid_smem = 0;
   int mid_blocks = 0;
+  double* d_trace = nullptr;                     // set by spd_approx_plan_trace for the duration of one run
   bool pending = false;
   spd_run_info info;
 };
@@ -671,10 +711,20 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
   if (nov < 1 || nov > 65535) { set_error("approximation supports 1 <= n <= 65535 (got %d)", nov); return SPD_ELIMIT; }
   if (nnz < 0) { set_error("negative nnz"); return SPD_EINVAL; }
   if (scaling && (scale_intervals < 1 || scale_times < 0)) { set_error("bad scaling parameters"); return SPD_EINVAL; }
+  // the pattern comes straight from the caller over the C ABI: one pass of validation, so that a bad index
+  // cannot become an out-of-range shift or shared-memory access in the kernels
+  if (rptrs[0] != 0 || cptrs[0] != 0 || rptrs[nov] != nnz || cptrs[nov] != nnz) {
+    set_error("CRS/CCS pointers do not span nnz = %d (rptrs[0]=%d rptrs[n]=%d cptrs[0]=%d cptrs[n]=%d)", nnz, rptrs[0],
+              rptrs[nov], cptrs[0], cptrs[nov]);
+    return SPD_EINVAL;
+  }
   for (int r = 0; r < nov; ++r) {
-    if (rptrs[r + 1] - rptrs[r] > 255 || rptrs[r + 1] < rptrs[r]) {
-      set_error("row %d has %d entries; the estimators keep row degrees in bytes (<= 255)", r, rptrs[r + 1] - rptrs[r]);
-      return SPD_ELIMIT;
+    if (rptrs[r + 1] < rptrs[r] || cptrs[r + 1] < cptrs[r]) { set_error("CRS/CCS pointers are not monotone at %d", r); return SPD_EINVAL; }
+  }
+  for (int t = 0; t < nnz; ++t) {
+    if (cols[t] < 0 || cols[t] >= nov || rows[t] < 0 || rows[t] >= nov) {
+      set_error("CRS/CCS index out of range at entry %d (col %d, row %d, n = %d)", t, cols[t], rows[t], nov);
+      return SPD_EINVAL;
     }
   }
   spd_approx_plan* p = new (std::nothrow) spd_approx_plan();
@@ -702,7 +752,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
   }
   off += 2 * (size_t)nov * p->ellW * sizeof(unsigned short);
   off = (off + 15) & ~(size_t)15;
-  const size_t deg_bytes = ((size_t)nov + 15) & ~(size_t)15;
+  const size_t deg_bytes = (2 * (size_t)nov + 15) & ~(size_t)15;     // 16-bit degrees
   size_t warp_bytes = deg_bytes + 2 * (size_t)words * 4 + (scaling ? 2 * (size_t)(nov + 1) * 4 : 0);
   warp_bytes = (warp_bytes + 15) & ~(size_t)15;
   p->smem_bytes = off + APX_WARPS * warp_bytes;
@@ -784,6 +834,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     if (rc != SPD_OK) return fail(rc);
     p->small = true;
     if ((rc = lane_reserve_partials(&L, (size_t)2 * p->small_blocks + 16)) != SPD_OK) return fail(rc);
+    if ((rc = lane_reserve_aux(&L, (size_t)p->small_blocks + 16)) != SPD_OK) return fail(rc);
   }
   // ---- thread-per-trial Rasmussen for nov > 64 when the per-thread state fits shared memory ----
   int maxdeg = 0;
@@ -801,6 +852,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
         p->mid = true;
         p->mid_blocks = per * L.sm_count;
         if ((rc = lane_reserve_partials(&L, (size_t)2 * p->mid_blocks + 16)) != SPD_OK) return fail(rc);
+        if ((rc = lane_reserve_aux(&L, (size_t)p->mid_blocks + 16)) != SPD_OK) return fail(rc);
       } else {
         (void)cudaGetLastError();
       }
@@ -811,6 +863,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
   if (e != cudaSuccess || per_sm < 1) { set_error("approx kernel does not fit on an SM: %s", cudaGetErrorString(e)); return fail(SPD_ECUDA); }
   p->blocks = per_sm * L.sm_count;     // persistent grid: resident blocks x SM count
   if ((rc = lane_reserve_partials(&L, (size_t)2 * p->blocks + 16)) != SPD_OK) return fail(rc);
+  if ((rc = lane_reserve_aux(&L, (size_t)p->blocks + 16)) != SPD_OK) return fail(rc);
   *out = p;
   return SPD_OK;
 }
@@ -837,7 +890,7 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
     if (need < (unsigned long long)blocks) blocks = (int)(need ? need : 1);
     SmallArgs sa;
     sa.rowmask = p->d_rowmask; sa.colmask = p->d_colmask; sa.wdense = p->d_wdense;
-    sa.partial_sum = L.d_partials; sa.partial_sq = L.d_partials + blocks;
+    sa.partial_sum = L.d_partials; sa.partial_sq = L.d_partials + blocks; sa.partial_alive = L.d_aux; sa.trace = p->d_trace;
     sa.trial_lo = lo; sa.trial_hi = hi; sa.seed = p->seed; sa.sq_scale = p->sq_scale;
     sa.nov = p->nov; sa.scaling = p->scaling; sa.scale_intervals = p->y; sa.scale_times = p->z;
     SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
@@ -848,9 +901,10 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
     int rc2;
     if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
     if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc2;
-    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    if ((rc2 = launch_reduce_u64(L, L.d_aux, (size_t)blocks, L.d_result, 2, false)) != SPD_OK) return rc2;
+    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 3 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
     SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
-    p->info.launches = 3;
+    p->info.launches = 4;
     p->pending = true;
     return SPD_OK;
   }
@@ -860,7 +914,7 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
     if (need < (unsigned long long)blocks) blocks = (int)(need ? need : 1);
     MidArgs ma;
     ma.rptrs = p->d_rptrs; ma.cols = p->d_cols; ma.cptrs = p->d_cptrs; ma.rows = p->d_rows;
-    ma.partial_sum = L.d_partials; ma.partial_sq = L.d_partials + blocks;
+    ma.partial_sum = L.d_partials; ma.partial_sq = L.d_partials + blocks; ma.partial_alive = L.d_aux; ma.trace = p->d_trace;
     ma.trial_lo = lo; ma.trial_hi = hi; ma.seed = p->seed; ma.sq_scale = p->sq_scale;
     ma.nov = p->nov; ma.nnz = p->nnz;
     SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
@@ -869,9 +923,10 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
     int rc2;
     if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
     if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc2;
-    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    if ((rc2 = launch_reduce_u64(L, L.d_aux, (size_t)blocks, L.d_result, 2, false)) != SPD_OK) return rc2;
+    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 3 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
     SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
-    p->info.launches = 3;
+    p->info.launches = 4;
     p->pending = true;
     return SPD_OK;
   }
@@ -883,7 +938,7 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
   a.rptrs = p->d_rptrs; a.cols = p->d_cols; a.cptrs = p->d_cptrs; a.rows = p->d_rows;
   a.rvals = p->d_rvals; a.cvals = p->d_cvals;
   a.ell_rows = p->d_ell_rows; a.ell_cols = p->d_ell_cols;
-  a.partial_sum = L.d_partials; a.partial_sq = L.d_partials + blocks;
+  a.partial_sum = L.d_partials; a.partial_sq = L.d_partials + blocks; a.partial_alive = L.d_aux; a.trace = p->d_trace;
   a.trial_lo = lo; a.trial_hi = hi; a.seed = p->seed; a.sq_scale = p->sq_scale;
   a.nov = p->nov; a.nnz = p->nnz; a.scaling = p->scaling;
   a.scale_intervals = p->y; a.scale_times = p->z;
@@ -893,9 +948,10 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
   int rc;
   if ((rc = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc;
   if ((rc = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc;
-  SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+  if ((rc = launch_reduce_u64(L, L.d_aux, (size_t)blocks, L.d_result, 2, false)) != SPD_OK) return rc;
+  SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 3 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
   SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
-  p->info.launches = 3;
+  p->info.launches = 4;
   p->pending = true;
   return SPD_OK;
 }
@@ -910,6 +966,7 @@ int spd_approx_plan_wait(spd_approx_plan* p, double* sum, spd_run_info* info) {
   p->info.kernel_ms = ms;
   p->info.aux0 = p->lanep->h_result[1];   // sum of (estimate * sq_scale)^2
   p->info.aux1 = p->sq_scale;
+  memcpy(&p->info.visited, &p->lanep->h_result[2], sizeof(unsigned long long));   // trials that reached the last step
   if (sum) *sum = p->lanep->h_result[0];
   if (info) *info = p->info;
   return SPD_OK;
@@ -922,13 +979,44 @@ int spd_approx_plan_run(spd_approx_plan* p, unsigned long long lo, unsigned long
   return spd_approx_plan_wait(p, sum, info);
 }
 
-// One trial on the device, for bit-exact comparison with the oracle (tests only use tiny counts).
-int spd_approx_plan_trial(spd_approx_plan* p, unsigned long long trial, double* value) {
+// Trials [lo, hi) in one launch with their per-trial record, for bit-exact comparison with the oracle
+// (tests; <= 2^16 trials): estimate[i] (0 for a dead end), steps[i] completed and the running product at
+// that point (== estimate when the trial reached the last step).  A dead trial still has to agree with the
+// CPU restatement in how far it got and in the product it had built -- on patterns where nearly every trial dies
+// (the 36 x 36 grid) this is what makes the comparison say something.
+int spd_approx_plan_trace(spd_approx_plan* p, unsigned long long lo, unsigned long long hi, double* estimate,
+                          int* steps, double* partial) {
+  if (!p || hi < lo || hi - lo > 65536ull) { set_error("bad trace range"); return SPD_EINVAL; }
+  const size_t cnt = (size_t)(hi - lo);
+  if (cnt == 0) return SPD_OK;
+  Lane& L = *p->lanep;
+  SPB_CUDA(cudaSetDevice(L.device));
+  double* d_trace = nullptr;
+  SPB_CUDA(cudaMalloc(&d_trace, 2 * cnt * sizeof(double)));
+  p->d_trace = d_trace;
   double s = 0.0;
   spd_run_info info;
-  int rc = spd_approx_plan_run(p, trial, trial + 1, &s, &info);
-  if (rc == SPD_OK && value) *value = s;
-  return rc;
+  int rc = spd_approx_plan_run(p, lo, hi, &s, &info);
+  p->d_trace = nullptr;
+  std::vector<double> h(2 * cnt);
+  if (rc == SPD_OK && cudaMemcpy(h.data(), d_trace, 2 * cnt * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("trace read-back failed");
+    rc = SPD_ECUDA;
+  }
+  cudaFree(d_trace);
+  if (rc != SPD_OK) return rc;
+  for (size_t i = 0; i < cnt; ++i) {
+    const int st = (int)h[2 * i];
+    if (steps) steps[i] = st;
+    if (partial) partial[i] = h[2 * i + 1];
+    if (estimate) estimate[i] = (st == p->nov) ? h[2 * i + 1] : 0.0;
+  }
+  return SPD_OK;
+}
+
+// One trial on the device (kept for callers that want a single estimate).
+int spd_approx_plan_trial(spd_approx_plan* p, unsigned long long trial, double* value) {
+  return spd_approx_plan_trace(p, trial, trial + 1, value, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -85,6 +85,23 @@ static int report_failure(void) {
 static int g_compress = 0;
 static double g_threshold = 0.0;   /* 0: scale leaves only when the compression changed the matrix */
 static int g_preprocessing = 0;
+static int g_usable_devices = 1;   /* visible devices from the first one used (-l) on */
+
+/* id 66 is the reference's hand-made 3:3:1:1 split over exactly four GPUs (gpu_exact_dense.cu:906-989,
+ * gpu_exact_sparse.cu:1326-1407), a hack for one heterogeneous box; it is served by the even static split
+ * over four devices, or over as many as the box has */
+static int devices_for_66(void) {
+  const int g = g_usable_devices < 4 ? g_usable_devices : 4;
+  if (g < 4) fprintf(stderr, "perman: -p66 wants 4 devices, %d usable; using %d\n", g_usable_devices, g);
+  return g < 1 ? 1 : g;
+}
+
+/* full-precision companion lines of an approximation (PERMAN_PRECISION=1): standard error of the mean and
+ * how many trials reached the last step (the rest ran into an empty row and estimate 0) */
+static void approx_precision(const char *name, const sp_stats *st) {
+  if (getenv("PERMAN_PRECISION"))
+    printf("StdError: %s %.6g trials %llu survived %llu\n", name, st->std_error, st->units, st->visited);
+}
 
 static void print_compressed(const sp_stats *st) {
   printf("Compressed: %d leaf matrix(es), %llu Gray indices\n", st->chunks, st->units);
@@ -103,10 +120,8 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
           "gpu_perman64_xshared_coalescing_mshared", "gpu_perman64_xshared_coalescing_mshared_multigpu",
           "gpu_perman64_xshared_coalescing_mshared_multigpucpu_chunks"};
       if (perman_algo == 66) {
-        /* 3:3:1:1 manual split over exactly four GPUs (gpu_exact_dense.cu:906-989): a hack for one
-         * heterogeneous box; served by the even static split over four devices */
         start = now_s();
-        perman = sp_dense_ryser(m->mat, nov, 5, 4, cpu, threads, &st);
+        perman = sp_dense_ryser(m->mat, nov, 5, devices_for_66(), cpu, threads, &st);
         if (isnan(perman) && st.error) return report_failure();
         print_kernel_lines(&st);
         printf("Result: gpu_perman64_xshared_coalescing_mshared_multigpu_manual_distribution %2lf in %lf\n",
@@ -143,6 +158,7 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
       if (isnan(perman) && st.error) return report_failure();
       print_kernel_lines(&st);
       result_both(name, "Result", perman, now_s() - start);
+      approx_precision(name, &st);
     }
   } else {
     if (!approximation) {
@@ -167,8 +183,10 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
       } else if (perman_algo == 7 || perman_algo == 8)
         perman = sp_skipper(m->mat, m->rptrs, m->cols, m->cptrs, m->rows, m->cvals, nov, perman_algo, gpu_num,
                             cpu, threads, &st);
-      else if (perman_algo == 66)
-        perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, nov, 5, 4, cpu, threads, &st);
+      else if (perman_algo == 66) {
+        if (g_compress || g_threshold > 0) fprintf(stderr, "perman: -o / -u are not applied to -p66\n");
+        perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, nov, 5, devices_for_66(), cpu, threads, &st);
+      }
       else
         perman = sp_sparse_ryser(m->mat, m->cptrs, m->rows, m->cvals, nov, perman_algo, gpu_num, cpu, threads, &st);
       if (isnan(perman) && st.error) return report_failure();
@@ -193,6 +211,7 @@ static int run_matrix(const sp_matrix *m, int perman_algo, int gpu_num, int thre
       if (isnan(perman) && st.error) return report_failure();
       print_kernel_lines(&st);
       result_both(name, "Result", perman, now_s() - start);
+      approx_precision(name, &st);
     }
   }
   return 0;
@@ -233,7 +252,7 @@ static int run_grid(int gm, int gn, int perman_algo, int gpu_num, int number_of_
   printf("Result: %s %2lf in %lf\n", name, perman, secs);
   printf("Try: %s %g in %g\n", try_name, perman, secs);
   extra_precision(name, perman);
-  if (getenv("PERMAN_PRECISION")) printf("StdError: %s %.6g trials %llu\n", name, st.std_error, st.units);
+  approx_precision(name, &st);
   /* the reference dumps m rows x n columns of the nov x nov matrix here (main.cu:309-316) */
   printf("------------GRID--------------\n");
   for (int i = 0; i < gm; ++i) {
@@ -337,6 +356,7 @@ int main(int argc, char **argv) {
     gpu_num = visible - first_device;
   }
   if (gpu_num < 1) gpu_num = 1;
+  g_usable_devices = visible - first_device;
   /* CUDA context creation (~0.15 s per device) is not part of any algorithm: do it before the
    * timed wrapper calls.  Single-GPU ids only need device 0. */
   {

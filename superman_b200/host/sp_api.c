@@ -437,13 +437,8 @@ static int approx_open(const void *job, int device, void **plan) {
 static int approx_launch(void *plan, unsigned long long lo, unsigned long long hi) {
   return spd_approx_plan_launch((spd_approx_plan *)plan, lo, hi);
 }
-/* the scheduler only carries one double per chunk; the squared sums ride along in a side table */
-static _Thread_local double g_sq_acc;
-static _Thread_local double g_sq_scale;
 static int approx_wait(void *plan, double *sum, spd_run_info *info) {
-  int rc = spd_approx_plan_wait((spd_approx_plan *)plan, sum, info);
-  if (rc == SPD_OK) { g_sq_acc += info->aux0; g_sq_scale = info->aux1; }
-  return rc;
+  return spd_approx_plan_wait((spd_approx_plan *)plan, sum, info);
 }
 static void approx_close(void *plan) { spd_approx_plan_destroy((spd_approx_plan *)plan); }
 static const sp_job_ops g_approx_ops = {approx_open, approx_launch, approx_wait, approx_close};
@@ -458,31 +453,18 @@ static double approx_common(const approx_job *job, long long trials, int gpu_num
   sp_stats local;
   sp_stats *st = stats ? stats : &local;
   double sum = 0.0;
-  int rc;
-  if (gpu_num == 1) {
-    /* single device: run on the calling thread so that the squared sum can be read back directly */
-    g_sq_acc = 0.0; g_sq_scale = 1.0;
-    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, 1, g_first_device, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
-    if (rc == SP_OK) {
-      const double n = (double)trials, mean = sum / n, ms = mean * g_sq_scale;
-      double var = g_sq_acc / n - ms * ms;
-      if (var < 0) var = 0;
-      st->std_error = (n > 1) ? sqrt(var / (n - 1)) / g_sq_scale : 0.0;
-    }
-  } else {
-    /* several devices: static even split of the trial indices; the standard error is taken from
-     * the per-device means (batch means) */
-    rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, gpu_num, g_first_device, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
-    if (rc == SP_OK) {
-      const double mean = sum / (double)trials;
-      double acc = 0.0;
-      for (int g = 0; g < st->devices; ++g) {
-        const double mg = st->device_partial[g] / (double)(st->device_units[g] ? st->device_units[g] : 1);
-        const double rel = (mean != 0.0) ? (mg / mean - 1.0) : 0.0;
-        acc += rel * rel;
-      }
-      st->std_error = (st->devices > 1) ? fabs(mean) * sqrt(acc / (st->devices - 1) / st->devices) : 0.0;
-    }
+  /* static even split of the trial indices over the devices; every device returns its sum, its sum of
+   * (scaled) squares and its count of trials that reached the last step, all carried by the scheduler */
+  int rc = sp_sched_run(&g_approx_ops, job, SP_SCHED_STATIC, gpu_num, g_first_device, 0ull, (unsigned long long)trials, 0, 0, &sum, st);
+  if (rc == SP_OK) {
+    const double n = (double)trials, mean = sum / n;
+    const double sc = st->sq_scale != 0.0 ? st->sq_scale : 1.0, ms = mean * sc;
+    double var = st->sumsq_scaled / n - ms * ms;
+    if (var < 0) var = 0;
+    st->std_error = (n > 1) ? sqrt(var / (n - 1)) / sc : 0.0;
+    /* the squares are accumulated in a scaled domain chosen from the order of the pattern; if they left the
+     * double range anyway, say so instead of reporting 0 */
+    if (!isfinite(st->sumsq_scaled) || (sum != 0.0 && st->sumsq_scaled == 0.0)) st->std_error = NAN;
   }
   st->wall_ms = sp_now_ms() - t0;
   if (rc != SP_OK) return fail(stats, rc);
@@ -559,54 +541,69 @@ double sp_scaling_dense(const double *mat, int nov, long long trials, int scale_
   return dense_approx(mat, nov, trials, 1, scale_intervals, scale_times, gpu_num, seed, stats);
 }
 
-double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
-                              int nov, int nnz, int scaling, int scale_intervals, int scale_times,
-                              unsigned long long seed, long long trial, int count, double *values,
-                              sp_stats *stats) {
-  stats_clear(stats);
-  if (!values || count < 1 || trial < 0) { sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
+/* shared tail of the four per-trial entry points: one plan, one traced launch */
+static double trace_common(const int *rptrs, const int *cols, const int *cptrs, const int *rows, const double *rvals,
+                           const double *cvals, int nov, int nnz, int scaling, int y, int z, unsigned long long seed,
+                           long long trial, int count, double *values, int *steps, double *partial, sp_stats *stats) {
   spd_approx_plan *plan = NULL;
-  int rc = spd_approx_plan_create(0, rptrs, cols, cptrs, rows, NULL, NULL, nov, nnz, scaling,
-                                  scale_intervals, scale_times, pick_seed(seed), &plan);
+  int rc = spd_approx_plan_create(g_first_device, rptrs, cols, cptrs, rows, rvals, cvals, nov, nnz, scaling, y, z,
+                                  pick_seed(seed), &plan);
   if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
-  double total = 0.0;
-  for (int i = 0; i < count; ++i) {
-    rc = spd_approx_plan_trial(plan, (unsigned long long)trial + (unsigned long long)i, &values[i]);
-    if (rc != SPD_OK) break;
-    total += values[i];
-  }
+  double *est = values ? values : (double *)malloc((size_t)count * sizeof(double));
+  if (!est) { spd_approx_plan_destroy(plan); sp_set_error("out of memory"); return fail(stats, SP_ENOMEM); }
+  rc = spd_approx_plan_trace(plan, (unsigned long long)trial, (unsigned long long)trial + (unsigned long long)count, est, steps, partial);
   spd_approx_plan_destroy(plan);
+  double total = 0.0;
+  if (rc == SPD_OK) for (int i = 0; i < count; ++i) total += est[i];
+  if (!values) free(est);
   if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
   return total;
 }
 
-/* per-trial estimates of the dense twins (pattern = entries != 0; the scaled estimator weights its
- * Sinkhorn sums by the entries, gpu_approximation_dense.cu:286-313) */
-double sp_approx_trial_dense(const double *mat, int nov, int scaling, int scale_intervals, int scale_times,
-                             unsigned long long seed, long long trial, int count, double *values,
-                             sp_stats *stats) {
+double sp_approx_trace_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows, int nov, int nnz,
+                              int scaling, int scale_intervals, int scale_times, unsigned long long seed,
+                              long long trial, int count, double *values, int *steps, double *partial,
+                              sp_stats *stats) {
   stats_clear(stats);
-  if (!mat || !values || count < 1 || trial < 0) { sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
+  if (count < 1 || count > 65536 || trial < 0) { sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
+  return trace_common(rptrs, cols, cptrs, rows, NULL, NULL, nov, nnz, scaling, scale_intervals, scale_times, seed, trial,
+                      count, values, steps, partial, stats);
+}
+
+double sp_approx_trial_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows,
+                              int nov, int nnz, int scaling, int scale_intervals, int scale_times,
+                              unsigned long long seed, long long trial, int count, double *values,
+                              sp_stats *stats) {
+  if (!values) { stats_clear(stats); sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
+  return sp_approx_trace_sparse(rptrs, cols, cptrs, rows, nov, nnz, scaling, scale_intervals, scale_times, seed, trial,
+                                count, values, NULL, NULL, stats);
+}
+
+/* per-trial records of the dense twins (pattern = entries != 0; the scaled estimator weights its
+ * Sinkhorn sums by the entries, gpu_approximation_dense.cu:286-313) */
+double sp_approx_trace_dense(const double *mat, int nov, int scaling, int scale_intervals, int scale_times,
+                             unsigned long long seed, long long trial, int count, double *values, int *steps,
+                             double *partial, sp_stats *stats) {
+  stats_clear(stats);
+  if (!mat || count < 1 || count > 65536 || trial < 0) { sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
   if (nov < 1 || nov > SP_MAX_NOV) { sp_set_error("matrix order %d out of range", nov); return fail(stats, SP_ELIMIT); }
   int *rptrs = NULL, *cols = NULL, *cptrs = NULL, *rows = NULL, nnz = 0;
   double *rvals = NULL, *cvals = NULL;
   int rc = dense_pattern(mat, nov, &rptrs, &cols, &rvals, &cptrs, &rows, &cvals, &nnz);
   double total = NAN;
-  if (rc == SP_OK) {
-    spd_approx_plan *plan = NULL;
-    rc = spd_approx_plan_create(0, rptrs, cols, cptrs, rows, scaling ? rvals : NULL, scaling ? cvals : NULL, nov, nnz,
-                                scaling, scale_intervals, scale_times, pick_seed(seed), &plan);
-    if (rc == SPD_OK) {
-      total = 0.0;
-      for (int i = 0; i < count && rc == SPD_OK; ++i) {
-        rc = spd_approx_plan_trial(plan, (unsigned long long)trial + (unsigned long long)i, &values[i]);
-        total += values[i];
-      }
-      spd_approx_plan_destroy(plan);
-    }
-    if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); total = NAN; }
-  }
+  if (rc == SP_OK)
+    total = trace_common(rptrs, cols, cptrs, rows, scaling ? rvals : NULL, scaling ? cvals : NULL, nov, nnz, scaling,
+                         scale_intervals, scale_times, seed, trial, count, values, steps, partial, stats);
+  else if (stats)
+    stats->error = rc;
   free(rptrs); free(cols); free(cptrs); free(rows); free(rvals); free(cvals);
-  if (rc != SP_OK) return fail(stats, rc);
   return total;
+}
+
+double sp_approx_trial_dense(const double *mat, int nov, int scaling, int scale_intervals, int scale_times,
+                             unsigned long long seed, long long trial, int count, double *values,
+                             sp_stats *stats) {
+  if (!values) { stats_clear(stats); sp_set_error("bad argument"); return fail(stats, SP_EINVAL); }
+  return sp_approx_trace_dense(mat, nov, scaling, scale_intervals, scale_times, seed, trial, count, values, NULL, NULL,
+                               stats);
 }

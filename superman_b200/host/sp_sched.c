@@ -67,6 +67,7 @@ typedef struct sched_worker {
   double partial;
   unsigned long long units, visited;
   int launches, chunks, path, tile_log2;
+  double aux0, aux1;          /* approximations: sum of scaled squares, the scale */
 } sched_worker;
 
 static void worker_fail(sched_shared *sh, int code) {
@@ -88,6 +89,8 @@ static void worker_account(sched_worker *w, const spd_run_info *info, double sum
   w->visited += info->visited;
   w->launches += info->launches;
   w->chunks += 1;
+  w->aux0 += info->aux0;
+  w->aux1 = info->aux1;
   w->path = info->path;
   if (info->tile_log2 > w->tile_log2) w->tile_log2 = info->tile_log2;
 }
@@ -228,6 +231,7 @@ int sp_sched_run(const sp_job_ops *ops, const void *job, int mode, int gpu_num, 
     stats->chunks = (int)(n_chunks > 0x7fffffffULL ? 0x7fffffff : n_chunks);
     stats->kernel_ms = 0.0;
     stats->units = 0; stats->visited = 0; stats->launches = 0;
+    stats->sumsq_scaled = 0.0; stats->sq_scale = 0.0;
     for (int g = 0; g < gpu_num; ++g) {
       stats->device_ms[g] = workers[g].ms;
       stats->device_partial[g] = workers[g].partial;
@@ -236,6 +240,8 @@ int sp_sched_run(const sp_job_ops *ops, const void *job, int mode, int gpu_num, 
       stats->units += workers[g].units;
       stats->visited += workers[g].visited;
       stats->launches += workers[g].launches;
+      stats->sumsq_scaled += workers[g].aux0;
+      if (workers[g].aux1 != 0.0) stats->sq_scale = workers[g].aux1;
       if (workers[g].path) stats->path = workers[g].path;
       if (workers[g].tile_log2 > stats->tile_log2) stats->tile_log2 = workers[g].tile_log2;
     }

@@ -80,6 +80,10 @@ class Oracle:
         L.orc_rasmussen_trial.argtypes = [_ip, _ip, C.c_int, u64, u64]
         L.orc_scaling_trial.restype = C.c_double
         L.orc_scaling_trial.argtypes = [_ip, _ip, _ip, _ip, _dp, _dp, C.c_int, C.c_int, C.c_int, u64, u64]
+        L.orc_rasmussen_trace.restype = C.c_double
+        L.orc_rasmussen_trace.argtypes = [_ip, _ip, C.c_int, u64, u64, C.POINTER(C.c_int), _dp]
+        L.orc_scaling_trace.restype = C.c_double
+        L.orc_scaling_trace.argtypes = [_ip, _ip, _ip, _ip, _dp, _dp, C.c_int, C.c_int, C.c_int, u64, u64, C.POINTER(C.c_int), _dp]
         L.orc_philox.restype = None
         L.orc_philox.argtypes = [u64, u64, C.c_uint, C.POINTER(C.c_uint * 4)]
 
@@ -95,6 +99,20 @@ class Oracle:
         rv = _pd(_d(rvals)) if rvals is not None else None
         cv = _pd(_d(cvals)) if cvals is not None else None
         return self.lib.orc_scaling_trial(_pi(_i(rptrs)), _pi(_i(cols)), _pi(_i(cptrs)), _pi(_i(rows)), rv, cv, nov, y, z, seed, trial)
+
+    def rasmussen_trace(self, rptrs, cols, nov, seed, trial):
+        """(estimate, steps completed, running product at that point) of one trial"""
+        st = C.c_int(); part = C.c_double()
+        v = self.lib.orc_rasmussen_trace(_pi(_i(rptrs)), _pi(_i(cols)), nov, seed, trial, C.byref(st), C.byref(part))
+        return v, st.value, part.value
+
+    def scaling_trace(self, rptrs, cols, cptrs, rows, nov, y, z, seed, trial, rvals=None, cvals=None):
+        rv = _pd(_d(rvals)) if rvals is not None else None
+        cv = _pd(_d(cvals)) if cvals is not None else None
+        st = C.c_int(); part = C.c_double()
+        v = self.lib.orc_scaling_trace(_pi(_i(rptrs)), _pi(_i(cols)), _pi(_i(cptrs)), _pi(_i(rows)), rv, cv, nov, y, z, seed,
+                                       trial, C.byref(st), C.byref(part))
+        return v, st.value, part.value
 
     # ---- dense ----
     def perm_ld(self, mat) -> float:

@@ -172,3 +172,93 @@ def test_dead_ends_and_errors(sp):
     assert sp.scaling_sparse(m.cptrs, m.rows, m.rptrs, m.cols, 5, m.nnz, 500, 4, 5, 1, seed=1) == 0.0
     with pytest.raises(sp.SupermanError):
         sp.rasmussen_sparse(m.rptrs, m.cols, m.cptrs, m.rows, 5, m.nnz, 0, 1)
+
+
+def _trace_equal(sp, oracle, g, scaling, seed, first, count, y=4, z=5):
+    est, steps, part = sp.approx_trace_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, scaling=scaling,
+                                              scale_intervals=y, scale_times=z, seed=seed, first=first, count=count)
+    for i in range(count):
+        if scaling:
+            want = oracle.scaling_trace(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, y, z, seed, first + i)
+        else:
+            want = oracle.rasmussen_trace(g.rptrs, g.cols, g.nov, seed, first + i)
+        assert (est[i], int(steps[i]), part[i]) == want, (scaling, first + i, est[i], steps[i], part[i], want)
+    return est, steps, part
+
+
+def test_config5_per_trial_record_36x36(sp, oracle):
+    """BASELINE.json configs[4] at full size (nov = 648): nearly every trial of either estimator dies, so
+    the estimates alone compare 0 with 0.  Each trial's record does not: the number of steps it completed
+    and the running product it had built by then must equal the oracle's, bit for bit -- hundreds of
+    min-degree searches, column picks and (scaled) 160 Sinkhorn phases per trial."""
+    g = _grid(sp, 36, 36)
+    for scaling, count in ((False, 96), (True, 24)):
+        est, steps, part = _trace_equal(sp, oracle, g, scaling, seed=3, first=0, count=count)
+        assert steps.max() > 300 and len(set(steps.tolist())) > 8          # long, different runs
+        # real products, not zeros (scaled trials die earlier: their factors are 1/p of the column picked)
+        assert np.median(part) > (1e3 if scaling else 1e30) and part.max() > 1e30 and (part > 0).all()
+    # the three engines agree on the same trials (thread-per-trial "mid" kernel vs warp-per-trial kernel)
+    import os
+    a = sp.approx_trace_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, seed=9, first=1000, count=64)
+    os.environ["SP_APPROX_FORCE_WARP"] = "1"
+    try:
+        b = sp.approx_trace_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, seed=9, first=1000, count=64)
+    finally:
+        del os.environ["SP_APPROX_FORCE_WARP"]
+    for x, y in zip(a, b):
+        assert (x == y).all()
+
+
+@pytest.mark.parametrize("dims", [(12, 12), (10, 16), (14, 14)])
+def test_confidence_interval_beyond_64_rows(sp, oracle, dims, monkeypatch):
+    """nov = 72 .. 98: the thread-per-trial Rasmussen kernel for large patterns (rasmussen_mid_kernel) and the
+    warp-per-trial kernel (scaled estimator; Rasmussen too when forced) against Kasteleyn's closed form
+    (12 x 12: 53 060 477 521 960 000), inside 5 standard errors; survivors are counted."""
+    g = _grid(sp, *dims)
+    assert g.nov > 64
+    exact = oracle.kasteleyn(*dims)
+    if dims == (12, 12):
+        assert exact == pytest.approx(53060477521960000.0, rel=1e-12)
+    N = 1 << 20
+    for mode in ("rasmussen", "rasmussen-warp", "scaled"):
+        st = sp._ffi.SpStats()
+        if mode == "rasmussen-warp":
+            monkeypatch.setenv("SP_APPROX_FORCE_WARP", "1")
+        if mode == "scaled":
+            v = sp.scaling_sparse(g.cptrs, g.rows, g.rptrs, g.cols, g.nov, g.nnz, N // 4, 4, 5, 1, seed=21, stats=st)
+        else:
+            v = sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, N, 1, seed=21, stats=st)
+        monkeypatch.delenv("SP_APPROX_FORCE_WARP", raising=False)
+        assert 0 < st.visited <= st.units                       # trials that reached the last step
+        assert st.std_error > 0 and abs(v - exact) < 5 * st.std_error, (dims, mode, v, exact, st.std_error)
+        assert st.std_error < 0.25 * exact, (dims, mode, st.std_error / exact)
+
+
+def test_row_with_more_than_255_entries(sp, oracle):
+    """a 300 x 300 pattern with a full row (the reference's 21-word masks take such rows,
+    gpu_approximation_sparse.cu:228; round 1 refused them): per-trial records equal to the oracle's, the
+    mean inside the confidence interval of the exact permanent (transfer-matrix DP, tests/_closed_forms.py)"""
+    import _closed_forms as cf
+    A, exact = cf.dense_row_over_band(300, 40)
+    n = 300
+    m = sp.Matrix.from_dense(A).compress(0)
+    assert max(np.diff(m.rptrs)) == 300
+    _trace_equal(sp, oracle, m, False, seed=5, first=0, count=12)
+    _trace_equal(sp, oracle, m, True, seed=5, first=0, count=4)
+    st = sp._ffi.SpStats()
+    v = sp.rasmussen_dense(A, n, 1 << 17, 1, seed=8, stats=st)
+    assert st.std_error > 0 and abs(v - exact) < 5 * st.std_error, (v, exact, st.std_error)
+    v = sp.scaling_dense(A, n, 1 << 14, 4, 5, 1, seed=8, stats=st)
+    assert st.std_error > 0 and abs(v - exact) < 5 * st.std_error, (v, exact, st.std_error)
+
+
+def test_malformed_patterns_are_refused(sp):
+    g = _grid(sp, 4, 4)
+    bad_cols = np.array(g.cols).copy(); bad_cols[3] = g.nov          # column index out of range
+    with pytest.raises(sp.SupermanError):
+        sp.rasmussen_sparse(g.rptrs, bad_cols, g.cptrs, g.rows, g.nov, g.nnz, 100, 1)
+    bad_ptr = np.array(g.rptrs).copy(); bad_ptr[2] = bad_ptr[1] - 1   # not monotone
+    with pytest.raises(sp.SupermanError):
+        sp.rasmussen_sparse(bad_ptr, g.cols, g.cptrs, g.rows, g.nov, g.nnz, 100, 1)
+    with pytest.raises(sp.SupermanError):
+        sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz - 1, 100, 1)   # nnz does not match

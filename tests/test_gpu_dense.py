@@ -218,6 +218,38 @@ def test_n36_properties(sp):
     assert sp.dense_ryser(A, n, 6, gpu_num=1) == pytest.approx(p0, rel=REL)
 
 
+def test_n40_known_answers(sp, oracle):
+    """n = 40 (2^39 Gray indices, ~2.5 s per permanent), the other half of BASELINE config 4: no CPU oracle
+    reaches this size, so the GPU value is checked against permanents known in closed form, computed in
+    exact rational arithmetic from the very (dyadic) parameters the float64 matrix is built from
+    (tests/_closed_forms.py): D1 (J - I) D2 -> derangements(40) prod d1 prod d2; u v^T + diag(d) -> a
+    polynomial identity; a hidden block-diagonal matrix -> product of exact __int128 permanents.
+    Observed relative errors 3e-13 .. 2e-10; the bar is the north star's 1e-9."""
+    import _closed_forms as cf
+    n = 40
+    rng = np.random.default_rng(40)
+    cases = [("derangement", cf.derangement_matrix(rng, n)),
+             ("rank1+diag", cf.rank1_plus_diag(rng, n)),
+             ("blocks 20+20 int", cf.block_diagonal(rng, oracle, [20, 20], "int")),
+             ("blocks 13+13+14 bin", cf.block_diagonal(rng, oracle, [13, 13, 14], "bin"))]
+    for name, (A, exact) in cases:
+        st = sp._ffi.SpStats()
+        got = sp.dense_ryser(A, n, 4, stats=st)
+        assert st.units == 1 << 39 and st.path == 1, name
+        assert abs(got / float(exact) - 1.0) < REL, (name, got, float(exact))
+    # the same permanent along different Gray sequences and through the other ids
+    A, exact = cases[1][1]
+    ex = float(exact)
+    assert abs(sp.dense_ryser(A.T.copy(), n, 4) / ex - 1.0) < REL
+    assert abs(sp.dense_ryser(A[rng.permutation(n)][:, rng.permutation(n)].copy(), n, 5, gpu_num=1) / ex - 1.0) < REL
+    assert abs(sp.dense_ryser(A, n, 6, gpu_num=1) / ex - 1.0) < REL
+    # additive over a ragged split of the 2^39 indices
+    full = 1 << 39
+    cuts = [0, 123456789012, full // 2 + 4097, full]
+    tot = sum(sp.dense_ryser_range(A, cuts[i], cuts[i + 1], n) for i in range(3))
+    assert abs(tot * sp.nw_factor(n) / ex - 1.0) < REL
+
+
 def test_multi_device_partitions(sp, oracle):
     ndev = sp.device_count()
     if ndev < 2:

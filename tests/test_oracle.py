@@ -170,3 +170,21 @@ def test_oracle_lands_on_the_permanents_recorded_by_the_reference_authors():
         assert rec[0] * (1 - 1e-12) <= e["ld"] <= rec[-1] * (1 + 1e-12), name
         assert abs(e["ld"] - round(e["ld"])) < 0.01 or e["ld"] > 2.0 ** 53   # a 0/1 permanent is an integer
     assert known == 6
+
+
+def test_closed_form_families_against_the_oracle(oracle):
+    """tests/_closed_forms.py (the n = 40 known-answer generators of the GPU tests) at orders the CPU
+    oracle can check: exact rational value vs long-double Ryser, and vs the exact __int128 Ryser where
+    the matrix is integer"""
+    import _closed_forms as cf
+    rng = np.random.default_rng(5)
+    assert [cf.derangements(k) for k in range(8)] == [1, 0, 1, 2, 9, 44, 265, 1854]
+    for n in (2, 5, 9, 14):
+        for gen in (cf.derangement_matrix, cf.rank1_plus_diag):
+            A, exact = gen(rng, n)
+            assert oracle.perm_ld(A) == pytest.approx(float(exact), rel=1e-12)
+        A, exact = cf.derangement_matrix(rng, n, scaled=False)
+        assert oracle.perm_i128(A.astype(int)) == exact == cf.derangements(n)
+    for sizes, kind in (([4, 5], "int"), ([3, 3, 4], "bin"), ([7, 9], "int")):
+        A, exact = cf.block_diagonal(rng, oracle, sizes, kind)
+        assert oracle.perm_i128(A.astype(int)) == exact
