@@ -174,6 +174,209 @@ def cpu_reference_rate(mat, n: int, seconds: float, threads: int | None = None):
     return count / dt, cores, sample, kind, count, dt
 
 
+def config3_matrix(kind: str, n: int = 33, density: float = 0.2):
+    """Seeded n = 33, p = 0.2 matrix of BASELINE config 3 in the three input types the reference corpus has:
+    'bin' (the -b flag: every entry 1), 'int' (1..5) and 'dbl' (uniform (0.01, 5), 6 decimals); one entry per
+    row and column is forced so that the permanent is not structurally zero."""
+    import numpy as np
+    rng = np.random.default_rng(1000 * n + {"bin": 1, "int": 2, "dbl": 3}[kind])
+    pat = rng.random((n, n)) < density
+    pat[np.arange(n), rng.permutation(n)] = True
+    if kind == "bin":
+        return pat.astype(np.float64)
+    if kind == "int":
+        return (pat * rng.integers(1, 6, (n, n))).astype(np.float64)
+    return (pat * np.round(rng.uniform(0.01, 5.0, (n, n)), 6)).astype(np.float64)
+
+
+class _StdoutToStderr:
+    """The reference's wrappers print `kernel0 in ...` with std::cout; rank 0's stdout must carry exactly one
+    JSON line, so file descriptor 1 is pointed at stderr while they run."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def _best_of(fn, st, reps=3, warm=1):
+    """(best kernel_ms, best wall_ms, last value) of `reps` timed calls after `warm` untimed ones"""
+    v = None
+    for _ in range(warm):
+        v = fn()
+    k, w = [], []
+    for _ in range(reps):
+        t = time.perf_counter()
+        v = fn()
+        w.append(1e3 * (time.perf_counter() - t))
+        k.append(st.kernel_ms)
+    return min(k), min(w), v
+
+
+def extra_configs(sp, world: int, peak: float, dev: int = 0) -> dict:
+    """The other BASELINE.json configs, measured after the headline's timed region on rank 0 (the other ranks
+    are parked at the closing barrier): config 2 (n = 32 -p4), config 3 (SpaRyser + SortOrder and SkipPer +
+    SkipOrder at n = 33, p = 0.2, per input type), config 4's n = 40, config 5 (both estimators on the 36 x 36
+    grid, -x100000 -y4 -z5), the library's own in-process multi-GPU ids 5 / 6 over `world` devices, and the
+    unmodified reference GPU wrappers (oracle/_ref/libref_gpu.so) on the same inputs as the kernels to beat."""
+    import ctypes as C
+    import numpy as np
+    from superman_b200._ffi import SpStats
+    nominal = 148 * 64 * 1.965e9
+    out = {}
+    st = SpStats()
+
+    def dense_block(n, algo=4, reps=3, warm=1):
+        A = synthetic_matrix(n, DENSITY)
+        kms, wms, v = _best_of(lambda: sp.dense_ryser(A, n, algo, stats=st), st, reps, warm)
+        its = (1 << (n - 1)) / (kms * 1e-3)
+        return {"workload": f"dense Ryser n={n} density {DENSITY} FP64 seeded synthetic, -p{algo}, one full permanent",
+                "kernel_ms": kms, "wall_ms": wms, "value": its, "unit": "iterations/s", "permanent": v,
+                "rel_err_vs_long_double_golden": golden_rel_err(n, v),
+                "roofline": {"bound": "fp64_issue", "frac": its * (2 * n + 1) / peak,
+                             "frac_executed_instr": its * (2 * n) / peak, "frac_vs_nominal": its * (2 * n + 1) / nominal,
+                             "unit": "fraction of thread-level FP64 instr/s", "peak": peak / 1e9, "nominal": nominal / 1e9}}
+
+    out["config2_n32_p4"] = dense_block(32)
+    out["config4_n40_p4"] = dense_block(40, reps=1, warm=0)
+
+    # ---- config 3 ----
+    c3 = {}
+    for kind in ("bin", "int", "dbl"):
+        A = config3_matrix(kind)
+        n = A.shape[0]
+        for pre, label, skip in ((1, "sparyser_sortorder", False), (2, "skipper_skiporder", True)):
+            m = sp.Matrix.from_dense(A).compress(pre)
+            if skip:
+                fn = lambda: sp.skipper(m.mat, m.rptrs, m.cols, m.cptrs, m.rows, m.cvals, n, 7, stats=st)
+            else:
+                fn = lambda: sp.sparse_ryser(m.mat, m.cptrs, m.rows, m.cvals, n, 4, stats=st)
+            kms, wms, v = _best_of(fn, st)
+            eff = (1 << (n - 1)) / (kms * 1e-3)
+            model = st.sq_scale          # sparse exact paths: the chosen engine's FP64 instructions per index (host model)
+            c3[f"{kind}_{label}"] = {
+                "kernel_ms": kms, "wall_ms": wms, "effective_iterations_per_s": eff, "visited": int(st.visited),
+                "visited_frac": st.visited / float(1 << (n - 1)), "permanent": v,
+                "fp64_instr_per_index_model": model,
+                "roofline_frac_model": (eff * model / peak) if model > 0 else None}
+    out["config3_n33_p0.2"] = {
+        "workload": "seeded 33x33 density 0.2 (bench.config3_matrix), -s -p4 -r1 (SpaRyser + SortOrder) and -s -p7 -r2 "
+                    "(SkipPer + SkipOrder); effective it/s = 2^32 / kernel time; the roofline fraction uses the host cost "
+                    "model's FP64 instructions per index for the chosen LevelRyser configuration (ncu: "
+                    "profiles/r02_ncu_level_engine.txt)", **c3}
+
+    # ---- config 5 ----
+    g = sp.Matrix.grid(36, 36)
+    int_peak = sp.int_peak(dev, 100)
+    ipt = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "estimator_inst_per_trial.json")) as f:
+            ipt = json.load(f)
+    except OSError:
+        pass
+    c5 = {}
+    for label, fn in (("rasmussen_p1", lambda: sp.rasmussen_sparse(g.rptrs, g.cols, g.cptrs, g.rows, g.nov, g.nnz, 100000, 1, seed=0, stats=st)),
+                      ("scaling_p2_y4_z5", lambda: sp.scaling_sparse(g.cptrs, g.rows, g.rptrs, g.cols, g.nov, g.nnz, 100000, 4, 5, 1, seed=0, stats=st))):
+        kms, wms, v = _best_of(fn, st)
+        tps = 100000 / (kms * 1e-3)
+        blk = {"kernel_ms": kms, "wall_ms": wms, "value": tps, "unit": "trials/s", "estimate": v, "std_error": st.std_error,
+               "survivors": int(st.visited), "trials": int(st.units)}
+        per = ipt.get(label)
+        if per:
+            blk["int_issue_roofline"] = {"thread_instr_per_trial": per["thread_instr_per_trial"], "source": per["source"],
+                                         "achieved": tps * per["thread_instr_per_trial"] / 1e9, "peak": int_peak / 1e9,
+                                         "unit": "Ginstr/s (thread-level)", "frac": tps * per["thread_instr_per_trial"] / int_peak}
+        c5[label] = blk
+    out["config5_grid36x36_x100000"] = {"workload": "-a -i -m36 -n36 -x100000 -y4 -z5 (nov 648, nnz 2520), Philox seed 0; exact value "
+                                                    "3.0597e159 (Kasteleyn); nearly every trial of either estimator dies on this "
+                                                    "pattern, in the reference as here (survivors reported)",
+                                        "int_peak_measured_ginstr_s": int_peak / 1e9, **c5}
+
+    # ---- in-process multi-GPU ids over `world` devices (what `perman -p5/-p6 -dN` runs) ----
+    gdev = max(1, min(world, sp.device_count()))
+    A36 = synthetic_matrix(N_DENSE, DENSITY)
+    inproc = {"devices": gdev}
+    for algo, label in ((5, "p5_static"), (6, "p6_dynamic")):
+        kms, wms, v = _best_of(lambda: sp.dense_ryser(A36, N_DENSE, algo, gpu_num=gdev, stats=st), st)
+        inproc[label] = {"kernel_ms_max_over_devices": kms, "wall_ms": wms, "value": (1 << (N_DENSE - 1)) / (wms * 1e-3),
+                         "unit": "iterations/s (host wall clock of the library call)", "chunks": st.chunks, "permanent": v,
+                         "rel_err_vs_long_double_golden": golden_rel_err(N_DENSE, v)}
+    out["in_process_n36"] = inproc
+
+    # ---- the unmodified reference GPU wrappers on the same B200, in a child process: the reference checks no
+    # CUDA call, and its sparse kernel faults ("misaligned address") whenever nov + 1 + nnz is odd (doubles
+    # placed after an odd number of ints in shared memory, gpu_exact_sparse.cu:467-476) -- a fault must not
+    # poison this process's context ----
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_gpu.so")
+    if os.path.exists(so):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--reference-gpu-child"], capture_output=True,
+                               text=True, timeout=300)
+            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            ref["ours"] = {"dense_n32_wall_ms": out["config2_n32_p4"]["wall_ms"],
+                           "sparyser_kernel_ms": {k: c3[f"{k}_sparyser_sortorder"]["kernel_ms"] for k in ("bin", "int", "dbl")},
+                           "rasmussen_grid36x36_ms_per_2^20_trials": c5["rasmussen_p1"]["kernel_ms"] * (1 << 20) / 100000}
+            out["reference_gpu"] = ref
+        except Exception as e:   # a reporting extra must not take the headline down
+            out["reference_gpu"] = {"error": str(e)[:200]}
+    return out
+
+
+def reference_gpu_child():
+    """Times the unmodified reference GPU wrappers (oracle/_ref/libref_gpu.so); prints one JSON line."""
+    import ctypes as C
+    import numpy as np
+    import superman_b200 as sp      # host-side reader / orderings only: nothing of ours runs on the GPU here
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_gpu.so"))
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.ref_gpu_dense_multigpu.restype = C.c_double
+    lib.ref_gpu_dense_multigpu.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_gpu_sparse_multigpu.restype = C.c_double
+    lib.ref_gpu_sparse_multigpu.argtypes = [dp, ip, ip, dp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_gpu_rasmussen_chunks_sparse.restype = C.c_double
+    lib.ref_gpu_rasmussen_chunks_sparse.argtypes = [ip, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
+    ref = {"note": "unmodified reference .cu files compiled for sm_100a (oracle/Makefile), launch geometry as RunAlgo "
+                   "(2048 x 128 / 256); wall seconds of the wrapper call, second of two calls; the reference keeps X in "
+                   "float, so its values on double-valued input are only ~3 digits (SURVEY 8(c))"}
+
+    def timed(fn):
+        with _StdoutToStderr():
+            fn()
+            t = time.perf_counter()
+            v = fn()
+            dt = time.perf_counter() - t
+        return dt, v
+    for n in (32, 36):
+        A = np.ascontiguousarray(synthetic_matrix(n, DENSITY))
+        s_, v = timed(lambda: lib.ref_gpu_dense_multigpu(A.ctypes.data_as(dp), n, 1, 2048, 128))
+        ref[f"dense_n{n}"] = {"wall_s": s_, "value": v, "iterations_per_s": (1 << (n - 1)) / s_}
+    g = sp.Matrix.grid(36, 36)
+    s_, v = timed(lambda: lib.ref_gpu_rasmussen_chunks_sparse(g.cptrs.ctypes.data_as(ip), g.rows.ctypes.data_as(ip), g.rptrs.ctypes.data_as(ip),
+                                                              g.cols.ctypes.data_as(ip), g.nov, g.nnz, 100000, 1))
+    ref["rasmussen_grid36x36"] = {"wall_s": s_, "value": v, "trials": 1 << 20,
+                                  "note": "the reference runs 1024 x 1024 trials per launch whatever -x says"}
+    sparse = {}
+    for kind in ("bin", "int", "dbl"):
+        m = sp.Matrix.from_dense(config3_matrix(kind)).compress(1)
+        if (33 + 1 + m.nnz) % 2:
+            sparse[kind] = {"skipped": f"nov + 1 + nnz = {34 + m.nnz} is odd: the reference kernel faults with a misaligned "
+                                       "shared-memory address on this input"}
+            continue
+        mat = np.ascontiguousarray(m.mat)
+        s_, v = timed(lambda: lib.ref_gpu_sparse_multigpu(mat.ctypes.data_as(dp), m.cptrs.ctypes.data_as(ip), m.rows.ctypes.data_as(ip),
+                                                          m.cvals.ctypes.data_as(dp), 33, 1, 2048, 256))
+        sparse[kind] = {"wall_s": s_, "value": v}
+    ref["sparyser_n33_sortorder"] = sparse
+    print(json.dumps(ref), flush=True)
+    return 0
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -208,7 +411,9 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"dense Ryser n={N_DENSE} density {DENSITY} FP64, one full permanent (2^{N_DENSE - 1} Gray indices) per step, "
                                f"seeded synthetic matrix (seed {1000 * N_DENSE}); BASELINE.json configs[3]",
-                   "sample_per_step": sample},
+                   "sample_per_step": sample,
+                   "rate_note": "rate extrapolated from a slice: one step = the sample above, not a whole 2^35-index permanent "
+                                "(the CPU would need ~50 s per permanent); iterations/s is independent of the slice"},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -280,7 +485,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_DENSE, help="matrix order (default 36, the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the block with the other BASELINE configs")
+    ap.add_argument("--reference-gpu-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.reference_gpu_child:
+        return reference_gpu_child()
     if args.warmup < 3:
         args.warmup = 3   # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
@@ -401,6 +610,9 @@ def main():
     roofline = {
         "bound": "fp64_issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s (thread-level FP64)",
         "frac": achieved / peak,
+        # the same fraction on the 2n instructions the kernel executes per index, and against the nominal peak
+        "frac_executed_instr": achieved / peak * (2 * n) / (2 * n + 1),
+        "frac_vs_nominal": achieved / (148 * 64 * 1.965e9),
         # dram__bytes_read.sum + dram__bytes_write.sum of one ryser_reg_kernel<36,4,128,4> launch over 2^35
         # indices (ncu --set full, profiles/r01_ncu_dense.txt): 87 296 B read + 0 B written
         "traffic": 87296 if (n == 36 and world == 1) else None,
@@ -443,6 +655,19 @@ def main():
             "gpu_launches": int(launches_total),
             "clocks": clocks,
         }
+        if not args.no_configs:
+            sampler2 = ClockSampler(dev)
+            sampler2.start()
+            c0 = time.time()
+            try:
+                line["configs"] = extra_configs(sp, world, peak, dev)
+            except Exception as e:     # the headline line is printed whatever happens to the extras
+                line["configs"] = {"error": str(e)[:300]}
+            c1 = time.time()
+            time.sleep(0.15)
+            sampler2.stop()
+            line["configs"]["clocks"] = sampler2.summary(c0, c1)
+            line["configs"]["seconds"] = c1 - c0
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

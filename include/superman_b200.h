@@ -53,7 +53,7 @@ typedef struct sp_stats {
   /* approximations: sum over all trials of (estimate * sq_scale)^2 and that scale, from which std_error
    * is derived; `visited` counts the trials that reached the last step (the rest estimate 0) */
   double sumsq_scaled;
-  double sq_scale;
+  double sq_scale;             /* (sparse exact paths: the chosen engine's modelled FP64 instructions per index) */
 } sp_stats;
 
 const char *sp_last_error(void);
@@ -272,6 +272,8 @@ double sp_nw_factor(int nov);
 
 /* Measured FP64 instruction issue rate of a device (thread-level instr/s); roofline denominator. */
 double sp_fp64_peak(int device, int millis);
+/* Measured integer ALU issue rate (thread-level IADD3 / LOP3 instr/s): the estimators' roofline denominator. */
+double sp_int_peak(int device, int millis);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,8 @@ typedef struct spd_run_info {
   int path;                 /* SPD_PATH_* of the dominant kernel */
   int tile_log2;            /* log2 of the per-thread tile (exact register paths), else 0 */
   int reserved;
-  double aux0, aux1;        /* approximations: sum of (estimate*aux1)^2, and the scale aux1 */
+  double aux0, aux1;        /* approximations: sum of (estimate*aux1)^2, and the scale aux1;
+                             * SpaRyser / SkipPer: aux1 = the host model's FP64 instructions per Gray index */
 } spd_run_info;
 
 #define SPD_PATH_DENSE_REG      1   /* X in registers, templated on n            */
@@ -61,6 +62,9 @@ int         spd_device_sm_clock_khz(int device);  /* max SM clock */
  * `millis` ms and returns warp-level FP64 instructions * 32 per second (thread-level FP64
  * instr/s), the denominator of the dense roofline.  Negative on error. */
 double      spd_fp64_peak_instr_per_s(int device, int millis);
+/* Measured integer ALU issue rate (IADD3 / LOP3 chains), thread-level instr/s: what the estimators'
+ * instruction throughput is quoted against ("report against measured INT32 issue rate"). */
+double      spd_int_peak_instr_per_s(int device, int millis);
 
 /* ---- dense Ryser --------------------------------------------------------------------------- */
 typedef struct spd_dense_plan spd_dense_plan;

@@ -15,7 +15,7 @@ __all__ = [
     "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
     "SpStats", "dense_ryser", "dense_ryser_range", "DenseHandle", "permanent_compressed",
     "sparse_ryser", "skipper", "sparse_ryser_range",
-    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense", "approx_trace_sparse", "approx_trace_dense",
+    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense", "approx_trace_sparse", "approx_trace_dense", "int_peak",
     "gpu_perman64_rasmussen_sparse", "gpu_perman64_rasmussen_multigpucpu_chunks_sparse",
     "gpu_perman64_approximation_sparse", "gpu_perman64_approximation_multigpucpu_chunks_sparse",
     "gpu_perman64_rasmussen", "gpu_perman64_rasmussen_multigpucpu_chunks",
@@ -197,6 +197,13 @@ def nw_factor(nov: int) -> float:
 
 def fp64_peak(device: int = 0, millis: int = 200) -> float:
     r = lib.sp_fp64_peak(device, millis)
+    if r < 0:
+        raise SupermanError(-1, _ffi.last_error())
+    return r
+
+
+def int_peak(device: int = 0, millis: int = 200) -> float:
+    r = lib.sp_int_peak(device, millis)
     if r < 0:
         raise SupermanError(-1, _ffi.last_error())
     return r

@@ -257,6 +257,25 @@ fp64_probe_kernel(double* out, double a, double b, int iters) {
   if (s == 12345.678) out[0] = s;   // never true for the probe's inputs; keeps the chains alive
 }
 
+// ---- integer issue-rate probe ---------------------------------------------------------------------
+// 8 independent chains of (x + a) ^ b per thread: one IADD3 and one LOP3 per link, nothing else in the
+// loop.  The estimators (sp_approx.cu) are integer / bit-manipulation kernels with no FP64 to speak of;
+// the rate this sustains is the ceiling their instruction throughput is quoted against.
+__global__ void __launch_bounds__(256, 4)
+int_probe_kernel(unsigned* out, unsigned a, unsigned b, int iters) {
+  unsigned c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      c0 = (c0 + a) ^ b; c1 = (c1 + a) ^ b; c2 = (c2 + a) ^ b; c3 = (c3 + a) ^ b;
+      c4 = (c4 + a) ^ b; c5 = (c5 + a) ^ b; c6 = (c6 + a) ^ b; c7 = (c7 + a) ^ b;
+    }
+  }
+  const unsigned s = ((c0 ^ c1) + (c2 ^ c3)) ^ ((c4 + c5) ^ (c6 + c7));
+  if (s == 0x12345678u) out[0] = s;   // practically never; keeps the chains alive
+}
+
 }  // namespace spb
 
 using namespace spb;
@@ -305,6 +324,40 @@ int spd_device_sm_clock_khz(int device) {
   int v = 0;
   SPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device));
   return v;
+}
+
+double spd_int_peak_instr_per_s(int device, int millis) {
+  Lane* lp = nullptr;
+  if (lane_acquire(device, &lp) != SPD_OK) return -1.0;
+  Lane& lane = *lp;
+  cudaSetDevice(device);
+  const int threads = 256, blocks = lane.sm_count * 8;
+  const double per_iter = 16.0 * 8.0 * 2.0;   // IADD3 + LOP3 per link
+  auto run = [&](int iters, float* ms) -> int {
+    SPB_CUDA(cudaEventRecord(lane.ev0, lane.stream));
+    int_probe_kernel<<<blocks, threads, 0, lane.stream>>>(reinterpret_cast<unsigned*>(lane.d_result), 0x9E3779B9u, 0x85EBCA6Bu, iters);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(lane.ev1, lane.stream));
+    SPB_CUDA(cudaEventSynchronize(lane.ev1));
+    SPB_CUDA(cudaEventElapsedTime(ms, lane.ev0, lane.ev1));
+    return SPD_OK;
+  };
+  float ms = 0.f;
+  int iters = 2000;
+  double best = -1.0;
+  if (run(iters, &ms) == SPD_OK && run(iters, &ms) == SPD_OK && ms > 0.f) {
+    double scale = (double)(millis > 0 ? millis : 50) / ms;
+    long long it2 = (long long)(iters * scale);
+    if (it2 < 1000) it2 = 1000;
+    if (it2 > 50000000) it2 = 50000000;
+    for (int rep = 0; rep < 3; ++rep) {
+      if (run((int)it2, &ms) != SPD_OK) { best = -1.0; break; }
+      const double rate = per_iter * (double)it2 * (double)threads * (double)blocks / (ms * 1e-3);
+      if (rate > best) best = rate;
+    }
+  }
+  lane_release(lp);
+  return best;
 }
 
 double spd_fp64_peak_instr_per_s(int device, int millis) {

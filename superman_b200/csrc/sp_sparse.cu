@@ -62,6 +62,7 @@ struct spd_sparse_plan {
   // LevelRyser image (level_reg.cuh); lvB == 0 when the matrix does not fit its slots
   int lvB = 0, lvS0 = 0, lvS = 0, lvR = 0, NC = 0, NCP = 0, HSP = 0;
   double lv_cost = 1e300, hc_cost = 1e300;
+  double lv_instr = 0.0;       // FP64 instructions per Gray index of the chosen LevelRyser configuration (model)
   double *d_colT_hot = nullptr, *d_lowR = nullptr, *d_dcold = nullptr, *d_xb_hot = nullptr, *d_xb_cold = nullptr;
   int* d_cold_start = nullptr;
   bool pending = false;
@@ -370,10 +371,11 @@ int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase
           double cost = 0;
           if (!level_pack(n, B, S0, S, R, lvl, dmat_t, xbase, h, l, d, xh, xc, cs, &NC, &cost)) continue;
           fits = true;
+          const double raw = cost;
           cost *= 1.15;
           if (level_minblocks(B, S0, S, p->skip != 0) < 4) cost *= 1.1;      // 3 instead of 4 blocks per SM
           if (cost < p->lv_cost) {
-            p->lv_cost = cost; p->lvB = B; p->lvS0 = S0; p->lvS = S; p->lvR = R; p->NC = NC;
+            p->lv_cost = cost; p->lv_instr = raw; p->lvB = B; p->lvS0 = S0; p->lvS = S; p->lvR = R; p->NC = NC;
             bh.swap(h); bl.swap(l); bd.swap(d); bxh.swap(xh); bxc.swap(xc); bcs.swap(cs);
           }
           break;   // more level-0 slots for the same S only cost more
@@ -434,6 +436,10 @@ int spd_sparse_plan_wait(spd_sparse_plan* p, double* sum, spd_run_info* info) {
     memcpy(&blocks, &p->lanep->h_result[1], sizeof(blocks));
     p->info.visited += blocks << p->info.reserved;
   }
+  // the host model's FP64 instructions per index of the engine that ran (0 for the shared-memory kernel):
+  // what a roofline fraction of the sparse paths is quoted with
+  if (p->info.path == SPD_PATH_SPARSE_REG || p->info.path == SPD_PATH_SKIPPER)
+    p->info.aux1 = p->lvB ? p->lv_instr : std::min(hotcold_cost(p, 3), hotcold_cost(p, 4));
   if (sum) *sum = p->lanep->h_result[0];
   if (info) *info = p->info;
   return SPD_OK;

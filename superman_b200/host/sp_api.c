@@ -30,6 +30,12 @@ int sp_device_count(void) {
   return n;
 }
 
+double sp_int_peak(int device, int millis) {
+  double r = spd_int_peak_instr_per_s(device, millis);
+  if (r < 0) sp_set_error("%s", spd_last_error());
+  return r;
+}
+
 double sp_nw_factor(int nov) { return (double)(4 * (nov & 1) - 2); }
 
 double sp_fp64_peak(int device, int millis) {
