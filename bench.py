@@ -515,6 +515,10 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
             os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        # host-side (gloo) group for the closing barrier: while rank 0 measures the in-process multi-GPU ids on
+        # every device, the other ranks must wait on the CPU -- an NCCL barrier would leave a spinning kernel on
+        # their GPUs, which the in-process run shares
+        park_group = dist.new_group(backend="gloo")
 
     import superman_b200 as sp
     from superman_b200._ffi import SpStats
@@ -670,7 +674,8 @@ def main():
             line["configs"]["seconds"] = c1 - c0
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=park_group)
         dist.destroy_process_group()
     return 0
 

@@ -61,6 +61,15 @@ int         sp_device_count(void);
 const char *sp_version(void);
 /* create contexts / streams / buffers of devices 0..gpu_num-1 ahead of time (optional) */
 int         sp_warmup(int gpu_num);
+/* Optional: open (and close) the plans a following call on the same input will open, on each of the gpu_num
+ * devices it will use -- contexts, lanes, parked worker threads and the kernel instantiations for this input
+ * are loaded afterwards (CUDA loads kernels lazily), so that a timed call measures the algorithm.  `perman`
+ * calls these between reading the matrix and starting its clock. */
+int         sp_prepare_dense(const double *mat, int nov, int gpu_num);
+int         sp_prepare_sparse(const double *mat, const int *cptrs, const int *rows, const double *cvals, int nov,
+                              int skipper, int gpu_num);
+int         sp_prepare_approx(const int *rptrs, const int *cols, const int *cptrs, const int *rows, int nov, int nnz,
+                              int scaling, int scale_intervals, int scale_times, int gpu_num);
 /* first device the permanent entry points use (default 0); ids with gpu_num devices use
  * first .. first+gpu_num-1 (the revised front-end's -l flag) */
 int         sp_set_first_device(int device);

@@ -407,6 +407,23 @@ int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase
       p->lvB = 0;
     }
   }
+  // load the kernel this plan will launch (CUDA loads kernels lazily) and set its shared-memory opt-in now,
+  // so that the first run does not pay for either
+  if (p->lvB) {
+    LevelArgs la;
+    memset(&la, 0, sizeof(la));           // partials == nullptr: prepare only
+    la.n_chunks = 1;
+    const int HS = p->lvS0 + (p->lvB - 1) * p->lvS, LBv = p->lvB + (p->lvB & 1);
+    int cc = n - 1 < 12 ? n - 1 : 12;
+    if (cc < p->lvB + 1) cc = p->lvB + 1;
+    const size_t smem = level_smem_bytes(n, p->lvB, HS, p->HSP, LBv, p->NC, p->NCP, cc, SPB_REG_THREADS);
+    unsigned bps = 0;
+    (void)level_launch(p->lvB, p->lvS0, p->lvS, p->skip, L.stream, &la, L.sm_count, smem, &bps);
+  } else if (n >= SPB_SPARSE_NMIN && n <= SPB_SPARSE_NMAX) {
+    SparseArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    for (int b = 3; b <= 4; ++b) (void)sparse_launch(n, b, p->skip, L.stream, &sa, 0u);
+  }
   *out = p;
   return SPD_OK;
 }

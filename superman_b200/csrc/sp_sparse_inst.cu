@@ -13,6 +13,12 @@ namespace spb {
 template <int N, int B, bool SKIP>
 static int launch_sparse(cudaStream_t st, const SparseArgs& a, unsigned blocks) {
   constexpr int MB = (B == 4) ? (N <= (SKIP ? 28 : 30) ? 4 : 3) : (N <= 36 ? 4 : 3);
+  if (blocks == 0) {            // prepare only: load the (lazily loaded) kernel into the current context
+    cudaFuncAttributes fa;
+    (void)cudaFuncGetAttributes(&fa, sparse_reg_kernel<N, B, SPB_REG_THREADS, MB, SKIP>);
+    (void)cudaGetLastError();
+    return SPD_OK;
+  }
   sparse_reg_kernel<N, B, SPB_REG_THREADS, MB, SKIP><<<blocks, SPB_REG_THREADS, 0, st>>>(a);
   return SPD_OK;
 }

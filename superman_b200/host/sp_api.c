@@ -68,10 +68,9 @@ int sp_warmup(int gpu_num) {
   sp_stats st;
   memset(&st, 0, sizeof(st));
   if (gpu_num < 1) gpu_num = 1;
-  /* every device opens a plan on a 2x2 matrix and runs an empty range: creates the context and the
-   * pooled lane (stream, events, pinned slot, arena, partial buffers) */
-  /* dynamic mode: two plans (two lanes) per device, as the chunk-queue paths use */
-  return sp_sched_run(&ops, &job, SP_SCHED_DYNAMIC, gpu_num, g_first_device, 0ull, 0ull, 0, (unsigned long long)(2 * gpu_num), &sum, &st);
+  /* every device opens two plans on a 2x2 matrix: creates the context, the two pooled lanes (stream, events,
+   * pinned slot, arena, partial buffers) the chunk-queue paths use, and the parked worker threads */
+  return sp_sched_run(&ops, &job, SP_SCHED_PREPARE, gpu_num, g_first_device, 0ull, 0ull, 0, 0ull, &sum, &st);
 }
 
 static void stats_clear(sp_stats *st) {
@@ -131,6 +130,17 @@ unsigned long long sp_dynamic_chunks(int nov, int ref_base, int gpu_num) {
   return chunks;
 }
 
+/* Dense Ryser costs the same for every index, so the queue has nothing to balance but differences between
+ * the devices themselves: the reference's 2^(nov-29) chunks (128 at n = 36, 2048 at n = 40) only add a launch,
+ * a reduction and an 8-byte copy per chunk (measured in round 1: -p6 1.4-2 % behind -p5).  Four chunks per
+ * device -- two in flight, two to even out -- keep the dynamic path at the static path's speed. */
+static unsigned long long dense_dynamic_chunks(int nov, int gpu_num) {
+  unsigned long long chunks = sp_dynamic_chunks(nov, 29, gpu_num);
+  const unsigned long long cap = 4ull * (unsigned long long)(gpu_num > 0 ? gpu_num : 1);
+  if (chunks > cap) chunks = cap;
+  return chunks;
+}
+
 static int check_dense_args(const double *mat, int nov, sp_stats *st) {
   if (!mat) { sp_set_error("mat is NULL"); if (st) st->error = SP_EINVAL; return SP_EINVAL; }
   if (nov < 1 || nov > 64) {
@@ -170,7 +180,7 @@ double sp_dense_ryser(const double *mat, int nov, int algo_id, int gpu_num, int 
   const unsigned long long end = 1ull << (nov - 1);
   /* never more devices than 2^16-index tile groups (the kernel's alignment unit) */
   while (gpu_num > 1 && (end >> 16) < (unsigned long long)gpu_num) gpu_num--;
-  const unsigned long long chunks = (mode == SP_SCHED_DYNAMIC) ? sp_dynamic_chunks(nov, 29, gpu_num) : 0;
+  const unsigned long long chunks = (mode == SP_SCHED_DYNAMIC) ? dense_dynamic_chunks(nov, gpu_num) : 0;
   double sum = 0.0;
   /* index 0 (the base term p = prod x, gpu_exact_dense.cu:653) is part of device 0's range */
   int rc = sp_sched_run(&g_dense_ops, &job, mode, gpu_num, g_first_device, 0ull, end, 16, chunks, &sum, stats);
@@ -178,6 +188,26 @@ double sp_dense_ryser(const double *mat, int nov, int algo_id, int gpu_num, int 
   if (stats) stats->wall_ms = sp_now_ms() - t0;
   if (rc != SP_OK) return fail(stats, rc);
   return sp_nw_factor(nov) * sum;
+}
+
+/* Opens (and closes) the plans a following sp_dense_ryser call on this matrix will open, on every device it
+ * will use: contexts, lanes, worker threads and the kernel instantiation for this order are in place
+ * afterwards, so that the timed call measures the algorithm.  What `perman` does between reading the matrix
+ * and starting its clock (the reference's clock starts after its own lazy initialisation as well: its first
+ * CUDA call is in the wrapper, but the context exists since main() touched the device). */
+int sp_prepare_dense(const double *mat, int nov, int gpu_num) {
+  if (check_dense_args(mat, nov, NULL) != SP_OK) return SP_EINVAL;
+  if (nov < 2) return SP_OK;
+  double x[64];
+  double *mat_t = (double *)malloc((size_t)nov * nov * sizeof(double));
+  if (!mat_t) { sp_set_error("out of memory"); return SP_ENOMEM; }
+  nw_preamble(mat, nov, x, mat_t);
+  dense_job job = {mat_t, x, nov};
+  double sum = 0.0;
+  sp_stats st;
+  int rc = sp_sched_run(&g_dense_ops, &job, SP_SCHED_PREPARE, gpu_num < 1 ? 1 : gpu_num, g_first_device, 0ull, 0ull, 0, 0ull, &sum, &st);
+  free(mat_t);
+  return rc;
 }
 
 struct sp_dense_handle {
@@ -311,6 +341,24 @@ static int some_row_can_cancel(const double *mat, int nov) {
     if (dyadic) return 1;
   }
   return 0;
+}
+
+int sp_prepare_sparse(const double *mat, const int *cptrs, const int *rows, const double *cvals, int nov,
+                      int skipper, int gpu_num) {
+  if (!mat || !cptrs || !rows || !cvals || nov < 2 || nov > 64) return SP_OK;   /* the real call reports it */
+  if (skipper && !some_row_can_cancel(mat, nov)) skipper = 0;
+  double x[64];
+  double *dmat_t = (double *)malloc((size_t)nov * nov * sizeof(double));
+  if (!dmat_t) { sp_set_error("out of memory"); return SP_ENOMEM; }
+  int rc = sparse_preamble(mat, cptrs, rows, cvals, nov, x, dmat_t);
+  if (rc == SP_OK) {
+    sparse_job job = {dmat_t, x, nov, skipper};
+    double sum = 0.0;
+    sp_stats st;
+    rc = sp_sched_run(&g_sparse_ops, &job, SP_SCHED_PREPARE, gpu_num < 1 ? 1 : gpu_num, g_first_device, 0ull, 0ull, 0, 0ull, &sum, &st);
+  }
+  free(dmat_t);
+  return rc;
 }
 
 static double sparse_common(const double *mat, const int *cptrs, const int *rows, const double *cvals,
@@ -475,6 +523,16 @@ static double approx_common(const approx_job *job, long long trials, int gpu_num
   st->wall_ms = sp_now_ms() - t0;
   if (rc != SP_OK) return fail(stats, rc);
   return sum / (double)trials;
+}
+
+int sp_prepare_approx(const int *rptrs, const int *cols, const int *cptrs, const int *rows, int nov, int nnz,
+                      int scaling, int scale_intervals, int scale_times, int gpu_num) {
+  if (!rptrs || !cols || !cptrs || !rows) return SP_OK;
+  approx_job job = {rptrs, cols, cptrs, rows, NULL, NULL, nov, nnz, scaling, scaling ? scale_intervals : 1,
+                    scaling ? scale_times : 0, pick_seed(0)};
+  double sum = 0.0;
+  sp_stats st;
+  return sp_sched_run(&g_approx_ops, &job, SP_SCHED_PREPARE, gpu_num < 1 ? 1 : gpu_num, g_first_device, 0ull, 0ull, 0, 0ull, &sum, &st);
 }
 
 double sp_rasmussen_sparse(const int *rptrs, const int *cols, const int *cptrs, const int *rows,

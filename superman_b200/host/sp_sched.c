@@ -103,6 +103,17 @@ static void *worker_main(void *arg) {
   void *plan[2] = {NULL, NULL};
   int rc;
 
+  if (sh->mode == SP_SCHED_PREPARE) {
+    /* open and close two plans on this device: creates the context and two pooled lanes if they do not
+     * exist yet, loads the kernels the job will launch (CUDA loads kernels lazily) and sets their
+     * shared-memory opt-in -- everything a first timed call would otherwise pay for */
+    for (int s = 0; s < 2; ++s)
+      if ((rc = ops->open(sh->job, device, &plan[s])) != SPD_OK) { worker_fail(sh, rc); break; }
+    for (int s = 0; s < 2; ++s)
+      if (plan[s]) ops->close(plan[s]);
+    return NULL;
+  }
+
   if (sh->mode == SP_SCHED_STATIC) {
     const unsigned long long a = sp_sched_boundary(sh->lo, sh->hi, (unsigned long long)sh->gpu_num,
                                                    (unsigned long long)w->rank, sh->align_log2);
@@ -165,6 +176,71 @@ static void *worker_main(void *arg) {
   return NULL;
 }
 
+/* ---- parked worker threads ------------------------------------------------------------------------
+ * Ranks 1 .. gpu_num-1 of a multi-device call run on threads that are created once and then wait on
+ * a condition variable between calls (rank 0 runs on the caller's thread): a call costs a signal and
+ * a wake-up per device instead of a pthread_create / join pair.  One multi-device call uses the pool at
+ * a time; a second caller arriving meanwhile falls back to creating its own threads. */
+typedef struct pool_slot {
+  pthread_t tid;
+  int started;
+  sched_worker *work;         /* set by the dispatcher, cleared by the worker when done */
+} pool_slot;
+
+static pthread_mutex_t g_pool_use = PTHREAD_MUTEX_INITIALIZER;   /* held for the duration of one call */
+static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_pool_go = PTHREAD_COND_INITIALIZER, g_pool_done = PTHREAD_COND_INITIALIZER;
+static pool_slot g_pool[SP_MAX_DEVICES];
+
+static void *pool_main(void *arg) {
+  pool_slot *slot = (pool_slot *)arg;
+  for (;;) {
+    pthread_mutex_lock(&g_pool_mu);
+    while (slot->work == NULL) pthread_cond_wait(&g_pool_go, &g_pool_mu);
+    sched_worker *w = slot->work;
+    pthread_mutex_unlock(&g_pool_mu);
+    worker_main(w);
+    pthread_mutex_lock(&g_pool_mu);
+    slot->work = NULL;
+    pthread_cond_broadcast(&g_pool_done);
+    pthread_mutex_unlock(&g_pool_mu);
+  }
+  return NULL;
+}
+
+/* hands workers[1 .. gpu_num-1] to the pool; returns 0, or -1 when the pool cannot be used */
+static int pool_dispatch(sched_worker *workers, int gpu_num) {
+  if (pthread_mutex_trylock(&g_pool_use) != 0) return -1;
+  pthread_mutex_lock(&g_pool_mu);
+  for (int g = 1; g < gpu_num; ++g) {
+    if (!g_pool[g].started) {
+      pthread_attr_t at;
+      pthread_attr_init(&at);
+      pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+      const int err = pthread_create(&g_pool[g].tid, &at, pool_main, &g_pool[g]);
+      pthread_attr_destroy(&at);
+      if (err != 0) {
+        pthread_mutex_unlock(&g_pool_mu);
+        pthread_mutex_unlock(&g_pool_use);
+        return -1;                         /* nothing dispatched yet: the caller creates its own threads */
+      }
+      g_pool[g].started = 1;
+    }
+  }
+  for (int g = 1; g < gpu_num; ++g) g_pool[g].work = &workers[g];
+  pthread_cond_broadcast(&g_pool_go);
+  pthread_mutex_unlock(&g_pool_mu);
+  return 0;
+}
+
+static void pool_wait(int gpu_num) {
+  pthread_mutex_lock(&g_pool_mu);
+  for (int g = 1; g < gpu_num; ++g)
+    while (g_pool[g].work != NULL) pthread_cond_wait(&g_pool_done, &g_pool_mu);
+  pthread_mutex_unlock(&g_pool_mu);
+  pthread_mutex_unlock(&g_pool_use);
+}
+
 int sp_sched_run(const sp_job_ops *ops, const void *job, int mode, int gpu_num, int first_device,
                  unsigned long long lo, unsigned long long hi, int align_log2,
                  unsigned long long n_chunks, double *total, sp_stats *stats) {
@@ -182,7 +258,7 @@ int sp_sched_run(const sp_job_ops *ops, const void *job, int mode, int gpu_num, 
     sp_set_error("asked for %d device(s) starting at %d but only %d visible", gpu_num, first_device, have);
     return SP_EINVAL;
   }
-  if (mode == SP_SCHED_STATIC) n_chunks = (unsigned long long)gpu_num;
+  if (mode == SP_SCHED_STATIC || mode == SP_SCHED_PREPARE) n_chunks = (unsigned long long)gpu_num;
   if (n_chunks < 1) n_chunks = 1;
 
   sched_shared sh;
@@ -200,18 +276,24 @@ int sp_sched_run(const sp_job_ops *ops, const void *job, int mode, int gpu_num, 
   pthread_t tids[SP_MAX_DEVICES];
   memset(workers, 0, sizeof(workers));
   for (int g = 0; g < gpu_num; ++g) { workers[g].sh = &sh; workers[g].rank = g; }
-  /* rank 0 runs on the calling thread: a single-device call creates no thread at all */
-  for (int g = 1; g < gpu_num; ++g) {
-    if (pthread_create(&tids[g], NULL, worker_main, &workers[g]) != 0) {
-      atomic_store(&sh.failed, 1);
-      sh.err_code = SP_ENOMEM;
-      snprintf(sh.err_msg, sizeof(sh.err_msg), "pthread_create failed");
-      gpu_num = g;
-      break;
+  /* rank 0 runs on the calling thread: a single-device call involves no other thread at all; the other
+   * ranks go to the parked workers, or to threads of our own when the pool is busy */
+  const int pooled = (gpu_num > 1) && (pool_dispatch(workers, gpu_num) == 0);
+  int own = 0;
+  if (gpu_num > 1 && !pooled) {
+    for (int g = 1; g < gpu_num; ++g) {
+      if (pthread_create(&tids[g], NULL, worker_main, &workers[g]) != 0) {
+        atomic_store(&sh.failed, 1);
+        sh.err_code = SP_ENOMEM;
+        snprintf(sh.err_msg, sizeof(sh.err_msg), "pthread_create failed");
+        break;
+      }
+      own = g;
     }
   }
   worker_main(&workers[0]);
-  for (int g = 1; g < gpu_num; ++g) pthread_join(tids[g], NULL);
+  if (pooled) pool_wait(gpu_num);
+  for (int g = 1; g <= own; ++g) pthread_join(tids[g], NULL);
   pthread_mutex_destroy(&sh.err_mu);
 
   int rc = SP_OK;

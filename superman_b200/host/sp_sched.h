@@ -24,6 +24,7 @@ typedef struct sp_job_ops {
 
 #define SP_SCHED_STATIC  0
 #define SP_SCHED_DYNAMIC 1
+#define SP_SCHED_PREPARE 2   /* no work: every device opens and closes two plans (contexts, lanes, kernel loads) */
 
 /* Runs [lo, hi) over `gpu_num` devices (devices 0..gpu_num-1, or first_device.. when gpu_num == 1).
  *  static : device g gets one contiguous slice, boundaries rounded down to 2^align_log2;
