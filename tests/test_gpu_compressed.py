@@ -183,7 +183,9 @@ def test_real_matrices_with_recorded_permanents(sp):
     14 digits for ten different reduction trees (transpose, permutations, leaf sizes).  will57 is only
     reachable through -o (2^56 indices directly): ~2300 leaves, 2 s on one B200, the same value to 15
     digits over ten reduction trees; the kit's two recorded values disagree with each other by 6 % and
-    are 6.5-6.9 times larger."""
+    are 6.5-6.9 times larger -- and wrong: the exact integer permanents of both matrices (Python-integer
+    transfer-matrix DP, tools/exact_permanent_dp.py) are 13 173 481 190 272 and 1 070 536 592 880 585 216,
+    which the -o path reproduces to 1e-12."""
     import _golden
     d = _golden.known_perman()
     assert set(d) >= {"chesapeake", "will57"}
@@ -211,6 +213,11 @@ def test_real_matrices_with_recorded_permanents(sp):
     assert scaled == pytest.approx(ref, rel=1e-9)
     if "ld_recursion" in e:
         assert ref == pytest.approx(e["ld_recursion"], rel=1e-11)
+    # the exact value: tools/exact_permanent_dp.py, a transfer-matrix DP in Python integers that shares
+    # nothing with the library (checked against the __int128 Ryser oracle in tests/test_oracle.py)
+    assert int(e["exact"]) == 13173481190272
+    assert round(ref) == int(e["exact"])
+    assert abs(ref / float(int(e["exact"])) - 1.0) < 1e-12
 
     e = d["will57"]
     a = _golden.dense_from(e)
@@ -221,9 +228,16 @@ def test_real_matrices_with_recorded_permanents(sp):
     v3 = sp.permanent_compressed(a.T.copy(), sparse=True, preprocessing=2, algo_id=7, leaf_nov=32)
     assert st.chunks > 1000 and st.error == 0
     assert v2 == pytest.approx(v1, rel=1e-12) and v3 == pytest.approx(v1, rel=1e-12)
-    assert v1 == pytest.approx(1.070536592880585e18, rel=1e-12)
     if "ld_recursion" in e:
         assert v1 == pytest.approx(e["ld_recursion"], rel=1e-11)
+    # exact: 1 070 536 592 880 585 216 (tools/exact_permanent_dp.py, 0.1 s in Python integers).  The two values
+    # the reference's kit recorded for this matrix (7.39e18 and 6.95e18, 6 % apart from each other) are wrong.
+    exact = int(e["exact"])
+    assert exact == 1070536592880585216
+    for v in (v1, v2, v3):
+        assert abs(v / float(exact) - 1.0) < 1e-12, (v, exact)
+    for r in e["recorded"].values():
+        assert float(r["perman"]) / exact > 6.0
 
 
 def test_extreme_row_and_column_scales(sp, oracle):

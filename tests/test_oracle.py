@@ -1,6 +1,7 @@
 """CPU: pins the oracle (oracle/*.c) against closed forms, the committed golden vectors produced by
 the unmodified reference, and -- when oracle/_ref/libref.so is present -- the reference itself."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -188,3 +189,23 @@ def test_closed_form_families_against_the_oracle(oracle):
     for sizes, kind in (([4, 5], "int"), ([3, 3, 4], "bin"), ([7, 9], "int")):
         A, exact = cf.block_diagonal(rng, oracle, sizes, kind)
         assert oracle.perm_i128(A.astype(int)) == exact
+
+
+def test_exact_transfer_matrix_dp(oracle):
+    """tools/exact_permanent_dp.py (the product-independent exact evaluator behind known_perman.json's `exact`
+    fields) against the __int128 Ryser oracle on random sparse integer matrices, and on will57 itself
+    (57 x 57: 0.1 s; chesapeake takes two minutes and is only stored)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from exact_permanent_dp import exact_permanent, load
+    rng = np.random.default_rng(12)
+    for n in (4, 8, 13, 18):
+        for p in (0.25, 0.5):
+            A = (rng.random((n, n)) < p) * rng.integers(1, 4, (n, n))
+            A[np.arange(n), rng.permutation(n)] = 1
+            assert exact_permanent(A.tolist()) == oracle.perm_i128(A), (n, p)
+    Z = np.ones((5, 5), dtype=int); Z[2, :] = 0
+    assert exact_permanent(Z.tolist()) == 0
+    import _golden
+    e = _golden.known_perman()["will57"]
+    assert exact_permanent(load("will57")) == int(e["exact"]) == 1070536592880585216
