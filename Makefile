@@ -13,6 +13,7 @@ BUILD   := build
 PKG     := superman_b200
 LIB     := $(PKG)/libsuperman_b200.so
 CLI     := $(PKG)/perman
+CONNECT := $(PKG)/libConnect.so
 
 GROUPS  := 0 1 2 3 4 5 6 7
 CU_SRCS := sp_device sp_dense sp_sparse sp_approx
@@ -20,7 +21,7 @@ CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(BUILD)/sp_level_inst_b3s0.o $(BUILD)/sp_l
 C_SRCS  := sp_sched sp_api sp_matrix sp_reduce sp_connector
 C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
 
-all: $(LIB) $(CLI) profiles/resource_usage.txt
+all: $(LIB) $(CLI) $(CONNECT) profiles/resource_usage.txt
 
 # registers / stack (spills) / shared memory of every shipped kernel, regenerated from the linked library
 profiles/resource_usage.txt: $(LIB) tools/resource_report.py
@@ -55,10 +56,15 @@ $(LIB): $(CU_OBJS) $(C_OBJS)
 $(CLI): $(PKG)/host/perman_main.c $(LIB) include/superman_b200.h
 	$(CC) -O2 -std=c11 -Wall -Wextra -Iinclude -o $@ $< -L$(PKG) -lsuperman_b200 -lm -Wl,-rpath,'$$ORIGIN'
 
+# the file the reference's bindings load by name (superPython.py, supermaTlab.m): reference symbol names,
+# forwarding to $(LIB)
+$(CONNECT): $(PKG)/host/libconnect.c $(LIB) include/superman_b200.h
+	$(CC) -O2 -std=c11 -fPIC -shared -Wall -Wextra -Iinclude -Wl,-Bsymbolic -o $@ $< -L$(PKG) -lsuperman_b200 -Wl,-rpath,'$$ORIGIN'
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(BUILD) $(LIB) $(CLI)
+	rm -rf $(BUILD) $(LIB) $(CLI) $(CONNECT)
 
 .PHONY: all oracle clean

@@ -269,9 +269,13 @@ double sp_approx_trace_dense(const double *mat, int nov, int scaling, int scale_
 /* ---------------------------------------------------------------------------------------------
  * The reference's Python / MATLAB shim on the GPU engine (interface_connector.c:61-231,
  * matlab_calculate_return.h:4,12,20): same names and arguments; see superman_b200/host/sp_connector.c
- * for the algorithm numbering and the two defects fixed.  `connect()` is exported as sp_connect().
+ * for the algorithm numbering and the two defects fixed.  `connect()` is exported as sp_connect() here and
+ * under its own name by libConnect.so (host/libconnect.c), the file the reference's bindings load.
  * ------------------------------------------------------------------------------------------- */
 void   sp_connect(void);
+double sp_read_calculate_return(char *filename, int algorithm, int nt, int x, int y, int z);
+double sp_matlab_calculate_return_int(int *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz);
+double sp_matlab_calculate_return_double(double *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz);
 double read_calculate_return(char *filename, int algorithm, int nt, int x, int y, int z);
 double matlab_calculate_return_int(int *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz);
 double matlab_calculate_return_double(double *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz);

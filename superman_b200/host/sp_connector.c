@@ -14,8 +14,11 @@
  * ignored.  Two defects of the shim are fixed: the result is returned as a double (the shim
  * truncates it through `int perman`, :22), and matrix values are honoured (the shim forces every
  * entry to 1, `generic = 0`, :76) -- set SP_CONNECT_BINARY=1 for the old 0/1 behaviour.
- * The shim's `connect()` is exported as sp_connect(): a library that defines `connect` would
- * shadow the socket call of every process that loads it.
+ * The shim's `connect()` is exported from this library as sp_connect(): a library that defines `connect`
+ * and is linked into a process would shadow the socket call.  The file the reference's bindings actually
+ * load, libConnect.so (superPython.py:6-7, supermaTlab.m), is built next to this library from
+ * host/libconnect.c: it exports `connect` and the three entry points under their reference names and
+ * forwards here; it is only ever dlopen'ed (ctypes / loadlibrary: RTLD_LOCAL), never linked.
  */
 #define _POSIX_C_SOURCE 200809L
 #include "superman_b200.h"
@@ -57,7 +60,7 @@ static double decide_and_call(sp_matrix *m, int algorithm, int x, int y, int z) 
   }
 }
 
-double read_calculate_return(char *filename, int algorithm, int nt, int x, int y, int z) {
+double sp_read_calculate_return(char *filename, int algorithm, int nt, int x, int y, int z) {
   (void)nt;
   sp_matrix m;
   if (sp_matrix_read(filename, connector_binary(), &m) != SP_OK) return NAN;
@@ -78,13 +81,13 @@ static double from_dense(const double *mat, int nov, int algorithm, int x, int y
   return r;
 }
 
-double matlab_calculate_return_double(double *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz) {
+double sp_matlab_calculate_return_double(double *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz) {
   (void)nt; (void)nnz;
   if (!mat || nov < 1) { sp_set_error("bad matrix"); return NAN; }
   return from_dense(mat, nov, algorithm, x, y, z);
 }
 
-double matlab_calculate_return_int(int *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz) {
+double sp_matlab_calculate_return_int(int *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz) {
   (void)nt; (void)nnz;
   if (!mat || nov < 1 || nov > SP_MAX_NOV) { sp_set_error("bad matrix"); return NAN; }
   double *d = (double *)malloc((size_t)nov * nov * sizeof(double));
@@ -93,4 +96,15 @@ double matlab_calculate_return_int(int *mat, int algorithm, int nt, int x, int y
   const double r = from_dense(d, nov, algorithm, x, y, z);
   free(d);
   return r;
+}
+
+/* the reference's own names, kept in this library as well (libConnect.so forwards to the sp_ names above) */
+double read_calculate_return(char *filename, int algorithm, int nt, int x, int y, int z) {
+  return sp_read_calculate_return(filename, algorithm, nt, x, y, z);
+}
+double matlab_calculate_return_double(double *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz) {
+  return sp_matlab_calculate_return_double(mat, algorithm, nt, x, y, z, nov, nnz);
+}
+double matlab_calculate_return_int(int *mat, int algorithm, int nt, int x, int y, int z, int nov, int nnz) {
+  return sp_matlab_calculate_return_int(mat, algorithm, nt, x, y, z, nov, nnz);
 }

@@ -216,3 +216,16 @@ def test_wide_corpus_files_read_back_exactly(sp, tmp_path):
                 assert np.array_equal(m.mat, A)
             else:   # a row / column permutation of the same entries
                 assert np.array_equal(np.sort(m.mat, axis=None), np.sort(A, axis=None))
+
+
+def test_libconnect_exports_the_reference_names():
+    """superman_b200/libConnect.so: the file and the four symbols the reference's bindings load
+    (interface_connector.c:61-231, superPython.py:6-7)"""
+    so = os.path.join(ROOT, "superman_b200", "libConnect.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    for sym in ("connect", "read_calculate_return", "matlab_calculate_return_int", "matlab_calculate_return_double"):
+        assert re.search(r" T %s$" % sym, out, flags=re.M), sym
+    lib = C.CDLL(so)               # loads (RTLD_LOCAL) and resolves libsuperman_b200.so through its rpath
+    lib.read_calculate_return.restype = C.c_double
+    v = lib.read_calculate_return(b"/nonexistent", 5, 1, 1, 1, 1)
+    assert v != v                  # NaN: no such file (and no compute without a GPU)
