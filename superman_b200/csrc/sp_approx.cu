@@ -26,11 +26,12 @@
 #include "sp_internal.cuh"
 #include <string.h>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 namespace spb {
 
-#define APX_WARPS 8
+#define APX_WARPS 16
 #define APX_THREADS (APX_WARPS * 32)
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -55,9 +56,8 @@ struct ApproxArgs {
   const double* rvals; const double* cvals;  // entry weights (dense twins) or nullptr
   const unsigned short* ell_rows;      // [nov * W] rows of column j, CCS order, padded with nov (W > 0 only)
   const unsigned short* ell_cols;      // [nov * W] columns of row i, CRS order, padded with nov
-  double* partial_sum;                 // per block: sum of estimates
-  double* partial_sq;                  // per block: sum of (estimate * sq_scale)^2
-  unsigned long long* partial_alive;   // per block: trials that reached the last step
+  double* est;                         // [trial_hi - trial_lo] every trial's estimate (0 for a dead end)
+  unsigned int* queue;                 // next trial to hand out, relative to trial_lo (zeroed before the launch)
   double* trace;                       // tests only (else nullptr): per trial {steps completed, running product}
   unsigned long long trial_lo, trial_hi;
   unsigned long long seed;
@@ -75,52 +75,77 @@ __device__ __forceinline__ bool bit_test(const unsigned* m, int i) { return (m[i
 // pattern in ELL form, W 16-bit indices per row / column padded with the index nov, whose scaling
 // factor is a constant 0 -- fixed trip count, no pointer loads, and adding the padding's exact
 // zeros after the real entries leaves every float sum bit-identical.
-template <bool WEIGHTED, int W>
-__global__ void __launch_bounds__(APX_THREADS)
+// With W > 0 the ELL arrays are the only copy of the pattern in shared memory (the column pick and the degree
+// updates read them too), which together with byte-sized degrees (WIDE = false: no row has more than 255
+// entries) lets 32 warps = 32 concurrent trials share an SM on the 36 x 36 grid instead of 16.
+template <bool WEIGHTED, int W, bool WIDE>
+__global__ void __launch_bounds__(APX_THREADS, 2)
 approx_kernel(const ApproxArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int nov = a.nov, nnz = a.nnz;
+  typedef typename std::conditional<WIDE, unsigned short, unsigned char>::type deg_t;
+  const int nov = a.nov, nnz = (W > 0) ? 0 : a.nnz;
   const int words = (nov + 31) >> 5;
-  // block-shared pattern
+  // block-shared pattern (CRS + CCS; absent when the ELL form is used)
   int* s_rptrs = reinterpret_cast<int*>(smraw);
-  int* s_cptrs = s_rptrs + (nov + 1);
-  int* s_cols = s_cptrs + (nov + 1);
+  int* s_cptrs = s_rptrs + (W > 0 ? 0 : nov + 1);
+  int* s_cols = s_cptrs + (W > 0 ? 0 : nov + 1);
   int* s_rows = s_cols + nnz;
-  size_t off = (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
+  size_t off = (W > 0) ? 0 : (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
   off = (off + 15) & ~(size_t)15;
   unsigned short* s_ell_rows = reinterpret_cast<unsigned short*>(smraw + off);
   unsigned short* s_ell_cols = s_ell_rows + (size_t)nov * W;
   off += 2 * (size_t)nov * W * sizeof(unsigned short);
   off = (off + 15) & ~(size_t)15;
   // per-warp state
-  const int deg_bytes = (2 * nov + 15) & ~15;   // 16-bit degrees: a dense row may hold more than 255 entries
+  const int deg_bytes = ((int)sizeof(deg_t) * nov + 15) & ~15;   // 16-bit degrees when a row may hold more than 255 entries
   const size_t warp_bytes = (size_t)deg_bytes + 2 * (size_t)words * 4 + (a.scaling ? 2 * (size_t)(nov + 1) * 4 : 0);
   const size_t warp_stride = (warp_bytes + 15) & ~(size_t)15;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbase = smraw + off + wib * warp_stride;
-  unsigned short* deg = reinterpret_cast<unsigned short*>(wbase);
+  deg_t* deg = reinterpret_cast<deg_t*>(wbase);
   unsigned* rowx = reinterpret_cast<unsigned*>(wbase + deg_bytes);
   unsigned* colx = rowx + words;
   float* d_r = reinterpret_cast<float*>(colx + words);
   float* d_c = d_r + (nov + 1);                 // d_r[nov] = d_c[nov] = 0: the ELL padding
-  __shared__ double blk_sum[APX_WARPS], blk_sq[APX_WARPS];
-  __shared__ unsigned long long blk_alive[APX_WARPS];
+  __shared__ unsigned int s_tix[APX_WARPS];
 
-  for (int e = threadIdx.x; e <= nov; e += APX_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
-  for (int e = threadIdx.x; e < nnz; e += APX_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
-  if (W > 0)
+  if (W == 0) {
+    for (int e = threadIdx.x; e <= nov; e += APX_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
+    for (int e = threadIdx.x; e < nnz; e += APX_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
+  } else {
     for (int e = threadIdx.x; e < nov * W; e += APX_THREADS) { s_ell_rows[e] = a.ell_rows[e]; s_ell_cols[e] = a.ell_cols[e]; }
+  }
   __syncthreads();
 
-  const unsigned long long total_warps = (unsigned long long)gridDim.x * APX_WARPS;
-  const unsigned long long wg = (unsigned long long)blockIdx.x * APX_WARPS + wib;
-  double wsum = 0.0, wsq = 0.0;
-  unsigned long long walive = 0;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+  const unsigned int n_trials = (unsigned int)(a.trial_hi - a.trial_lo);
 
-  for (unsigned long long trial = a.trial_lo + wg; trial < a.trial_hi; trial += total_warps) {
+  // Trials differ wildly in length (most hit a dead end early, a survivor runs nov steps with a Sinkhorn
+  // phase every scale_intervals of them): every warp pulls its next trial from a global counter instead of
+  // owning a fixed stride of them (a static split left 19 % of the warp-time idle at the end of the launch).
+  // Each estimate goes to its own slot, so the sums do not depend on which warp ran which trial.
+  for (;;) {
+    unsigned int tix = 0;
+    if (lane == 0) tix = atomicAdd(a.queue, 1u);
+    tix = __shfl_sync(0xffffffffu, tix, 0);
+    if (tix >= n_trials) break;
+    // the trial index is read back from shared memory where it is needed (every fourth step and at the
+    // end): one register less to carry through the whole trial
+    if (lane == 0) s_tix[wib] = tix;
+    __syncwarp();
+#define SPB_TRIAL() (a.trial_lo + (unsigned long long)s_tix[wib])
     // ---- reset state ----
-    for (int r = lane; r < nov; r += 32) deg[r] = (unsigned short)(s_rptrs[r + 1] - s_rptrs[r]);
+    for (int r = lane; r < nov; r += 32) {
+      int d0;
+      if (W > 0) {
+        d0 = 0;
+#pragma unroll
+        for (int q = 0; q < W; ++q) d0 += (s_ell_cols[r * W + q] != (unsigned short)nov);
+      } else {
+        d0 = s_rptrs[r + 1] - s_rptrs[r];
+      }
+      deg[r] = (deg_t)d0;
+    }
     for (int w = lane; w < words; w += 32) { rowx[w] = 0u; colx[w] = 0u; }
     if (a.scaling) {
       for (int i = lane; i < nov; i += 32) { d_r[i] = 1.0f; d_c[i] = 1.0f; }
@@ -132,8 +157,10 @@ approx_kernel(const ApproxArgs a) {
     bool dead = false;
     int step = 0;                 // steps completed so far
     for (; step < nov && !dead; ++step) {
-      if ((step & 3) == 0)
+      if ((step & 3) == 0) {
+        const unsigned long long trial = SPB_TRIAL();
         philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)(step >> 2), 0u, k0, k1, rnd);
+      }
       const int rw = step & 3;   // select, not index: keeps the four words in registers
       const uint32_t draw = (rw == 0) ? rnd[0] : (rw == 1) ? rnd[1] : (rw == 2) ? rnd[2] : rnd[3];
       // ---- minimum-degree remaining row, first in ascending order ----
@@ -144,9 +171,9 @@ approx_kernel(const ApproxArgs a) {
       const int row = (int)(best & 0xffffu);
       const int dmin = (int)(best >> 16);
       if (dmin == 0) { dead = true; break; }
-      const int rb = s_rptrs[row], re = s_rptrs[row + 1];
+      const int rb = (W > 0) ? 0 : s_rptrs[row], re = (W > 0) ? 0 : s_rptrs[row + 1];
       int col = -1;
-      if (!a.scaling) {
+      if (W == 0 && !a.scaling) {
         // ---- Rasmussen: perm *= deg; uniform pick of the r-th remaining column ----
         perm *= (double)dmin;
         int want = (int)(((uint64_t)draw * (uint64_t)dmin) >> 32);
@@ -228,15 +255,31 @@ approx_kernel(const ApproxArgs a) {
         // ---- column with probability d_r[row]*d_c[c] / sum (all lanes compute the same) ----
         const float dr = d_r[row];
         double tot = 0.0;
-        for (int t = rb; t < re; ++t) tot += (double)(dr * d_c[s_cols[t]]);   // + 0 for extracted columns
+        if (W > 0) {
+          // the row's entries in CRS order, then padding (index nov, factor 0): the same sums bit for bit
+#pragma unroll 1
+          for (int q = 0; q < W; ++q) tot += (double)(dr * d_c[s_ell_cols[row * W + q]]);
+        } else {
+          for (int t = rb; t < re; ++t) tot += (double)(dr * d_c[s_cols[t]]);   // + 0 for extracted columns
+        }
         if (tot == 0.0) { dead = true; break; }
         const double target = ((double)draw + 1.0) * (1.0 / 4294967296.0) * tot;
         double run = 0.0;
-        for (int t = rb; t < re; ++t) {
-          const int cc = s_cols[t];
-          const double s = (double)(dr * d_c[cc]);     // 0 for an extracted column: run does not move
-          run += s;
-          if (target <= run) { col = cc; perm /= (s / tot); break; }
+        if (W > 0) {
+#pragma unroll 1
+          for (int q = 0; q < W; ++q) {
+            const int cc = s_ell_cols[row * W + q];
+            const double s = (double)(dr * d_c[cc]);
+            run += s;
+            if (col < 0 && cc < nov && target <= run) { col = cc; perm /= (s / tot); }
+          }
+        } else {
+          for (int t = rb; t < re; ++t) {
+            const int cc = s_cols[t];
+            const double s = (double)(dr * d_c[cc]);     // 0 for an extracted column: run does not move
+            run += s;
+            if (target <= run) { col = cc; perm /= (s / tot); break; }
+          }
         }
         if (col < 0) { dead = true; break; }   // cannot happen: run reaches tot exactly
       }
@@ -250,33 +293,27 @@ approx_kernel(const ApproxArgs a) {
         if (a.scaling) { d_r[row] = 0.0f; d_c[col] = 0.0f; }
       }
       __syncwarp();
-      for (int t = s_cptrs[col] + lane; t < s_cptrs[col + 1]; t += 32) {
-        const int r = s_rows[t];
-        if (!bit_test(rowx, r)) deg[r] -= 1;
+      if (W > 0) {
+        if (lane < W) {
+          const int r = s_ell_rows[col * W + lane];
+          if (r < nov && !bit_test(rowx, r)) deg[r] -= 1;
+        }
+      } else {
+        for (int t = s_cptrs[col] + lane; t < s_cptrs[col + 1]; t += 32) {
+          const int r = s_rows[t];
+          if (!bit_test(rowx, r)) deg[r] -= 1;
+        }
       }
       __syncwarp();
     }
     // a dead end estimates 0; `perm` is still the product over the `step` steps it completed
     if (a.trace && lane == 0) {
-      a.trace[2 * (trial - a.trial_lo)] = (double)step;
-      a.trace[2 * (trial - a.trial_lo) + 1] = perm;
+      a.trace[2 * (size_t)s_tix[wib]] = (double)step;
+      a.trace[2 * (size_t)s_tix[wib] + 1] = perm;
     }
-    const double est = dead ? 0.0 : perm;
-    wsum += est;
-    const double q = est * a.sq_scale;
-    wsq += q * q;
-    walive += dead ? 0ull : 1ull;
+    if (lane == 0) a.est[s_tix[wib]] = dead ? 0.0 : perm;
     __syncwarp();
-  }
-  if (lane == 0) { blk_sum[wib] = wsum; blk_sq[wib] = wsq; blk_alive[wib] = walive; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0, q = 0.0;
-    unsigned long long al = 0;
-    for (int w = 0; w < APX_WARPS; ++w) { s += blk_sum[w]; q += blk_sq[w]; al += blk_alive[w]; }
-    a.partial_sum[blockIdx.x] = s;
-    a.partial_sq[blockIdx.x] = q;
-    a.partial_alive[blockIdx.x] = al;
+#undef SPB_TRIAL
   }
 }
 
@@ -295,9 +332,8 @@ struct SmallArgs {
   const unsigned long long* rowmask;   // [nov] columns of row r
   const unsigned long long* colmask;   // [nov] rows of column c
   const double* wdense;                // [nov*nov] entry weights (scaled dense twin) or nullptr
-  double* partial_sum;
-  double* partial_sq;
-  unsigned long long* partial_alive;
+  double* est;
+  unsigned int* queue;
   double* trace;
   unsigned long long trial_lo, trial_hi;
   unsigned long long seed;
@@ -317,23 +353,22 @@ approx_small_kernel(const SmallArgs a) {
   float* s_d = reinterpret_cast<float*>(s_w + (WEIGHTED ? nov * nov : 0));   // SCALING: d_r | d_c, [i][thread]
   float* d_r = s_d + threadIdx.x;
   float* d_c = s_d + (size_t)nov * APS_THREADS + threadIdx.x;
-  __shared__ double blk_sum[APS_THREADS / 32], blk_sq[APS_THREADS / 32];
-  __shared__ unsigned long long blk_alive[APS_THREADS / 32];
   for (int e = threadIdx.x; e < nov; e += APS_THREADS) { s_row[e] = a.rowmask[e]; s_col[e] = a.colmask[e]; }
   if (WEIGHTED) for (int e = threadIdx.x; e < nov * nov; e += APS_THREADS) s_w[e] = a.wdense[e];
   __syncthreads();
 
-  const unsigned long long total = (unsigned long long)gridDim.x * APS_THREADS;
-  unsigned long long trial = a.trial_lo + (unsigned long long)blockIdx.x * APS_THREADS + threadIdx.x;
+  // persistent lanes pulling trial indices from a global counter (see approx_kernel); one slot per estimate
+  const unsigned int n_trials = (unsigned int)(a.trial_hi - a.trial_lo);
+  unsigned int tix = atomicAdd(a.queue, 1u);
+  unsigned long long trial = a.trial_lo + tix;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-  double tsum = 0.0, tsq = 0.0, perm = 1.0;
-  unsigned long long talive = 0ull;
+  double perm = 1.0;
   unsigned long long rowx = 0ull, colx = 0ull;
   uint32_t rnd0 = 0, rnd1 = 0, rnd2 = 0, rnd3 = 0;
   int step = 0;
 
   for (int it = 0;; ++it) {
-    const bool have = trial < a.trial_hi;
+    const bool have = tix < n_trials;
     if (!__any_sync(0xffffffffu, have)) break;
     if (!have) continue;
     // scaled estimator: a new trial only starts on a loop trip that is a multiple of the scaling
@@ -432,51 +467,34 @@ approx_small_kernel(const SmallArgs a) {
         a.trace[2 * (trial - a.trial_lo)] = (double)step;
         a.trace[2 * (trial - a.trial_lo) + 1] = perm;
       }
-      const double est = dead ? 0.0 : perm;
-      tsum += est;
-      const double q = est * a.sq_scale;
-      tsq += q * q;
-      talive += dead ? 0ull : 1ull;
-      trial += total;
+      a.est[tix] = dead ? 0.0 : perm;
+      tix = atomicAdd(a.queue, 1u);
+      trial = a.trial_lo + tix;
       step = 0;
     }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    tsum += __shfl_down_sync(0xffffffffu, tsum, o);
-    tsq += __shfl_down_sync(0xffffffffu, tsq, o);
-    talive += __shfl_down_sync(0xffffffffu, talive, o);
-  }
-  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; blk_alive[threadIdx.x >> 5] = talive; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double sv = 0.0, qv = 0.0;
-    unsigned long long al = 0;
-    for (int w = 0; w < APS_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; al += blk_alive[w]; }
-    a.partial_sum[blockIdx.x] = sv;
-    a.partial_sq[blockIdx.x] = qv;
-    a.partial_alive[blockIdx.x] = al;
   }
 }
 
 // ---- thread-per-trial Rasmussen for 64 < nov (sparse patterns, e.g. the 36x36 grid: nov = 648) ----
 // One thread runs a trial; its state lives in shared memory as 32-bit words laid out [word][thread]
 // (every lane stays in its own bank):
-//   deg   one byte per row: remaining column count, 0xFF once the row is extracted
-//   gmin  one byte per group of 32 rows: the minimum of the group's deg bytes
+//   deg   one BITS-wide field per row: remaining column count, all ones once the row is extracted
+//         (BITS = 4 when no row has more than 14 entries -- grids have 4 -- else 8)
+//   gmin  one byte per group of 32 rows: the minimum of the group's deg fields
 //   colx  one bit per column: extracted
 // The minimum-degree row (first in ascending order, as gpu_approximation_sparse.cu:242-256 scans) is
 // found through gmin: SIMD byte minimum over the ngroups bytes, first group holding it, first row of
 // that group holding it -- about 100 instructions per step instead of a scan of every CRS row.
-// Persistent lanes as in approx_small_kernel.  Per-trial values are bit-identical to the other
+// The pattern (CRS + CCS, 16-bit) is shared by the block.  With 4-bit degrees a trial's state on the
+// 36 x 36 grid is 432 bytes instead of 756, so two blocks of 224 threads share an SM (14 warps instead of 8).
+// Persistent lanes pulling trials from a global counter.  Per-trial values are bit-identical to the other
 // engines and to the oracle.
-#define APM_THREADS 256
+#define APM_MAX_THREADS 256
 
 struct MidArgs {
   const int* rptrs; const int* cols; const int* cptrs; const int* rows;
-  double* partial_sum;
-  double* partial_sq;
-  unsigned long long* partial_alive;
+  double* est;
+  unsigned int* queue;
   double* trace;
   unsigned long long trial_lo, trial_hi;
   unsigned long long seed;
@@ -490,69 +508,107 @@ __device__ __forceinline__ unsigned byte_min4(unsigned w) {   // minimum of the 
   return m & 0xffu;
 }
 
-__global__ void __launch_bounds__(APM_THREADS)
+// BITS-wide unsigned fields packed in 32-bit words
+template <int BITS> struct Fields;
+template <> struct Fields<8> {
+  static constexpr unsigned EX = 0xffu;
+  // running field-wise minimum accumulator over several words, and its final value
+  __device__ static void acc_init(unsigned& a0, unsigned& a1) { a0 = 0xffffffffu; a1 = 0xffffffffu; }
+  __device__ static void acc_add(unsigned& a0, unsigned& a1, unsigned w) { a0 = __vminu4(a0, w); (void)a1; }
+  __device__ static unsigned acc_min(unsigned a0, unsigned a1) { (void)a1; return byte_min4(a0); }
+  // index of the first field of w equal to v, or -1
+  __device__ static int first_eq(unsigned w, unsigned v) {
+    const unsigned eq = __vcmpeq4(w, v * 0x01010101u);
+    return eq ? ((__ffs(eq) - 1) >> 3) : -1;
+  }
+};
+template <> struct Fields<4> {
+  static constexpr unsigned EX = 0xfu;
+  __device__ static void acc_init(unsigned& a0, unsigned& a1) { a0 = 0xffffffffu; a1 = 0xffffffffu; }
+  __device__ static void acc_add(unsigned& a0, unsigned& a1, unsigned w) {
+    a0 = __vminu4(a0, w & 0x0f0f0f0fu);              // even fields
+    a1 = __vminu4(a1, (w >> 4) & 0x0f0f0f0fu);       // odd fields
+  }
+  __device__ static unsigned acc_min(unsigned a0, unsigned a1) { return byte_min4(__vminu4(a0, a1)); }
+  __device__ static int first_eq(unsigned w, unsigned v) {
+    const unsigned pat = v * 0x01010101u;
+    const unsigned m = (__vcmpeq4(w & 0x0f0f0f0fu, pat) & 0x0f0f0f0fu) | (__vcmpeq4((w >> 4) & 0x0f0f0f0fu, pat) & 0xf0f0f0f0u);
+    return m ? ((__ffs(m) - 1) >> 2) : -1;
+  }
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(APM_MAX_THREADS)
 rasmussen_mid_kernel(const MidArgs a) {
+  using F = Fields<BITS>;
+  constexpr int RPW = 32 / BITS;                 // rows per deg word
+  constexpr int GW = 32 / RPW;                   // deg words per group of 32 rows
   extern __shared__ __align__(16) unsigned char smraw[];
   const int nov = a.nov, nnz = a.nnz;
-  const int WD = (nov + 3) >> 2;                 // deg words
+  const int T = blockDim.x;
+  const int WD = (nov + RPW - 1) / RPW;          // deg words
   const int NG = (nov + 31) >> 5;                // groups of 32 rows
   const int WG = (NG + 3) >> 2;                  // gmin words
   const int WC = (nov + 31) >> 5;                // colx words
-  int* s_rptrs = reinterpret_cast<int*>(smraw);
-  int* s_cptrs = s_rptrs + (nov + 1);
-  int* s_cols = s_cptrs + (nov + 1);
-  int* s_rows = s_cols + nnz;
-  unsigned* s_deg0 = reinterpret_cast<unsigned*>(s_rows + nnz);      // initial deg words
+  unsigned short* s_rptrs = reinterpret_cast<unsigned short*>(smraw);
+  unsigned short* s_cptrs = s_rptrs + (nov + 1);
+  unsigned short* s_cols = s_cptrs + (nov + 1);
+  unsigned short* s_rows = s_cols + nnz;
+  unsigned* s_deg0 = reinterpret_cast<unsigned*>(smraw + (((size_t)(2 * (nov + 1) + 2 * nnz) * 2 + 15) & ~(size_t)15));   // initial deg words
   unsigned* s_gmin0 = s_deg0 + WD;                                    // initial gmin words
   unsigned* st = s_gmin0 + WG;                                        // per-thread state, [word][thread]
   unsigned* deg = st + threadIdx.x;
-  unsigned* gmin = deg + (size_t)WD * APM_THREADS;
-  unsigned* colx = gmin + (size_t)WG * APM_THREADS;
-  __shared__ double blk_sum[APM_THREADS / 32], blk_sq[APM_THREADS / 32];
-  __shared__ unsigned long long blk_alive[APM_THREADS / 32];
+  unsigned* gmin = deg + (size_t)WD * T;
+  unsigned* colx = gmin + (size_t)WG * T;
 
-  for (int e = threadIdx.x; e <= nov; e += APM_THREADS) { s_rptrs[e] = a.rptrs[e]; s_cptrs[e] = a.cptrs[e]; }
-  for (int e = threadIdx.x; e < nnz; e += APM_THREADS) { s_cols[e] = a.cols[e]; s_rows[e] = a.rows[e]; }
+  for (int e = threadIdx.x; e <= nov; e += T) { s_rptrs[e] = (unsigned short)a.rptrs[e]; s_cptrs[e] = (unsigned short)a.cptrs[e]; }
+  for (int e = threadIdx.x; e < nnz; e += T) { s_cols[e] = (unsigned short)a.cols[e]; s_rows[e] = (unsigned short)a.rows[e]; }
   __syncthreads();
-  for (int w = threadIdx.x; w < WD; w += APM_THREADS) {
+  for (int w = threadIdx.x; w < WD; w += T) {
     unsigned v = 0;
-    for (int b = 0; b < 4; ++b) {
-      const int r = 4 * w + b;
-      const unsigned d = (r < nov) ? (unsigned)min(254, s_rptrs[r + 1] - s_rptrs[r]) : 0xffu;   // padding rows: extracted
-      v |= d << (8 * b);
+    for (int b = 0; b < RPW; ++b) {
+      const int r = RPW * w + b;
+      const unsigned d = (r < nov) ? (unsigned)(s_rptrs[r + 1] - s_rptrs[r]) : F::EX;   // padding rows: extracted
+      v |= d << (BITS * b);
     }
     s_deg0[w] = v;
   }
   __syncthreads();
-  for (int w = threadIdx.x; w < WG; w += APM_THREADS) {
+  for (int w = threadIdx.x; w < WG; w += T) {
     unsigned v = 0;
     for (int b = 0; b < 4; ++b) {
       const int g = 4 * w + b;
       unsigned m = 0xffu;
-      if (g < NG) for (int q = 0; q < 8; ++q) { const int wi = 8 * g + q; if (wi < WD) m = min(m, byte_min4(s_deg0[wi])); }
+      if (g < NG) {
+        unsigned a0, a1;
+        F::acc_init(a0, a1);
+        for (int q = 0; q < GW; ++q) { const int wi = GW * g + q; if (wi < WD) F::acc_add(a0, a1, s_deg0[wi]); }
+        m = F::acc_min(a0, a1);
+        if (m == F::EX) m = 0xffu;                 // a group without rows
+      }
       v |= m << (8 * b);
     }
     s_gmin0[w] = v;
   }
   __syncthreads();
 
-  const unsigned long long total = (unsigned long long)gridDim.x * APM_THREADS;
-  unsigned long long trial = a.trial_lo + (unsigned long long)blockIdx.x * APM_THREADS + threadIdx.x;
+  const unsigned int n_trials = (unsigned int)(a.trial_hi - a.trial_lo);
+  unsigned int tix = atomicAdd(a.queue, 1u);
+  unsigned long long trial = a.trial_lo + tix;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-  double tsum = 0.0, tsq = 0.0, perm = 1.0;
-  unsigned long long talive = 0ull;
+  double perm = 1.0;
   uint32_t rnd0 = 0, rnd1 = 0, rnd2 = 0, rnd3 = 0;
   int step = 0;
 
   for (;;) {
-    const bool have = trial < a.trial_hi;
+    const bool have = tix < n_trials;
     if (!__any_sync(0xffffffffu, have)) break;
     if (!have) continue;
     if (step == 0) {
       perm = 1.0;
-      for (int w = 0; w < WD; ++w) deg[w * APM_THREADS] = s_deg0[w];
-      for (int w = 0; w < WG; ++w) gmin[w * APM_THREADS] = s_gmin0[w];
-      for (int w = 0; w < WC; ++w) colx[w * APM_THREADS] = 0u;
+      for (int w = 0; w < WD; ++w) deg[w * T] = s_deg0[w];
+      for (int w = 0; w < WG; ++w) gmin[w * T] = s_gmin0[w];
+      for (int w = 0; w < WC; ++w) colx[w * T] = 0u;
     }
     if ((step & 3) == 0) {
       uint32_t r[4];
@@ -563,54 +619,55 @@ rasmussen_mid_kernel(const MidArgs a) {
     const uint32_t draw = (rw == 0) ? rnd0 : (rw == 1) ? rnd1 : (rw == 2) ? rnd2 : rnd3;
     // ---- minimum remaining degree, first group and first row holding it ----
     unsigned acc4 = 0xffffffffu;
-    for (int w = 0; w < WG; ++w) acc4 = __vminu4(acc4, gmin[w * APM_THREADS]);
+    for (int w = 0; w < WG; ++w) acc4 = __vminu4(acc4, gmin[w * T]);
     const unsigned dmin = byte_min4(acc4);
     bool dead = (dmin == 0u);
     if (!dead) {
-      const unsigned pat = dmin * 0x01010101u;
       int g = 0;
       for (int w = 0; w < WG; ++w) {
-        const unsigned eq = __vcmpeq4(gmin[w * APM_THREADS], pat);     // 0xFF in every matching byte
-        if (eq) { g = 4 * w + ((__ffs(eq) - 1) >> 3); break; }
+        const int f = Fields<8>::first_eq(gmin[w * T], dmin);
+        if (f >= 0) { g = 4 * w + f; break; }
       }
       int row = 0;
-      for (int q = 0; q < 8; ++q) {
-        const int wi = 8 * g + q;
+      for (int q = 0; q < GW; ++q) {
+        const int wi = GW * g + q;
         if (wi >= WD) break;
-        const unsigned eq = __vcmpeq4(deg[wi * APM_THREADS], pat);
-        if (eq) { row = 4 * wi + ((__ffs(eq) - 1) >> 3); break; }
+        const int f = F::first_eq(deg[wi * T], dmin);
+        if (f >= 0) { row = RPW * wi + f; break; }
       }
       perm *= (double)dmin;
       int want = (int)(((uint64_t)draw * (uint64_t)dmin) >> 32);
       int col = -1;
       for (int t = s_rptrs[row]; t < s_rptrs[row + 1]; ++t) {
         const int c = s_cols[t];
-        if ((colx[(c >> 5) * APM_THREADS] >> (c & 31)) & 1u) continue;
+        if ((colx[(c >> 5) * T] >> (c & 31)) & 1u) continue;
         if (want == 0) { col = c; break; }
         --want;
       }
       // ---- extract row and column ----
-      colx[(col >> 5) * APM_THREADS] |= 1u << (col & 31);
-      deg[(row >> 2) * APM_THREADS] |= 0xffu << (8 * (row & 3));
+      colx[(col >> 5) * T] |= 1u << (col & 31);
+      deg[(row / RPW) * T] |= F::EX << (BITS * (row % RPW));
       {
-        unsigned m4 = 0xffffffffu;
+        unsigned a0, a1;
+        F::acc_init(a0, a1);
         const int gb = row >> 5;
-        for (int q = 0; q < 8; ++q) { const int wi = 8 * gb + q; if (wi < WD) m4 = __vminu4(m4, deg[wi * APM_THREADS]); }
-        const unsigned gm = byte_min4(m4);
-        unsigned gw = gmin[(gb >> 2) * APM_THREADS];
+        for (int q = 0; q < GW; ++q) { const int wi = GW * gb + q; if (wi < WD) F::acc_add(a0, a1, deg[wi * T]); }
+        unsigned gm = F::acc_min(a0, a1);
+        if (gm == F::EX) gm = 0xffu;               // the whole group is extracted
+        unsigned gw = gmin[(gb >> 2) * T];
         gw = (gw & ~(0xffu << (8 * (gb & 3)))) | (gm << (8 * (gb & 3)));
-        gmin[(gb >> 2) * APM_THREADS] = gw;
+        gmin[(gb >> 2) * T] = gw;
       }
       for (int t = s_cptrs[col]; t < s_cptrs[col + 1]; ++t) {
         const int r2 = s_rows[t];
-        const unsigned dw = deg[(r2 >> 2) * APM_THREADS];
-        const unsigned d = (dw >> (8 * (r2 & 3))) & 0xffu;
-        if (d == 0xffu) continue;                                      // extracted
-        deg[(r2 >> 2) * APM_THREADS] = dw - (1u << (8 * (r2 & 3)));
+        const unsigned dw = deg[(r2 / RPW) * T];
+        const unsigned d = (dw >> (BITS * (r2 % RPW))) & F::EX;
+        if (d == F::EX) continue;                                      // extracted
+        deg[(r2 / RPW) * T] = dw - (1u << (BITS * (r2 % RPW)));
         const int g2 = r2 >> 5;
-        const unsigned gw = gmin[(g2 >> 2) * APM_THREADS];
+        const unsigned gw = gmin[(g2 >> 2) * T];
         const unsigned cur = (gw >> (8 * (g2 & 3))) & 0xffu;
-        if (d - 1u < cur) gmin[(g2 >> 2) * APM_THREADS] = (gw & ~(0xffu << (8 * (g2 & 3)))) | ((d - 1u) << (8 * (g2 & 3)));
+        if (d - 1u < cur) gmin[(g2 >> 2) * T] = (gw & ~(0xffu << (8 * (g2 & 3)))) | ((d - 1u) << (8 * (g2 & 3)));
       }
     }
     if (!dead) ++step;
@@ -620,30 +677,11 @@ rasmussen_mid_kernel(const MidArgs a) {
         a.trace[2 * (trial - a.trial_lo)] = (double)step;
         a.trace[2 * (trial - a.trial_lo) + 1] = perm;
       }
-      const double est = dead ? 0.0 : perm;
-      tsum += est;
-      const double q = est * a.sq_scale;
-      tsq += q * q;
-      talive += dead ? 0ull : 1ull;
-      trial += total;
+      a.est[tix] = dead ? 0.0 : perm;
+      tix = atomicAdd(a.queue, 1u);
+      trial = a.trial_lo + tix;
       step = 0;
     }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    tsum += __shfl_down_sync(0xffffffffu, tsum, o);
-    tsq += __shfl_down_sync(0xffffffffu, tsq, o);
-    talive += __shfl_down_sync(0xffffffffu, talive, o);
-  }
-  if ((threadIdx.x & 31) == 0) { blk_sum[threadIdx.x >> 5] = tsum; blk_sq[threadIdx.x >> 5] = tsq; blk_alive[threadIdx.x >> 5] = talive; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double sv = 0.0, qv = 0.0;
-    unsigned long long al = 0;
-    for (int w = 0; w < APM_THREADS / 32; ++w) { sv += blk_sum[w]; qv += blk_sq[w]; al += blk_alive[w]; }
-    a.partial_sum[blockIdx.x] = sv;
-    a.partial_sq[blockIdx.x] = qv;
-    a.partial_alive[blockIdx.x] = al;
   }
 }
 
@@ -663,6 +701,7 @@ struct spd_approx_plan {
   size_t smem_bytes = 0;
   int blocks = 0;
   int ellW = 0;                                  // 0: CSR sweeps; 4 or 8: ELL width (pattern-only scaling)
+  bool wide = false;                             // some row has more than 255 entries: 16-bit degrees
   unsigned short *d_ell_rows = nullptr, *d_ell_cols = nullptr;
   // thread-per-trial engine (nov <= 64)
   bool small = false;
@@ -672,6 +711,7 @@ struct spd_approx_plan {
   int small_blocks = 0;
   // thread-per-trial Rasmussen for larger sparse patterns
   bool mid = false;
+  int mid_bits = 8, mid_threads = APM_MAX_THREADS;
   size_t mid_smem = 0;
   int mid_blocks = 0;
   double* d_trace = nullptr;                     // set by spd_approx_plan_trace for the duration of one run
@@ -681,10 +721,10 @@ struct spd_approx_plan {
 
 typedef void (*warp_kernel_t)(const ApproxArgs);
 static warp_kernel_t warp_kernel_of(const spd_approx_plan* p) {
-  if (p->weighted) return approx_kernel<true, 0>;
-  if (p->ellW == 4) return approx_kernel<false, 4>;
-  if (p->ellW == 8) return approx_kernel<false, 8>;
-  return approx_kernel<false, 0>;
+  if (p->weighted) return p->wide ? approx_kernel<true, 0, true> : approx_kernel<true, 0, false>;
+  if (p->ellW == 4) return approx_kernel<false, 4, false>;
+  if (p->ellW == 8) return approx_kernel<false, 8, false>;
+  return p->wide ? approx_kernel<false, 0, true> : approx_kernel<false, 0, false>;
 }
 
 template <typename K>
@@ -739,8 +779,8 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
   // estimates of a large pattern are ~1e159 (36x36 grid): square them in a scaled domain
   p->sq_scale = (nov > 64) ? ldexp(1.0, -4 * nov / 5) : 1.0;
   const int words = (nov + 31) / 32;
-  size_t off = (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
-  off = (off + 15) & ~(size_t)15;
+  for (int i = 0; i < nov; ++i)
+    if (rptrs[i + 1] - rptrs[i] > 255) p->wide = true;
   // ELL form of the pattern for the Sinkhorn sweeps when every row and column has <= 8 entries
   if (p->scaling && !p->weighted && env_int("SP_APPROX_ELL", 1) != 0) {
     int maxdeg = 0;
@@ -750,9 +790,12 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     }
     if (maxdeg <= 8) p->ellW = maxdeg <= 4 ? 4 : 8;
   }
+  // the ELL arrays replace CRS + CCS in shared memory when they are used
+  size_t off = p->ellW ? 0 : (size_t)(2 * (nov + 1) + 2 * nnz) * sizeof(int);
+  off = (off + 15) & ~(size_t)15;
   off += 2 * (size_t)nov * p->ellW * sizeof(unsigned short);
   off = (off + 15) & ~(size_t)15;
-  const size_t deg_bytes = (2 * (size_t)nov + 15) & ~(size_t)15;     // 16-bit degrees
+  const size_t deg_bytes = ((p->wide ? 2 : 1) * (size_t)nov + 15) & ~(size_t)15;
   size_t warp_bytes = deg_bytes + 2 * (size_t)words * 4 + (scaling ? 2 * (size_t)(nov + 1) * 4 : 0);
   warp_bytes = (warp_bytes + 15) & ~(size_t)15;
   p->smem_bytes = off + APX_WARPS * warp_bytes;
@@ -833,26 +876,34 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
     else rc = small_prepare(p, approx_small_kernel<true, false>);
     if (rc != SPD_OK) return fail(rc);
     p->small = true;
-    if ((rc = lane_reserve_partials(&L, (size_t)2 * p->small_blocks + 16)) != SPD_OK) return fail(rc);
-    if ((rc = lane_reserve_aux(&L, (size_t)p->small_blocks + 16)) != SPD_OK) return fail(rc);
+
   }
   // ---- thread-per-trial Rasmussen for nov > 64 when the per-thread state fits shared memory ----
   int maxdeg = 0;
   for (int r = 0; r < nov; ++r) maxdeg = (rptrs[r + 1] - rptrs[r] > maxdeg) ? rptrs[r + 1] - rptrs[r] : maxdeg;
-  if (!p->small && !scaling && maxdeg <= 254 && env_int("SP_APPROX_FORCE_WARP", 0) == 0) {
-    const int WD = (nov + 3) / 4, NG = (nov + 31) / 32, WG = (NG + 3) / 4, WC = (nov + 31) / 32;
-    const size_t shared_part = (size_t)(2 * (nov + 1) + 2 * nnz) * 4 + (size_t)(WD + WG) * 4;
-    const size_t state = (size_t)(WD + WG + WC) * 4 * APM_THREADS;
-    p->mid_smem = shared_part + state;
+  if (!p->small && !scaling && maxdeg <= 254 && nnz < 65536 && env_int("SP_APPROX_FORCE_WARP", 0) == 0) {
+    // 4-bit degrees when they fit (no row with more than 14 entries), and the largest block of whole warps
+    // that lets two blocks share an SM (else one block of 256 threads, if that fits at all)
+    p->mid_bits = (maxdeg <= 14 && env_int("SP_APPROX_MID_BITS", 4) == 4) ? 4 : 8;
+    const int RPW = 32 / p->mid_bits;
+    const int WD = (nov + RPW - 1) / RPW, NG = (nov + 31) / 32, WG = (NG + 3) / 4, WC = (nov + 31) / 32;
+    const size_t shared_part = (((size_t)(2 * (nov + 1) + 2 * nnz) * 2 + 15) & ~(size_t)15) + (size_t)(WD + WG) * 4;
+    const size_t per_thread = (size_t)(WD + WG + WC) * 4;
+    const size_t half_sm = (227 * 1024) / 2 - 2048;
+    int threads = 0;
+    if (shared_part < half_sm) threads = (int)((half_sm - shared_part) / per_thread) / 32 * 32;
+    if (threads > APM_MAX_THREADS) threads = APM_MAX_THREADS;
+    if (threads < 128) threads = APM_MAX_THREADS;                 // two blocks would be too thin: one full block
+    p->mid_threads = threads;
+    p->mid_smem = shared_part + per_thread * threads;
     if (p->mid_smem <= 220 * 1024) {
-      e = cudaFuncSetAttribute(rasmussen_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);
+      const void* kern = (p->mid_bits == 4) ? (const void*)rasmussen_mid_kernel<4> : (const void*)rasmussen_mid_kernel<8>;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);
       int per = 0;
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, rasmussen_mid_kernel, APM_THREADS, p->mid_smem);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, threads, p->mid_smem);
       if (e == cudaSuccess && per >= 1) {
         p->mid = true;
         p->mid_blocks = per * L.sm_count;
-        if ((rc = lane_reserve_partials(&L, (size_t)2 * p->mid_blocks + 16)) != SPD_OK) return fail(rc);
-        if ((rc = lane_reserve_aux(&L, (size_t)p->mid_blocks + 16)) != SPD_OK) return fail(rc);
       } else {
         (void)cudaGetLastError();
       }
@@ -862,8 +913,7 @@ int spd_approx_plan_create(int device, const int* rptrs, const int* cols, const 
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel_of(p), APX_THREADS, p->smem_bytes);
   if (e != cudaSuccess || per_sm < 1) { set_error("approx kernel does not fit on an SM: %s", cudaGetErrorString(e)); return fail(SPD_ECUDA); }
   p->blocks = per_sm * L.sm_count;     // persistent grid: resident blocks x SM count
-  if ((rc = lane_reserve_partials(&L, (size_t)2 * p->blocks + 16)) != SPD_OK) return fail(rc);
-  if ((rc = lane_reserve_aux(&L, (size_t)p->blocks + 16)) != SPD_OK) return fail(rc);
+  if ((rc = lane_reserve_partials(&L, (size_t)1 << 17)) != SPD_OK) return fail(rc);    // estimate slots; grows on demand
   *out = p;
   return SPD_OK;
 }
@@ -882,76 +932,69 @@ int spd_approx_plan_launch(spd_approx_plan* p, unsigned long long lo, unsigned l
   SPB_CUDA(cudaSetDevice(L.device));
   memset(&p->info, 0, sizeof(p->info));
   p->info.units = hi - lo;
-  p->info.visited = hi - lo;
   p->info.path = p->scaling ? SPD_PATH_SCALING : SPD_PATH_RASMUSSEN;
-  if (p->small) {
-    int blocks = p->small_blocks;
-    const unsigned long long need = (hi - lo + APS_THREADS - 1) / APS_THREADS;
-    if (need < (unsigned long long)blocks) blocks = (int)(need ? need : 1);
-    SmallArgs sa;
-    sa.rowmask = p->d_rowmask; sa.colmask = p->d_colmask; sa.wdense = p->d_wdense;
-    sa.partial_sum = L.d_partials; sa.partial_sq = L.d_partials + blocks; sa.partial_alive = L.d_aux; sa.trace = p->d_trace;
-    sa.trial_lo = lo; sa.trial_hi = hi; sa.seed = p->seed; sa.sq_scale = p->sq_scale;
-    sa.nov = p->nov; sa.scaling = p->scaling; sa.scale_intervals = p->y; sa.scale_times = p->z;
-    SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
-    if (!p->scaling) approx_small_kernel<false, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
-    else if (p->weighted) approx_small_kernel<true, true><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
-    else approx_small_kernel<true, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
-    SPB_CUDA(cudaGetLastError());
-    int rc2;
-    if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
-    if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc2;
-    if ((rc2 = launch_reduce_u64(L, L.d_aux, (size_t)blocks, L.d_result, 2, false)) != SPD_OK) return rc2;
-    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 3 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
-    SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
-    p->info.launches = 4;
-    p->pending = true;
-    return SPD_OK;
-  }
-  if (p->mid) {
-    int blocks = p->mid_blocks;
-    const unsigned long long need = (hi - lo + APM_THREADS - 1) / APM_THREADS;
-    if (need < (unsigned long long)blocks) blocks = (int)(need ? need : 1);
-    MidArgs ma;
-    ma.rptrs = p->d_rptrs; ma.cols = p->d_cols; ma.cptrs = p->d_cptrs; ma.rows = p->d_rows;
-    ma.partial_sum = L.d_partials; ma.partial_sq = L.d_partials + blocks; ma.partial_alive = L.d_aux; ma.trace = p->d_trace;
-    ma.trial_lo = lo; ma.trial_hi = hi; ma.seed = p->seed; ma.sq_scale = p->sq_scale;
-    ma.nov = p->nov; ma.nnz = p->nnz;
-    SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
-    rasmussen_mid_kernel<<<blocks, APM_THREADS, p->mid_smem, L.stream>>>(ma);
-    SPB_CUDA(cudaGetLastError());
-    int rc2;
-    if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
-    if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc2;
-    if ((rc2 = launch_reduce_u64(L, L.d_aux, (size_t)blocks, L.d_result, 2, false)) != SPD_OK) return rc2;
-    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 3 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
-    SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
-    p->info.launches = 4;
-    p->pending = true;
-    return SPD_OK;
-  }
-  unsigned long long warps_needed = (hi - lo);
-  int blocks = p->blocks;
-  const unsigned long long need_blocks = (warps_needed + APX_WARPS - 1) / APX_WARPS;
-  if (need_blocks < (unsigned long long)blocks) blocks = (int)(need_blocks ? need_blocks : 1);
-  ApproxArgs a;
-  a.rptrs = p->d_rptrs; a.cols = p->d_cols; a.cptrs = p->d_cptrs; a.rows = p->d_rows;
-  a.rvals = p->d_rvals; a.cvals = p->d_cvals;
-  a.ell_rows = p->d_ell_rows; a.ell_cols = p->d_ell_cols;
-  a.partial_sum = L.d_partials; a.partial_sq = L.d_partials + blocks; a.partial_alive = L.d_aux; a.trace = p->d_trace;
-  a.trial_lo = lo; a.trial_hi = hi; a.seed = p->seed; a.sq_scale = p->sq_scale;
-  a.nov = p->nov; a.nnz = p->nnz; a.scaling = p->scaling;
-  a.scale_intervals = p->y; a.scale_times = p->z;
   SPB_CUDA(cudaEventRecord(L.ev0, L.stream));
-  warp_kernel_of(p)<<<blocks, APX_THREADS, p->smem_bytes, L.stream>>>(a);
-  SPB_CUDA(cudaGetLastError());
-  int rc;
-  if ((rc = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc;
-  if ((rc = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 1, false)) != SPD_OK) return rc;
-  if ((rc = launch_reduce_u64(L, L.d_aux, (size_t)blocks, L.d_result, 2, false)) != SPD_OK) return rc;
+  // one slot per estimate (at most 2^22 trials = 32 MiB per launch), a global trial counter, and a
+  // fixed-order reduction of the slots into {sum, sum of scaled squares, survivors}
+  const unsigned long long max_trials = 1ull << 22;
+  int launches = 0, rc;
+  bool first = true;
+  unsigned long long t0 = lo;
+  if (hi == lo) {
+    if ((rc = launch_reduce_estimates(L, L.d_partials, 0, p->sq_scale, L.d_result, false)) != SPD_OK) return rc;
+    ++launches;
+  }
+  while (t0 < hi) {
+    const unsigned long long cnt = (hi - t0 < max_trials) ? hi - t0 : max_trials;
+    if ((rc = lane_reserve_partials(&L, (size_t)cnt)) != SPD_OK) return rc;
+    SPB_CUDA(cudaMemsetAsync(L.d_queue, 0, sizeof(unsigned int), L.stream));
+    double* d_trace = p->d_trace ? p->d_trace + 2 * (t0 - lo) : nullptr;
+    if (p->small) {
+      int blocks = p->small_blocks;
+      const unsigned long long need = (cnt + APS_THREADS - 1) / APS_THREADS;
+      if (need < (unsigned long long)blocks) blocks = (int)need;
+      SmallArgs sa;
+      sa.rowmask = p->d_rowmask; sa.colmask = p->d_colmask; sa.wdense = p->d_wdense;
+      sa.est = L.d_partials; sa.queue = L.d_queue; sa.trace = d_trace;
+      sa.trial_lo = t0; sa.trial_hi = t0 + cnt; sa.seed = p->seed; sa.sq_scale = p->sq_scale;
+      sa.nov = p->nov; sa.scaling = p->scaling; sa.scale_intervals = p->y; sa.scale_times = p->z;
+      if (!p->scaling) approx_small_kernel<false, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
+      else if (p->weighted) approx_small_kernel<true, true><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
+      else approx_small_kernel<true, false><<<blocks, APS_THREADS, p->small_smem, L.stream>>>(sa);
+    } else if (p->mid) {
+      int blocks = p->mid_blocks;
+      const unsigned long long need = (cnt + p->mid_threads - 1) / p->mid_threads;
+      if (need < (unsigned long long)blocks) blocks = (int)need;
+      MidArgs ma;
+      ma.rptrs = p->d_rptrs; ma.cols = p->d_cols; ma.cptrs = p->d_cptrs; ma.rows = p->d_rows;
+      ma.est = L.d_partials; ma.queue = L.d_queue; ma.trace = d_trace;
+      ma.trial_lo = t0; ma.trial_hi = t0 + cnt; ma.seed = p->seed; ma.sq_scale = p->sq_scale;
+      ma.nov = p->nov; ma.nnz = p->nnz;
+      if (p->mid_bits == 4) rasmussen_mid_kernel<4><<<blocks, p->mid_threads, p->mid_smem, L.stream>>>(ma);
+      else rasmussen_mid_kernel<8><<<blocks, p->mid_threads, p->mid_smem, L.stream>>>(ma);
+    } else {
+      int blocks = p->blocks;
+      const unsigned long long need = (cnt + APX_WARPS - 1) / APX_WARPS;
+      if (need < (unsigned long long)blocks) blocks = (int)need;
+      ApproxArgs a;
+      a.rptrs = p->d_rptrs; a.cols = p->d_cols; a.cptrs = p->d_cptrs; a.rows = p->d_rows;
+      a.rvals = p->d_rvals; a.cvals = p->d_cvals;
+      a.ell_rows = p->d_ell_rows; a.ell_cols = p->d_ell_cols;
+      a.est = L.d_partials; a.queue = L.d_queue; a.trace = d_trace;
+      a.trial_lo = t0; a.trial_hi = t0 + cnt; a.seed = p->seed; a.sq_scale = p->sq_scale;
+      a.nov = p->nov; a.nnz = p->nnz; a.scaling = p->scaling;
+      a.scale_intervals = p->y; a.scale_times = p->z;
+      warp_kernel_of(p)<<<blocks, APX_THREADS, p->smem_bytes, L.stream>>>(a);
+    }
+    SPB_CUDA(cudaGetLastError());
+    if ((rc = launch_reduce_estimates(L, L.d_partials, (size_t)cnt, p->sq_scale, L.d_result, !first)) != SPD_OK) return rc;
+    launches += 2;
+    first = false;
+    t0 += cnt;
+  }
   SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, 3 * sizeof(double), cudaMemcpyDeviceToHost, L.stream));
   SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
-  p->info.launches = 4;
+  p->info.launches = launches;
   p->pending = true;
   return SPD_OK;
 }

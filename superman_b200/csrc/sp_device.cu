@@ -220,6 +220,54 @@ reduce_u64_kernel(const unsigned long long* __restrict__ counts, unsigned long l
   if (threadIdx.x == 0) *out = accumulate ? *out + sh[0] : sh[0];
 }
 
+// Estimators: out[0] (+)= sum est[i], out[1] (+)= sum (est[i] * scale)^2, out[2] (as u64) (+)= #{est[i] != 0},
+// in a fixed order (thread t takes i = t, t + 1024, ...; fixed tree): the result depends on the estimates
+// only, not on which warp produced which.
+__global__ void __launch_bounds__(1024, 1)
+reduce_estimates_kernel(const double* __restrict__ est, unsigned long long count, double scale, double* out,
+                        int accumulate) {
+  __shared__ double hi[1024], lo[1024], sq[1024];
+  __shared__ unsigned long long al[1024];
+  double h = 0.0, l = 0.0, q = 0.0;
+  unsigned long long n = 0;
+  for (unsigned long long i = threadIdx.x; i < count; i += 1024) {
+    const double v = est[i];
+    double s, e;
+    two_sum(h, v, s, e);
+    h = s;
+    l += e;
+    const double w = v * scale;
+    q += w * w;
+    n += (v != 0.0) ? 1ull : 0ull;
+  }
+  hi[threadIdx.x] = h; lo[threadIdx.x] = l; sq[threadIdx.x] = q; al[threadIdx.x] = n;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      double s, e;
+      two_sum(hi[threadIdx.x], hi[threadIdx.x + w], s, e);
+      hi[threadIdx.x] = s;
+      lo[threadIdx.x] = lo[threadIdx.x] + lo[threadIdx.x + w] + e;
+      sq[threadIdx.x] += sq[threadIdx.x + w];
+      al[threadIdx.x] += al[threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(out + 2);
+    const double v = hi[0] + lo[0];
+    out[0] = accumulate ? out[0] + v : v;
+    out[1] = accumulate ? out[1] + sq[0] : sq[0];
+    *cnt = accumulate ? *cnt + al[0] : al[0];
+  }
+}
+
+int launch_reduce_estimates(const Lane& lane, const double* est, size_t count, double scale, double* out, bool accumulate) {
+  reduce_estimates_kernel<<<1, 1024, 0, lane.stream>>>(est, (unsigned long long)count, scale, out, accumulate ? 1 : 0);
+  SPB_CUDA(cudaGetLastError());
+  return SPD_OK;
+}
+
 int launch_reduce_u64(const Lane& lane, const unsigned long long* counts, size_t count, double* out,
                       int slot, bool accumulate) {
   reduce_u64_kernel<<<1, 1024, 0, lane.stream>>>(counts, (unsigned long long)count,

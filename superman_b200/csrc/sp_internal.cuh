@@ -63,6 +63,9 @@ int launch_reduce(const Lane& lane, const double* partials, size_t count, double
 int launch_reduce_u64(const Lane& lane, const unsigned long long* counts, size_t count, double* out,
                       int slot, bool accumulate);
 
+// estimators: out[0] = sum, out[1] = sum of (est * scale)^2, out[2] = number of non-zero estimates (u64 bits)
+int launch_reduce_estimates(const Lane& lane, const double* est, size_t count, double scale, double* out, bool accumulate);
+
 int check_device(int device);
 
 // shared-memory-X dense kernel on [lo, hi) (sp_dense.cu); appends its blocks at partials[*pcount]
