@@ -70,6 +70,16 @@ int         sp_prepare_sparse(const double *mat, const int *cptrs, const int *ro
                               int skipper, int gpu_num);
 int         sp_prepare_approx(const int *rptrs, const int *cols, const int *cptrs, const int *rows, int nov, int nnz,
                               int scaling, int scale_intervals, int scale_times, int gpu_num);
+/* Calculation precision of the dense exact entry points (sp_dense_ryser, sp_dense_ryser_range, sp_dense_open and
+ * the dense leaves of sp_permanent_compressed).  SP_PRECISION_DOUBLE: FP64 (default).  SP_PRECISION_QUAD: the
+ * revised front-end's -q (flags.calculation_quad, revised_perman/flags.h:61-64, main.cpp:1298-1325) as
+ * double-double arithmetic: X, the products and the sums are pairs of doubles (~106 bits), about 8 x the FP64
+ * instruction count.  For permanents that are tiny against the Ryser terms they are the sum of (chesapeake: FP64 is
+ * 2e-6 off, double-double exact to the printed digits).  The half / mixed precision flags -h -w -v have no
+ * counterpart: FP64 is this library's lowest precision.  Process-wide. */
+#define SP_PRECISION_DOUBLE 0
+#define SP_PRECISION_QUAD   1
+int         sp_set_precision(int precision);
 /* first device the permanent entry points use (default 0); ids with gpu_num devices use
  * first .. first+gpu_num-1 (the revised front-end's -l flag) */
 int         sp_set_first_device(int device);

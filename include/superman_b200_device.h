@@ -50,6 +50,7 @@ typedef struct spd_run_info {
 #define SPD_PATH_SKIPPER        5
 #define SPD_PATH_RASMUSSEN      6
 #define SPD_PATH_SCALING        7
+#define SPD_PATH_DENSE_DD       8   /* dense Ryser in double-double arithmetic (the -q precision mode) */
 
 int         spd_device_count(void);               /* >= 0, or SPD_ENODEV */
 const char *spd_last_error(void);
@@ -68,6 +69,12 @@ double      spd_int_peak_instr_per_s(int device, int millis);
 
 /* ---- dense Ryser --------------------------------------------------------------------------- */
 typedef struct spd_dense_plan spd_dense_plan;
+
+/* Dense plans created after spd_set_quad(1) compute in double-double arithmetic (X, products and sums as
+ * pairs of doubles, ~106 bits): the revised front-end's -q ("quad" calculation precision,
+ * revised_perman/flags.h:61-64).  About 8 x the FP64 instruction count; process-wide switch. */
+void spd_set_quad(int on);
+int  spd_get_quad(void);
 
 /* mat_t[k*nov + j] = A[j][k] (the transposed matrix the reference uploads, gpu_exact_dense.cu:657-674),
  * xbase[j] = A[j][nov-1] - rowsum_j/2 (gpu_exact_dense.cu:647-654).  2 <= nov <= 64. */

@@ -89,6 +89,7 @@ _sig("sp_set_first_device", C.c_int, [C.c_int])
 _sig("sp_nw_factor", C.c_double, [C.c_int])
 _sig("sp_fp64_peak", C.c_double, [C.c_int, C.c_int])
 _sig("sp_int_peak", C.c_double, [C.c_int, C.c_int])
+_sig("sp_set_precision", C.c_int, [C.c_int])
 _sig("sp_dense_ryser", C.c_double, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _sp])
 _sig("sp_dense_ryser_range", C.c_double, [_dp, C.c_int, C.c_int, C.c_longlong, C.c_longlong, _sp])
 _sig("sp_dense_open", C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_void_p)])

@@ -15,7 +15,7 @@ __all__ = [
     "SupermanError", "device_count", "fp64_peak", "nw_factor", "Matrix",
     "SpStats", "dense_ryser", "dense_ryser_range", "DenseHandle", "permanent_compressed",
     "sparse_ryser", "skipper", "sparse_ryser_range",
-    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense", "approx_trace_sparse", "approx_trace_dense", "int_peak",
+    "rasmussen_sparse", "scaling_sparse", "rasmussen_dense", "scaling_dense", "approx_trials_sparse", "approx_trials_dense", "approx_trace_sparse", "approx_trace_dense", "int_peak", "set_precision",
     "gpu_perman64_rasmussen_sparse", "gpu_perman64_rasmussen_multigpucpu_chunks_sparse",
     "gpu_perman64_approximation_sparse", "gpu_perman64_approximation_multigpucpu_chunks_sparse",
     "gpu_perman64_rasmussen", "gpu_perman64_rasmussen_multigpucpu_chunks",
@@ -200,6 +200,11 @@ def fp64_peak(device: int = 0, millis: int = 200) -> float:
     if r < 0:
         raise SupermanError(-1, _ffi.last_error())
     return r
+
+
+def set_precision(quad: bool) -> None:
+    """dense exact paths in double-double arithmetic (the revised front-end's -q) when `quad`, else FP64"""
+    lib.sp_set_precision(1 if quad else 0)
 
 
 def int_peak(device: int = 0, millis: int = 200) -> float:

@@ -6,6 +6,7 @@
 // (start, end) arguments, which the multi-GPU wrappers slice (gpu_exact_dense.cu:729-752, 786-889).
 #include "sp_internal.cuh"
 #include "sp_dense_reg.h"
+#include "ryser_dd.cuh"
 #include <stdlib.h>
 #include <string.h>
 #include <new>
@@ -153,11 +154,15 @@ int smem_kernel_prepare(int n) {
 
 using namespace spb;
 
+static int g_quad = 0;      // spd_set_quad: plans created from now on compute in double-double
+
 struct spd_dense_plan {
   Lane* lanep = nullptr;
   int n = 0;
+  bool quad = false;
   double* d_mat_t = nullptr;
   double* d_xbase = nullptr;
+  double* d_xbase_lo = nullptr;
   bool pending = false;
   spd_run_info info;
 };
@@ -185,6 +190,38 @@ static int dense_enqueue(spd_dense_plan* p, unsigned long long lo, unsigned long
   bool first_reduce = true;
   size_t pcount = 0;
   const unsigned long long len = hi - lo;
+
+  if (p->quad) {
+    // double-double mode (-q): one kernel over the whole range, X in shared memory; the block sums come back as
+    // (high, low) pairs and both halves go through the compensated reduction
+    const size_t smem_bytes = ((size_t)n * n + 2 * (size_t)n * DDK_THREADS) * sizeof(double);
+    if (smem_bytes > 40 * 1024)
+      SPB_CUDA(cudaFuncSetAttribute(ryser_dd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES));
+    int bps = 1;
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ryser_dd_kernel, DDK_THREADS, smem_bytes));
+    unsigned long long blocks = (unsigned long long)L.sm_count * (unsigned)(bps > 0 ? bps : 1) * 8ull;   // 8 waves: tail below 1 %
+    unsigned long long per_thread = (len + blocks * DDK_THREADS - 1) / (blocks * DDK_THREADS);
+    unsigned long long pt = 16;
+    while (pt < per_thread) pt <<= 1;                  // power of two: the flipped column stays warp-uniform
+    if (pt > 4096) pt = 4096;                          // short chains (accuracy is the point of this mode)
+    per_thread = pt;
+    blocks = (len + per_thread * DDK_THREADS - 1) / (per_thread * DDK_THREADS);
+    if (blocks == 0) blocks = 1;
+    if (blocks > (1ull << 22)) { set_error("range too long for one double-double launch"); return SPD_ELIMIT; }
+    int rc2 = lane_reserve_partials(&L, 2 * (size_t)blocks);
+    if (rc2 != SPD_OK) return rc2;
+    ryser_dd_kernel<<<(unsigned)blocks, DDK_THREADS, smem_bytes, L.stream>>>(p->d_mat_t, p->d_xbase, p->d_xbase_lo, n, lo, hi,
+                                                                             per_thread, L.d_partials);
+    SPB_CUDA(cudaGetLastError());
+    if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
+    if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 0, true)) != SPD_OK) return rc2;
+    SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
+    p->info.launches = 3;
+    p->info.path = SPD_PATH_DENSE_DD;
+    p->pending = true;
+    return SPD_OK;
+  }
 
   const int B = dense_lowcols(n);
   const bool reg_ok = (n >= SPB_REG_NMIN && n <= SPB_REG_NMAX && env_int("SP_DENSE_FORCE_SMEM", 0) == 0);
@@ -260,6 +297,9 @@ static int dense_enqueue(spd_dense_plan* p, unsigned long long lo, unsigned long
 
 extern "C" {
 
+void spd_set_quad(int on) { g_quad = on ? 1 : 0; }
+int spd_get_quad(void) { return g_quad; }
+
 int spd_dense_plan_create(int device, const double* mat_t, const double* xbase, int nov,
                           spd_dense_plan** out) {
   if (!mat_t || !xbase || !out) { set_error("null argument"); return SPD_EINVAL; }
@@ -273,12 +313,26 @@ int spd_dense_plan_create(int device, const double* mat_t, const double* xbase, 
   auto fail = [&](int code) { spd_dense_plan_destroy(p); return code; };
   if ((rc = lane_arena_alloc(&L, (size_t)nov * nov * sizeof(double), (void**)&p->d_mat_t)) != SPD_OK) return fail(rc);
   if ((rc = lane_arena_alloc(&L, (size_t)nov * sizeof(double), (void**)&p->d_xbase)) != SPD_OK) return fail(rc);
+  p->quad = g_quad != 0;
+  double xlo[64];
+  if (p->quad) {
+    // low word of the NW start vector: a[j][n-1] - rowsum_j / 2 in long double, minus the double the caller computed
+    for (int j = 0; j < nov; ++j) {
+      long double rs = 0.0L;
+      for (int k = 0; k < nov; ++k) rs += (long double)mat_t[(size_t)k * nov + j];
+      const long double x = (long double)mat_t[(size_t)(nov - 1) * nov + j] - rs / 2.0L;
+      xlo[j] = (double)(x - (long double)xbase[j]);
+    }
+    if ((rc = lane_arena_alloc(&L, (size_t)nov * sizeof(double), (void**)&p->d_xbase_lo)) != SPD_OK) return fail(rc);
+  }
   cudaError_t e;
   // pageable sources: the copies are staged by the runtime before returning, so the caller's
   // arrays are not referenced after this function
   if ((e = cudaSetDevice(device)) != cudaSuccess ||
       (e = cudaMemcpyAsync(p->d_mat_t, mat_t, (size_t)nov * nov * sizeof(double), cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
-      (e = cudaMemcpyAsync(p->d_xbase, xbase, (size_t)nov * sizeof(double), cudaMemcpyHostToDevice, L.stream)) != cudaSuccess) {
+      (e = cudaMemcpyAsync(p->d_xbase, xbase, (size_t)nov * sizeof(double), cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+      (p->quad && ((e = cudaMemcpyAsync(p->d_xbase_lo, xlo, (size_t)nov * sizeof(double), cudaMemcpyHostToDevice, L.stream)) != cudaSuccess ||
+                   (e = cudaStreamSynchronize(L.stream)) != cudaSuccess))) {
     set_error("dense plan upload: %s", cudaGetErrorString(e));
     return fail(SPD_ECUDA);
   }

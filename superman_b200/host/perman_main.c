@@ -11,7 +11,8 @@
  * Also accepted, from the revised front-end (revised_perman/main.cpp:1298-1325): -k <reps> repeats
  * the calculation, -l <device> picks the first GPU, -o (= --reduce) applies the degree compression
  * and the d34 recursion, -u <t> Sinkhorn-scales each matrix to row/column sums t before the kernel;
- * -h -w -q -v -e (precision and launch-shape knobs) are accepted and ignored.
+ * -q (quad calculation precision) selects the double-double dense kernel; -h -w -v -e (half / mixed
+ * precision and launch-shape knobs) are accepted and ignored: FP64 is the lowest precision here.
  * Extra, off by default: `--dm` erases the entries that lie on no perfect matching (Dulmage-
  * Mendelsohn, dead code upstream) before the exact algorithms; the environment variable PERMAN_PRECISION=<digits> adds a second line
  * `Result17: <name> <value>` with that many significant digits (the reference prints 6).
@@ -280,10 +281,11 @@ int main(int argc, char **argv) {
 
   /* the reference's option string (main.cu:347) plus the revised front-end's extra letters
    * (revised_perman/main.cpp:1298): -k reps, -l device id, -o degree compression, -u <threshold>
-   * Sinkhorn scaling, and the precision / launch-shape flags -h -w -q -v -e, which are accepted and
-   * ignored (this engine always computes in FP64 and sizes its own launches) */
+   * Sinkhorn scaling, -q quad (double-double) calculation precision, and the half / mixed precision and
+   * launch-shape flags -h -w -v -e, which are accepted and ignored (FP64 is the lowest precision of this
+   * engine, and it sizes its own launches) */
   static const char *short_options = "bsr:t:f:gd:cap:x:y:z:im:n:hwqk:e:ol:vu:";
-  int reps = 1, first_device = 0, dm = 0;
+  int reps = 1, first_device = 0, dm = 0, quad = 0;
   static const struct option long_options[] = {
       {"binary", 0, NULL, 'b'},        {"sparse", 0, NULL, 's'},       {"preprocessing", 1, NULL, 'r'},
       {"threads", 1, NULL, 't'},       {"file", 1, NULL, 'f'},         {"gpu", 0, NULL, 'g'},
@@ -324,7 +326,8 @@ int main(int argc, char **argv) {
       case 'l': first_device = atoi(optarg); break;     /* flags.device_id */
       case 'u': g_threshold = (double)atoi(optarg); break;   /* flags.scaling_threshold (main.cpp:1466) */
       case 1001: dm = 1; break;
-      case 'h': case 'w': case 'q': case 'v': case 'e': break;
+      case 'q': quad = 1; break;             /* flags.calculation_quad (revised main.cpp:1298-1325): double-double */
+      case 'h': case 'w': case 'v': case 'e': break;
       case '?': return 1;
       default: abort();
     }
@@ -383,6 +386,13 @@ int main(int argc, char **argv) {
 
   sp_matrix m;
   if (sp_matrix_read(filename, !generic, &m) != SP_OK) return report_failure();
+  if (quad && !approximation) {
+    /* -q: the exact ids compute in double-double arithmetic; that engine is the dense one, which returns the
+     * same permanent as SpaRyser / SkipPer (they only skip terms that are exactly zero) */
+    if (!dense) fprintf(stderr, "perman: -q computes through the dense double-double kernel (-s is set aside)\n");
+    dense = 1;
+    sp_set_precision(SP_PRECISION_QUAD);
+  }
   if (dm && !approximation) {
     /* Dulmage-Mendelsohn: entries on no perfect matching cannot contribute (revised util.h:309) */
     int matching = 0;

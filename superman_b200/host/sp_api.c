@@ -24,6 +24,14 @@ int sp_set_first_device(int device) {
 
 int sp_first_device(void) { return g_first_device; }
 
+/* the revised front-end's -q (flags.calculation_quad, revised_perman/flags.h:61-64): dense exact calls made
+ * after sp_set_precision(SP_PRECISION_QUAD) run the double-double kernel */
+int sp_set_precision(int precision) {
+  if (precision != SP_PRECISION_DOUBLE && precision != SP_PRECISION_QUAD) { sp_set_error("unknown precision %d", precision); return SP_EINVAL; }
+  spd_set_quad(precision == SP_PRECISION_QUAD);
+  return SP_OK;
+}
+
 int sp_device_count(void) {
   int n = spd_device_count();
   if (n < 0) sp_set_error("%s", spd_last_error());

@@ -250,6 +250,43 @@ def test_n40_known_answers(sp, oracle):
     assert abs(tot * sp.nw_factor(n) / ex - 1.0) < REL
 
 
+def test_quad_precision_mode(sp, oracle):
+    """-q of the revised front-end (flags.calculation_quad, revised_perman/flags.h:61-64) = double-double
+    arithmetic in the dense kernel: (1) on a generic real matrix it agrees with the long-double oracle to the
+    oracle's own precision; (2) on ragged ranges it is additive; (3) on chesapeake (39 x 39, 0/1), where the
+    FP64 sum is 2e-6 off because the permanent is 1e-12 of the terms it is the sum of, it returns the exact
+    integer 13 173 481 190 272 (tests/golden/known_perman.json, Python-integer DP)."""
+    import _golden
+    rng = np.random.default_rng(77)
+    n = 18
+    A = _rand(rng, n, 0.6, "dbl")
+    want = oracle.perm_ld(A)
+    fp64 = sp.dense_ryser(A, n, 4)
+    sp.set_precision(True)
+    try:
+        st = sp._ffi.SpStats()
+        got = sp.dense_ryser(A, n, 4, stats=st)
+        assert st.path == 8                                   # SPD_PATH_DENSE_DD
+        assert got == pytest.approx(want, rel=5e-16)          # long double carries 64 bits, double-double 106
+        assert abs(got / want - 1.0) <= abs(fp64 / want - 1.0) + 1e-16
+        full = 1 << (n - 1)
+        cuts = [0, 1, 12345, full // 2 + 3, full]
+        tot = sum(sp.dense_ryser_range(A, cuts[i], cuts[i + 1], n) for i in range(4))
+        assert tot * sp.nw_factor(n) == pytest.approx(want, rel=5e-16)
+        for algo in (5, 6):
+            assert sp.dense_ryser(A, n, algo, gpu_num=1) == pytest.approx(want, rel=5e-16)
+        e = _golden.known_perman()["chesapeake"]
+        a = _golden.dense_from(e)
+        exact = int(e["exact"])
+        v = sp.dense_ryser(a, 39, 4, stats=st)
+        assert st.units == 1 << 38 and st.path == 8
+        assert round(v) == exact, (v, exact)
+    finally:
+        sp.set_precision(False)
+    v64 = sp.dense_ryser(a, 39, 4)
+    assert 1e-8 < abs(v64 / exact - 1.0) < 1e-4                # what FP64 Ryser delivers on this matrix (DESIGN 4.5)
+
+
 def test_multi_device_partitions(sp, oracle):
     ndev = sp.device_count()
     if ndev < 2:
