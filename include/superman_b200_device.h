@@ -100,6 +100,13 @@ typedef struct spd_sparse_plan spd_sparse_plan;
  * orders up to 64 run the shared-memory kernel on D. */
 int  spd_sparse_plan_create(int device, const double *dmat_t, const double *xbase, int nov, int skip,
                             spd_sparse_plan **plan);
+/* flags: SPD_SPARSE_REORDER -- the plan will be run over the whole index space [0, 2^(nov-1)) (in whatever
+ * chunks, on whatever devices, all created with the same flag): it may then walk the columns 0 .. nov-2 in an
+ * order of its own choosing (the B most frequently flipped ones are picked to fit the level engine's slots);
+ * without the flag [lo, hi) means the caller's Gray indices. */
+#define SPD_SPARSE_REORDER 1
+int  spd_sparse_plan_create_ex(int device, const double *dmat_t, const double *xbase, int nov, int skip, int flags,
+                               spd_sparse_plan **plan);
 void spd_sparse_plan_destroy(spd_sparse_plan *plan);
 int  spd_sparse_plan_run(spd_sparse_plan *plan, unsigned long long lo, unsigned long long hi,
                          double *sum, spd_run_info *info);

@@ -153,6 +153,108 @@ static bool level_pack(int n, int B, int S0, int S, int R, const std::vector<int
   return true;
 }
 
+// ---- choice of the low columns ------------------------------------------------------------------------
+// A plan that will be run over the WHOLE index space (flag SPD_SPARSE_REORDER: the id entry points, whatever
+// the split over chunks and devices) may walk the columns in any order: the Ryser sum runs over every subset
+// of the columns 0 .. n-2.  The cost of the level engine is set by how many rows have their first non-zero
+// in each of the B most frequently flipped columns (level populations, 2^(B-L) values per row of level L) and
+// by how well they fit the slot configurations that exist (S0 slots for level 0, S for the others).  SortOrder
+// puts the sparsest columns first but knows nothing about either: e.g. level populations (4, 5, 3, 3) need
+// S = 6, while the same matrix with columns 1 and 2 exchanged has (4, 4, 4, 3) and fits S = 4 (15 instead of
+// 18.5 FP64 instructions per index).  So: among the ordered B-tuples of the 9 sparsest columns take the one
+// with the cheapest fitting slot configuration; the other columns keep their order.
+static const int kSlotOpts[6] = {1, 2, 3, 4, 6, 8};
+
+// hot-slot FP64 instructions per index of the cheapest (S0, S) that takes level populations pops[0..B), or < 0
+static double fit_slots(const int* pops, int B) {
+  for (int si = 0; si < 6; ++si) {
+    const int S = kSlotOpts[si];
+    for (int S0 = std::max(1, S - 2); S0 <= S; ++S0) {
+      int free_[4] = {S0, S, S, S};
+      bool ok = true;
+      for (int L = 0; L < B && ok; ++L) {
+        int need = pops[L];
+        for (int LL = L; LL >= 0 && need > 0; --LL) { const int t = std::min(need, free_[LL]); free_[LL] -= t; need -= t; }
+        ok = need == 0;
+      }
+      if (ok) {
+        double c = 0.0;
+        for (int L = 0; L < B; ++L) c += (double)(L == 0 ? S0 : S) * 2.0 * (double)(1 << (B - L));
+        return c / (double)(1 << B);
+      }
+    }
+  }
+  return -1.0;
+}
+
+// perm[k'] = original column at position k' (a permutation of 0 .. n-2; column n-1 stays last)
+static void choose_low_columns(int n, const double* dmat_t, std::vector<int>& perm) {
+  perm.resize(n);
+  for (int k = 0; k < n; ++k) perm[k] = k;
+  if (n < 10) return;
+  std::vector<std::pair<int, int>> cnt;
+  for (int k = 0; k < n - 1; ++k) {
+    int c = 0;
+    for (int j = 0; j < n; ++j) c += dmat_t[(size_t)k * n + j] != 0.0;
+    cnt.push_back({c, k});
+  }
+  std::stable_sort(cnt.begin(), cnt.end());
+  const int K = std::min(9, n - 1);
+  unsigned long long rows_of[9];
+  int cand[9];
+  for (int i = 0; i < K; ++i) {
+    cand[i] = cnt[i].second;
+    rows_of[i] = 0ull;
+    for (int j = 0; j < n; ++j)
+      if (dmat_t[(size_t)cand[i] * n + j] != 0.0) rows_of[i] |= 1ull << j;
+  }
+  // the caller's order as the incumbent (ties keep it)
+  double best = 1e300;
+  int best_t[4] = {0, 1, 2, 3}, best_B = 0;
+  auto eval = [&](const int* t, int B, bool incumbent) {
+    unsigned long long seen = 0ull;
+    int pops[4];
+    for (int L = 0; L < B; ++L) {
+      unsigned long long r;
+      if (incumbent) { r = 0ull; for (int j = 0; j < n; ++j) if (dmat_t[(size_t)t[L] * n + j] != 0.0) r |= 1ull << j; }
+      else r = rows_of[t[L]];
+      pops[L] = __builtin_popcountll(r & ~seen);
+      seen |= r;
+    }
+    return fit_slots(pops, B);
+  };
+  for (int B = 3; B <= 4; ++B) {
+    int t0[4] = {0, 1, 2, 3};
+    const double c0 = eval(t0, B, true);
+    if (c0 >= 0 && c0 < best) { best = c0; best_B = 0; }
+  }
+  for (int B = 3; B <= 4; ++B) {
+    int t[4];
+    for (t[0] = 0; t[0] < K; ++t[0])
+      for (t[1] = 0; t[1] < K; ++t[1]) {
+        if (t[1] == t[0]) continue;
+        for (t[2] = 0; t[2] < K; ++t[2]) {
+          if (t[2] == t[0] || t[2] == t[1]) continue;
+          for (t[3] = 0; t[3] < (B == 4 ? K : 1); ++t[3]) {
+            if (B == 4 && (t[3] == t[0] || t[3] == t[1] || t[3] == t[2])) continue;
+            const double c = eval(t, B, false);
+            if (c >= 0 && c < best - 0.26) {       // at least a quarter instruction per index better than the incumbent
+              best = c; best_B = B;
+              for (int L = 0; L < B; ++L) best_t[L] = cand[t[L]];
+            }
+          }
+        }
+      }
+  }
+  if (best_B == 0) return;
+  std::vector<char> used(n, 0);
+  int pos = 0;
+  for (int L = 0; L < best_B; ++L) { perm[pos++] = best_t[L]; used[best_t[L]] = 1; }
+  for (int k = 0; k < n - 1; ++k)
+    if (!used[k]) perm[pos++] = k;
+  perm[n - 1] = n - 1;
+}
+
 static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned long long hi) {
   const int n = p->n;
   const unsigned long long full = 1ull << (n - 1);
@@ -302,8 +404,28 @@ extern "C" {
 
 int spd_sparse_plan_create(int device, const double* dmat_t, const double* xbase, int nov, int skip,
                            spd_sparse_plan** out) {
-  if (!dmat_t || !xbase || !out) { set_error("null argument"); return SPD_EINVAL; }
+  return spd_sparse_plan_create_ex(device, dmat_t, xbase, nov, skip, 0, out);
+}
+
+int spd_sparse_plan_create_ex(int device, const double* dmat_in, const double* xbase, int nov, int skip, int flags,
+                              spd_sparse_plan** out) {
+  if (!dmat_in || !xbase || !out) { set_error("null argument"); return SPD_EINVAL; }
   if (nov < 2 || nov > 64) { set_error("sparse Ryser supports 2 <= n <= 64 (got %d)", nov); return SPD_ELIMIT; }
+  // column order (see choose_low_columns): only for plans that will cover the whole index space
+  std::vector<double> dperm;
+  const double* dmat_t = dmat_in;
+  if ((flags & SPD_SPARSE_REORDER) && env_int("SP_SPARSE_REORDER", 1) != 0) {
+    std::vector<int> cperm;
+    choose_low_columns(nov, dmat_in, cperm);
+    bool moved = false;
+    for (int k = 0; k < nov; ++k) moved = moved || cperm[k] != k;
+    if (moved) {
+      dperm.resize((size_t)nov * nov);
+      for (int k = 0; k < nov; ++k)
+        memcpy(&dperm[(size_t)k * nov], &dmat_in[(size_t)cperm[k] * nov], (size_t)nov * sizeof(double));
+      dmat_t = dperm.data();
+    }
+  }
   spd_sparse_plan* p = new (std::nothrow) spd_sparse_plan();
   if (!p) return SPD_ENOMEM;
   int rc = lane_acquire(device, &p->lanep);

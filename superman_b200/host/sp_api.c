@@ -318,7 +318,8 @@ typedef struct sparse_job {
 
 static int sparse_open(const void *job, int device, void **plan) {
   const sparse_job *j = (const sparse_job *)job;
-  return spd_sparse_plan_create(device, j->dmat_t, j->x, j->nov, j->skip, (spd_sparse_plan **)plan);
+  /* the id entry points always cover the whole index space: the plan may choose its own column order */
+  return spd_sparse_plan_create_ex(device, j->dmat_t, j->x, j->nov, j->skip, SPD_SPARSE_REORDER, (spd_sparse_plan **)plan);
 }
 static int sparse_launch(void *plan, unsigned long long lo, unsigned long long hi) {
   return spd_sparse_plan_launch((spd_sparse_plan *)plan, lo, hi);
