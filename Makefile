@@ -18,7 +18,7 @@ CONNECT := $(PKG)/libConnect.so
 GROUPS  := 0 1 2 3 4 5 6 7
 CU_SRCS := sp_device sp_dense sp_sparse sp_approx
 CU_OBJS := $(CU_SRCS:%=$(BUILD)/%.o) $(BUILD)/sp_level_inst_b3s0.o $(BUILD)/sp_level_inst_b3s1.o $(BUILD)/sp_level_inst_b4s0.o $(BUILD)/sp_level_inst_b4s1.o $(GROUPS:%=$(BUILD)/sp_dense_inst_g%.o) $(GROUPS:%=$(BUILD)/sp_sparse_inst_g%.o)
-C_SRCS  := sp_sched sp_api sp_matrix sp_reduce sp_connector
+C_SRCS  := sp_sched sp_api sp_matrix sp_reduce sp_connector sp_level
 C_OBJS  := $(C_SRCS:%=$(BUILD)/%.o)
 
 all: $(LIB) $(CLI) $(CONNECT) profiles/resource_usage.txt

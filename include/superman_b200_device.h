@@ -92,21 +92,29 @@ int  spd_dense_plan_wait(spd_dense_plan *plan, double *sum, spd_run_info *info);
 /* ---- SpaRyser / SkipPer --------------------------------------------------------------------- */
 typedef struct spd_sparse_plan spd_sparse_plan;
 
-/* dmat_t[k*nov + j] = D[j][k], where D is the CCS (cptrs, rows, cvals) the reference's sparse
- * kernels iterate over, scattered back to dense form (gpu_exact_sparse.cu:467-476, 521-549);
- * xbase as for the dense plan but with row sums over the non-zeros of mat
- * (gpu_exact_sparse.cu:861-871).  skip != 0 selects SkipPer (zero products are skipped,
- * gpu_exact_sparse.cu:634-666), else SpaRyser.  7 <= nov <= 48 runs the register kernel; other
- * orders up to 64 run the shared-memory kernel on D. */
-int  spd_sparse_plan_create(int device, const double *dmat_t, const double *xbase, int nov, int skip,
-                            spd_sparse_plan **plan);
-/* flags: SPD_SPARSE_REORDER -- the plan will be run over the whole index space [0, 2^(nov-1)) (in whatever
- * chunks, on whatever devices, all created with the same flag): it may then walk the columns 0 .. nov-2 in an
- * order of its own choosing (the B most frequently flipped ones are picked to fit the level engine's slots);
- * without the flag [lo, hi) means the caller's Gray indices. */
-#define SPD_SPARSE_REORDER 1
-int  spd_sparse_plan_create_ex(int device, const double *dmat_t, const double *xbase, int nov, int skip, int flags,
-                               spd_sparse_plan **plan);
+/* A sparse plan as the C host planned it (superman_b200/host/sp_level.c: sp_sparse_plan_open):
+ *   mat_t[k*nov + j] = D[j][k], D the matrix the reference's sparse kernels iterate over -- the CCS (cptrs, rows,
+ *     cvals) scattered back to dense form (gpu_exact_sparse.cu:467-476, 521-549) -- with the ROWS already ordered
+ *     by level (the lowest flippable column holding a non-zero of the row) and the columns in the order the
+ *     plan will walk them; xbase in the same row order (row sums over the non-zeros, gpu_exact_sparse.cu:861-871);
+ *   level_sorted[j] the level of the row now at position j (ascending);
+ *   img: the LevelRyser engine's configuration and packed images (level_reg.cuh), or img->B == 0 for the
+ *     hot/cold register kernel (7 <= nov <= 48) / the shared-memory kernel.
+ * skip != 0 selects SkipPer (zero products are skipped, gpu_exact_sparse.cu:634-666), else SpaRyser.
+ * Nothing is decided on this side: it uploads, loads the kernel, launches and reduces. */
+typedef struct spd_level_image {
+  int B, S0, S, R;              /* low columns, slots of level 0 / of the other levels, register-cold rows */
+  int NC, NCP, HSP;             /* cold rows, padded cold rows, padded register rows */
+  const double *colT_hot;       /* [(nov-1) * HSP] */
+  const double *lowR;           /* [(S0 + (B-1)*S) * (B rounded up to even)] */
+  const double *dcold;          /* [(nov-1) * NCP] */
+  const double *xb_hot;         /* [HSP] */
+  const double *xb_cold;        /* [NCP] */
+  const int *cold_start;        /* [nov - B + 2] */
+  double instr_per_index;       /* the host model's FP64 instructions per Gray index (reported in spd_run_info.aux1) */
+} spd_level_image;
+int  spd_sparse_plan_create_packed(int device, const double *mat_t, const double *xbase, const int *level_sorted,
+                                   int nov, int skip, const spd_level_image *img, spd_sparse_plan **plan);
 void spd_sparse_plan_destroy(spd_sparse_plan *plan);
 int  spd_sparse_plan_run(spd_sparse_plan *plan, unsigned long long lo, unsigned long long hi,
                          double *sum, spd_run_info *info);

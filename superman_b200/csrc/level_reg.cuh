@@ -44,6 +44,7 @@
 #include <stdint.h>
 #include <type_traits>
 #include "ryser_reg.cuh"
+#include "superman_b200_level.h"
 
 
 namespace spb {
@@ -85,20 +86,8 @@ struct LevelLayout {
   __host__ __device__ static constexpr int count(int L) { return L == 0 ? S0 : S; }
 };
 
-// register-cold rows and resident blocks per SM that go with a slot configuration: 20 register rows fit
-// 128 registers (4 blocks of 128 threads per SM), about 30 fit 168 (3 blocks); the SkipPer variant needs a
-// few registers more (tile queue, votes) and gives up four register-cold rows at the edges
-__host__ __device__ constexpr int level_slots(int B, int S0, int S) { return S0 + (B - 1) * S; }
-__host__ __device__ constexpr int level_regcold(int B, int S0, int S, bool skip) {
-  const int hs = level_slots(B, S0, S);
-  int r = hs <= 12 ? 8 : hs <= 16 ? 4 : hs <= 24 ? 8 : 0;
-  if (skip && r >= 4 && (hs + r == 19 || hs + r == 20)) r -= 4;
-  return r;
-}
-__host__ __device__ constexpr int level_minblocks(int B, int S0, int S, bool skip) {
-  const int ht = level_slots(B, S0, S) + level_regcold(B, S0, S, skip);
-  return ht <= 20 ? 4 : (ht <= 30 || !skip) ? 3 : 2;
-}
+// register-cold rows and resident blocks per SM that go with a slot configuration: include/superman_b200_level.h
+// (spl_regcold, spl_minblocks), shared with the C host code that packs the matrix
 
 // bytes of dynamic shared memory the kernel needs (host and device agree through this one function)
 __host__ __device__ inline size_t level_smem_bytes(int n, int B, int HS, int HSP, int LB, int NC, int NCP, int c,

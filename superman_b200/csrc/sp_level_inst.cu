@@ -12,7 +12,7 @@ namespace spb {
 
 template <int B, int S0, int S, bool SKIP>
 static int launch_level(cudaStream_t st, const LevelArgs& a, int sm_count, size_t smem, unsigned* blocks_out) {
-  constexpr int R = level_regcold(B, S0, S, SKIP), MB = level_minblocks(B, S0, S, SKIP);
+  constexpr int R = spl_regcold(B, S0, S, SKIP), MB = spl_minblocks(B, S0, S, SKIP);
   auto kern = level_reg_kernel<B, S0, S, R, SPB_REG_THREADS, MB, SKIP>;
   // always the same constant (see SPB_SMEM_OPTIN_BYTES); also loads the lazily loaded kernel
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES);

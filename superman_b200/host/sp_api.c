@@ -319,7 +319,7 @@ typedef struct sparse_job {
 static int sparse_open(const void *job, int device, void **plan) {
   const sparse_job *j = (const sparse_job *)job;
   /* the id entry points always cover the whole index space: the plan may choose its own column order */
-  return spd_sparse_plan_create_ex(device, j->dmat_t, j->x, j->nov, j->skip, SPD_SPARSE_REORDER, (spd_sparse_plan **)plan);
+  return sp_sparse_plan_open(device, j->dmat_t, j->x, j->nov, j->skip, SP_PLAN_WHOLE_SPACE, (spd_sparse_plan **)plan);
 }
 static int sparse_launch(void *plan, unsigned long long lo, unsigned long long hi) {
   return spd_sparse_plan_launch((spd_sparse_plan *)plan, lo, hi);
@@ -449,9 +449,9 @@ double sp_sparse_ryser_range(const double *mat, const int *cptrs, const int *row
   int rc = sparse_preamble(mat, cptrs, rows, cvals, nov, x, dmat_t);
   if (rc != SP_OK) { free(dmat_t); return fail(stats, rc); }
   spd_sparse_plan *plan = NULL;
-  rc = spd_sparse_plan_create(device, dmat_t, x, nov, skipper, &plan);
+  rc = sp_sparse_plan_open(device, dmat_t, x, nov, skipper, 0, &plan);
   free(dmat_t);
-  if (rc != SPD_OK) { sp_set_error("%s", spd_last_error()); return fail(stats, rc); }
+  if (rc != SPD_OK) return fail(stats, rc);
   double sum = 0.0;
   spd_run_info info;
   rc = spd_sparse_plan_run(plan, (unsigned long long)start, (unsigned long long)end, &sum, &info);

@@ -41,6 +41,14 @@ int sp_sched_run(const sp_job_ops *ops, const void *job, int mode, int gpu_num, 
 unsigned long long sp_sched_boundary(unsigned long long lo, unsigned long long hi,
                                      unsigned long long parts, unsigned long long idx, int align_log2);
 
+/* host-side planning of a sparse exact plan (sp_level.c): column choice, row order, engine and packed images,
+ * then spd_sparse_plan_create_packed.  flags: SP_PLAN_WHOLE_SPACE -- the plan will be run over the whole index
+ * space [0, 2^(nov-1)) (in whatever chunks, on whatever devices, all opened with the same flag) and may walk the
+ * columns 0 .. nov-2 in an order of its own choosing; without it [lo, hi) means the caller's Gray indices. */
+#define SP_PLAN_WHOLE_SPACE 1
+int sp_sparse_plan_open(int device, const double *dmat_t, const double *xbase, int nov, int skip, int flags,
+                        spd_sparse_plan **plan);
+
 void sp_set_error(const char *fmt, ...);
 int sp_first_device(void);            /* what sp_set_first_device stored (sp_api.c) */
 double sp_now_ms(void);
