@@ -46,6 +46,12 @@
 #include "ryser_reg.cuh"
 #include "superman_b200_level.h"
 
+#ifndef SPB_LV_SPLIT
+#define SPB_LV_SPLIT 1      // walk every level in two half-chains
+#endif
+#ifndef SPB_LV_CHMAX
+#define SPB_LV_CHMAX 3      // slots of a level that advance together
+#endif
 
 namespace spb {
 
@@ -81,7 +87,9 @@ struct LevelLayout {
   static constexpr int HS = S0 + (B - 1) * S;   // level slots: [0, S0) level 0, then S per level
   static constexpr int HT = HS + R;             // + register-cold rows
   static constexpr int HSP = HT + (HT & 1);
-  static constexpr int LB = B + (B & 1);
+  static constexpr int LB = B + (B & 1);         // pitch of the host's lowR image
+  static constexpr int MIDX = B;                // shared-memory images: entry B = columns B-2 and B-1 together
+  static constexpr int LBS = SPB_LV_SPLIT ? (B + 2 - (B & 1)) : LB;
   __host__ __device__ static constexpr int base(int L) { return L == 0 ? 0 : S0 + (L - 1) * S; }
   __host__ __device__ static constexpr int count(int L) { return L == 0 ? S0 : S; }
 };
@@ -92,7 +100,8 @@ struct LevelLayout {
 // bytes of dynamic shared memory the kernel needs (host and device agree through this one function)
 __host__ __device__ inline size_t level_smem_bytes(int n, int B, int HS, int HSP, int LB, int NC, int NCP, int c,
                                                    int threads) {
-  const size_t dbl = 2 * (size_t)(n - 1) * HSP + HSP + 2 * (size_t)HS * LB + (size_t)(n - 1) * NCP + HSP + NCP +
+  const int LBS = SPB_LV_SPLIT ? (B + 2 - (B & 1)) : LB;      // LevelLayout::LBS
+  const size_t dbl = 2 * (size_t)(n - 1) * HSP + HSP + 2 * (size_t)HS * LBS + (size_t)(n - 1) * NCP + HSP + NCP +
                      (size_t)(NC + 2) * threads + (size_t)(c - B + 2) * threads;
   return dbl * sizeof(double) + (size_t)((n - B + 2) + (c - B + 1) + NC) * sizeof(int);
 }
@@ -105,7 +114,8 @@ template <int B, int S0, int S, int R, int THREADS, int MINBLOCKS, bool SKIP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 level_reg_kernel(const LevelArgs a) {
   using LL = LevelLayout<B, S0, S, R>;
-  constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
+  constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, LBS = LL::LBS, MIDX = LL::MIDX, NB = 1 << B,
+                WARPS = THREADS / 32;
   extern __shared__ __align__(16) double dsm[];
   const int n = a.n, NC = a.NC, NCP = a.NCP, c = a.c;
   const int nseg = c - B;                       // SP[0 .. nseg]
@@ -113,8 +123,8 @@ level_reg_kernel(const LevelArgs a) {
   double* s_colN = s_colP + (size_t)(n - 1) * HSP;   // -D
   double* s_zero = s_colN + (size_t)(n - 1) * HSP;   //  0 (first block of a tile: X is already explicit)
   double* s_low0 = s_zero + HSP;
-  double* s_low1 = s_low0 + HS * LB;            // column B-1 negated
-  double* s_dcold = s_low1 + HS * LB;
+  double* s_low1 = s_low0 + HS * LBS;           // column B-1 negated
+  double* s_dcold = s_low1 + HS * LBS;
   double* s_xbh = s_dcold + (size_t)(n - 1) * NCP;
   double* s_xbc = s_xbh + HSP;
   double* s_X = s_xbc + NCP;                    // [NC + 2][THREADS]
@@ -131,10 +141,18 @@ level_reg_kernel(const LevelArgs a) {
     s_colN[e] = -v;
   }
   for (int e = threadIdx.x; e < HSP; e += THREADS) s_zero[e] = 0.0;
-  for (int e = threadIdx.x; e < HS * LB; e += THREADS) {
-    const double v = a.lowR[e];
-    s_low0[e] = v;
-    s_low1[e] = (e % LB == B - 1) ? -v : v;
+  for (int e = threadIdx.x; e < HS * LBS; e += THREADS) {
+    const int sl = e / LBS, q = e % LBS;
+    double v0 = 0.0, v1 = 0.0;
+    if (q < B) {
+      v0 = a.lowR[sl * LB + q];
+      v1 = (q == B - 1) ? -v0 : v0;
+    } else if (SPB_LV_SPLIT && q == MIDX && B >= 2) {
+      v0 = a.lowR[sl * LB + B - 2] + a.lowR[sl * LB + B - 1];
+      v1 = a.lowR[sl * LB + B - 2] - a.lowR[sl * LB + B - 1];
+    }
+    s_low0[e] = v0;
+    s_low1[e] = v1;
   }
   for (int e = threadIdx.x; e < (n - 1) * NCP; e += THREADS) s_dcold[e] = a.dcold[e];
   for (int e = threadIdx.x; e < HT; e += THREADS) s_xbh[e] = a.xb_hot[e];
@@ -255,7 +273,7 @@ level_reg_kernel(const LevelArgs a) {
         }
         const uint32_t hi_addr = sm_colP + ((blk != 0) ? (uint32_t)(k * HSP * 8) + (up ? neg_off : 0u) : zero_off);
         // column B-1 flips in the middle of the block; its direction is bit B of the index
-        const uint32_t low_addr = sm_low0 + (uint32_t)((blk & 1) * (HS * LB * 8));
+        const uint32_t low_addr = sm_low0 + (uint32_t)((blk & 1) * (HS * LBS * 8));
 
         // ---- cold rows of level <= k: update, refresh SP[z .. 0] (per-thread direction) ----
         double Q;
@@ -296,7 +314,7 @@ level_reg_kernel(const LevelArgs a) {
 #pragma unroll
           for (int i = 0; i < HS; ++i) {
             double mt;
-            lds_f64(low_addr + (uint32_t)((i * LB + (B - 1)) * 8), mt);
+            lds_f64(low_addr + (uint32_t)((i * LBS + (B - 1)) * 8), mt);
             double d;
             lds_f64(hi_addr + (uint32_t)(i * 8), d);
             xh[i] = (xh[i] + d) + mt;
@@ -310,7 +328,7 @@ level_reg_kernel(const LevelArgs a) {
           static_for<0, B>([&](auto Lc) {
             constexpr int L = decltype(Lc)::value;
             constexpr int SL = LL::count(L), base = LL::base(L);
-            constexpr int NG = (SL + 2) / 3;        // chain groups of at most 3 slots, sizes as even as possible
+            constexpr int NG = (SL + SPB_LV_CHMAX - 1) / SPB_LV_CHMAX;   // chain groups of at most CHMAX slots, sizes as even as possible
             constexpr int cnt = NB >> L;
             double PL[NG > 1 ? cnt : 1];            // products across chain groups
             double tmp = 0.0, prev = 0.0;
@@ -318,41 +336,78 @@ level_reg_kernel(const LevelArgs a) {
               constexpr int gi = decltype(Gc)::value;
               constexpr int t0 = gi * (SL / NG) + (gi < SL % NG ? gi : SL % NG);
               constexpr int CH = SL / NG + (gi < SL % NG ? 1 : 0);
-              double v[CH], m[CH][LB];
+              // the level's walk is cut in two halves that advance side by side (twice the independent chains):
+              // the second half starts at u = 2^(B-1), where X differs from the block start by the columns
+              // B-2 and B-1 (every lower column has flipped an even number of times) -- the image's entry MIDX
+              constexpr bool SPLIT = SPB_LV_SPLIT && cnt >= 4;
+              constexpr int half = SPLIT ? cnt / 2 : cnt;
+              double v[CH], vb[SPLIT ? CH : 1], m[CH][LB];
 #pragma unroll
               for (int t = 0; t < CH; ++t) {
                 const int i = base + t0 + t;
 #pragma unroll
                 for (int qq = (L & ~1); qq < LB; qq += 2)       // only columns >= L flip inside this level
-                  lds_f64x2(low_addr + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
+                  lds_f64x2(low_addr + (uint32_t)((i * LBS + qq) * 8), m[t][qq], m[t][qq + 1]);
                 double d;
                 lds_f64(hi_addr + (uint32_t)(i * 8), d);
                 v[t] = xh[i] + d;
+                if constexpr (SPLIT) {
+                  double mid;
+                  lds_f64(low_addr + (uint32_t)((i * LBS + MIDX) * 8), mid);
+                  vb[t] = v[t] + mid;
+                }
               }
+              double prevb = 0.0, tmpb = 0.0;
 #pragma unroll
-              for (int w = 0; w < cnt; ++w) {
-                if (w > 0) {
-                  const int u = w << L;
-                  const int K = ctz_c(u);
+              for (int w2 = 0; w2 < half; ++w2) {
 #pragma unroll
-                  for (int t = 0; t < CH; ++t) {
-                    if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
-                    else v[t] -= m[t][K];
+                for (int hb = 0; hb < (SPLIT ? 2 : 1); ++hb) {
+                  const int w = w2 + hb * half;
+                  double pr;
+                  if (hb == 0) {
+                    if (w2 > 0) {
+                      const int u = w << L;
+                      const int K = ctz_c(u);
+#pragma unroll
+                      for (int t = 0; t < CH; ++t) {
+                        if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
+                        else v[t] -= m[t][K];
+                      }
+                    }
+                    pr = v[0];
+#pragma unroll
+                    for (int t = 1; t < CH; ++t) pr *= v[t];
+                  } else {
+                    if (w2 > 0) {
+                      const int u = w << L;
+                      const int K = ctz_c(u);
+#pragma unroll
+                      for (int t = 0; t < CH; ++t) {
+                        if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) vb[t] += m[t][K];
+                        else vb[t] -= m[t][K];
+                      }
+                    }
+                    pr = vb[0];
+#pragma unroll
+                    for (int t = 1; t < CH; ++t) pr *= vb[t];
+                  }
+                  if constexpr (NG > 1) {
+                    if (gi > 0) pr *= PL[w];
+                    if (gi < NG - 1) { PL[w] = pr; continue; }
+                  }
+                  // fold: level 0 pairs up with alternating signs, level L combines the sums below it
+                  double& pv = (hb == 0) ? prev : prevb;
+                  double& tm = (hb == 0) ? tmp : tmpb;
+                  if (L == 0) {
+                    if ((w & 1) == 0) pv = pr; else T[w >> 1] = pv - pr;
+                  } else {
+                    if ((w & 1) == 0) tm = pr * T[w]; else T[w >> 1] = fma(pr, T[w], tm);
                   }
                 }
-                double pr = v[0];
+              }
+              if constexpr (SPLIT) {
 #pragma unroll
-                for (int t = 1; t < CH; ++t) pr *= v[t];
-                if constexpr (NG > 1) {
-                  if (gi > 0) pr *= PL[w];
-                  if (gi < NG - 1) { PL[w] = pr; continue; }
-                }
-                // fold: level 0 pairs up with alternating signs, level L combines the sums below it
-                if (L == 0) {
-                  if ((w & 1) == 0) prev = pr; else T[w >> 1] = prev - pr;
-                } else {
-                  if ((w & 1) == 0) tmp = pr * T[w]; else T[w >> 1] = fma(pr, T[w], tmp);
-                }
+                for (int t = 0; t < CH; ++t) v[t] = vb[t];
               }
 #pragma unroll
               for (int t = 0; t < CH; ++t) xh[base + t0 + t] = v[t];
