@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsuperman_b200.so")
+# SUPERMAN_B200_LIB: development only (tools/level_variants.py compares kernel variants built side by side)
+LIB_PATH = os.environ.get("SUPERMAN_B200_LIB") or os.path.join(_HERE, "libsuperman_b200.so")
 
 SP_MAX_DEVICES = 16
 

@@ -18,12 +18,10 @@
 //   register-cold rows: the R cold rows of lowest level (the ones refreshed most often) also stay
 //     in registers: one update and one multiply per block, in straight-line code.
 //   cold rows (level >= B): X in shared memory (X[row][thread], conflict-free), sorted by level.
-//     Their product Q is kept as suffix products SP[i] = prod(rows of level >= B+i): the block that
-//     flips high column k only touches the rows of level <= k, refreshes SP[k-B .. 0] and reuses
-//     SP[k-B+1].  Half of the blocks flip column B, a quarter column B+1, ...: the expected number
-//     of cold rows touched per block is small.  Levels without rows share one SP slot with the
-//     next level that has some (s_grp), and every row knows the slot it closes (s_slot, a dummy
-//     slot for most rows), so the refresh is ONE flat loop over the touched rows.
+//     Their product Q is kept as suffix products SP[j] = prod(rows j .. NC-1): the block that flips high
+//     column k only touches the rows of level <= k (rows [0, top), top from the constant bank), refreshes
+//     SP[top-1 .. 0] and reuses SP[top].  Half of the blocks flip column B, a quarter column B+1, ...: the
+//     expected number of cold rows touched per block is small.
 //
 // As in the dense kernel, the direction of a register row's update is not a +/-1.0 factor but a
 // choice between shared-memory images (D, -D, zeros; two low-column images), so the block loop's
@@ -46,12 +44,7 @@
 #include "ryser_reg.cuh"
 #include "superman_b200_level.h"
 
-#ifndef SPB_LV_SPLIT
-#define SPB_LV_SPLIT 1      // walk every level in two half-chains
-#endif
-#ifndef SPB_LV_CHMAX
-#define SPB_LV_CHMAX 3      // slots of a level that advance together
-#endif
+#define SPB_LV_MAXSEG 64    // n - B + 2 <= 63
 
 namespace spb {
 
@@ -71,14 +64,19 @@ struct LevelArgs {
   const double* dcold;       // [(n-1) * NCP]   dcold[k*NCP + jc]    = D[cold row jc][k]
   const double* xb_hot;      // [HS + R]
   const double* xb_cold;     // [NC]
-  const int* cold_start;     // [n - B + 2]     first cold row of level >= B+i
+  int cold_start[SPB_LV_MAXSEG];   // [n - B + 2]  first cold row of level >= B+i (read through the constant bank)
   double* partials;          // [n_chunks]
   unsigned long long* visited;   // [n_chunks]  blocks of 2^B indices evaluated
   unsigned int* queue;       // {next chunk, warps that have left}; zero between launches
+  // two phases of tiles: chunks [0, n_chunks_big) hold tiles of 2^c indices starting at tile tile_first, the
+  // chunks after them tiles of 2^c_small starting at tile tile_first_small (in units of 2^c_small): the last
+  // part of a range goes out in small pieces so that the persistent warps finish together
   unsigned long long tile_first, n_tiles;
-  unsigned int n_chunks;     // chunk = tiles_per_warp consecutive tiles
+  unsigned long long tile_first_small, n_tiles_small;
+  unsigned int n_chunks;     // chunk = tiles_per_warp consecutive tiles (both phases)
+  unsigned int n_chunks_big;
   int n, NC, NCP, HSP;
-  int c;
+  int c, c_small;
   int tiles_per_warp;
 };
 
@@ -87,9 +85,7 @@ struct LevelLayout {
   static constexpr int HS = S0 + (B - 1) * S;   // level slots: [0, S0) level 0, then S per level
   static constexpr int HT = HS + R;             // + register-cold rows
   static constexpr int HSP = HT + (HT & 1);
-  static constexpr int LB = B + (B & 1);         // pitch of the host's lowR image
-  static constexpr int MIDX = B;                // shared-memory images: entry B = columns B-2 and B-1 together
-  static constexpr int LBS = SPB_LV_SPLIT ? (B + 2 - (B & 1)) : LB;
+  static constexpr int LB = B + (B & 1);
   __host__ __device__ static constexpr int base(int L) { return L == 0 ? 0 : S0 + (L - 1) * S; }
   __host__ __device__ static constexpr int count(int L) { return L == 0 ? S0 : S; }
 };
@@ -98,40 +94,34 @@ struct LevelLayout {
 // (spl_regcold, spl_minblocks), shared with the C host code that packs the matrix
 
 // bytes of dynamic shared memory the kernel needs (host and device agree through this one function)
-__host__ __device__ inline size_t level_smem_bytes(int n, int B, int HS, int HSP, int LB, int NC, int NCP, int c,
-                                                   int threads) {
-  const int LBS = SPB_LV_SPLIT ? (B + 2 - (B & 1)) : LB;      // LevelLayout::LBS
-  const size_t dbl = 2 * (size_t)(n - 1) * HSP + HSP + 2 * (size_t)HS * LBS + (size_t)(n - 1) * NCP + HSP + NCP +
-                     (size_t)(NC + 2) * threads + (size_t)(c - B + 2) * threads;
-  return dbl * sizeof(double) + (size_t)((n - B + 2) + (c - B + 1) + NC) * sizeof(int);
+__host__ __device__ inline size_t level_smem_bytes(int n, int B, int HS, int HSP, int LB, int NC, int NCP, int threads) {
+  const size_t dbl = 2 * (size_t)(n - 1) * HSP + HSP + 2 * (size_t)HS * LB + (size_t)(n - 1) * NCP + HSP + NCP +
+                     (size_t)(NC + 2) * threads + (size_t)(NC + 1) * threads;
+  return dbl * sizeof(double);
 }
 
-// dynamic shared memory (doubles):  colP | colN | zero | low0 | low1 | dcold | xb_hot | xb_cold | Xc[NC + 2][T] | SP[c-B+2][T]
+// dynamic shared memory (doubles):  colP | colN | zero | low0 | low1 | dcold | xb_hot | xb_cold | Xc[NC + 2][T] | SP[NC + 1][T]
 // (rows NC and NC+1 of Xc hold each thread's running sum and evaluated-block count for its current chunk: they
-// are kept out of the register file, which the block loop needs, and share the thread's X address register)
-// then ints: cold_start[n-B+2] | grp[c-B+1] | slot[NC]
+// are kept out of the register file, which the block loop needs, and share the thread's X address register;
+// SP[j] = product of the cold rows j .. NC-1, SP[NC] = 1)
 template <int B, int S0, int S, int R, int THREADS, int MINBLOCKS, bool SKIP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
-level_reg_kernel(const LevelArgs a) {
+level_reg_kernel(const __grid_constant__ LevelArgs a) {
   using LL = LevelLayout<B, S0, S, R>;
-  constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, LBS = LL::LBS, MIDX = LL::MIDX, NB = 1 << B,
-                WARPS = THREADS / 32;
+  constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
+  constexpr int G = (HT > 24) ? 2 : 4;          // cold rows refreshed together (fewer where registers are short)
   extern __shared__ __align__(16) double dsm[];
-  const int n = a.n, NC = a.NC, NCP = a.NCP, c = a.c;
-  const int nseg = c - B;                       // SP[0 .. nseg]
+  const int n = a.n, NC = a.NC, NCP = a.NCP;
   double* s_colP = dsm;                         //  D
   double* s_colN = s_colP + (size_t)(n - 1) * HSP;   // -D
   double* s_zero = s_colN + (size_t)(n - 1) * HSP;   //  0 (first block of a tile: X is already explicit)
   double* s_low0 = s_zero + HSP;
-  double* s_low1 = s_low0 + HS * LBS;           // column B-1 negated
-  double* s_dcold = s_low1 + HS * LBS;
+  double* s_low1 = s_low0 + HS * LB;           // column B-1 negated
+  double* s_dcold = s_low1 + HS * LB;
   double* s_xbh = s_dcold + (size_t)(n - 1) * NCP;
   double* s_xbc = s_xbh + HSP;
   double* s_X = s_xbc + NCP;                    // [NC + 2][THREADS]
-  double* s_SP = s_X + (size_t)(NC + 2) * THREADS;   // [nseg + 2][THREADS]: one per group of levels + a dummy
-  int* s_cs = reinterpret_cast<int*>(s_SP + (size_t)(nseg + 2) * THREADS);
-  int* s_grp = s_cs + (n - B + 2);              // [nseg + 1]  SP slot of segment seg
-  int* s_slot = s_grp + (nseg + 1);             // [NC]        SP slot closed by cold row jc (or the dummy)
+  double* s_SP = s_X + (size_t)(NC + 2) * THREADS;   // [NC + 1][THREADS]: suffix products of the cold rows
   __shared__ unsigned long long tq[WARPS][64];  // surviving tiles of the warp's current chunk
   __shared__ unsigned int s_chunk[WARPS];       // the chunk each warp is working on (same reason)
 
@@ -141,37 +131,15 @@ level_reg_kernel(const LevelArgs a) {
     s_colN[e] = -v;
   }
   for (int e = threadIdx.x; e < HSP; e += THREADS) s_zero[e] = 0.0;
-  for (int e = threadIdx.x; e < HS * LBS; e += THREADS) {
-    const int sl = e / LBS, q = e % LBS;
-    double v0 = 0.0, v1 = 0.0;
-    if (q < B) {
-      v0 = a.lowR[sl * LB + q];
-      v1 = (q == B - 1) ? -v0 : v0;
-    } else if (SPB_LV_SPLIT && q == MIDX && B >= 2) {
-      v0 = a.lowR[sl * LB + B - 2] + a.lowR[sl * LB + B - 1];
-      v1 = a.lowR[sl * LB + B - 2] - a.lowR[sl * LB + B - 1];
-    }
-    s_low0[e] = v0;
-    s_low1[e] = v1;
+  for (int e = threadIdx.x; e < HS * LB; e += THREADS) {
+    const double v = a.lowR[e];
+    s_low0[e] = v;
+    s_low1[e] = (e % LB == B - 1) ? -v : v;
   }
   for (int e = threadIdx.x; e < (n - 1) * NCP; e += THREADS) s_dcold[e] = a.dcold[e];
   for (int e = threadIdx.x; e < HT; e += THREADS) s_xbh[e] = a.xb_hot[e];
   for (int e = threadIdx.x; e < NC; e += THREADS) s_xbc[e] = a.xb_cold[e];
-  for (int e = threadIdx.x; e < n - B + 2; e += THREADS) s_cs[e] = a.cold_start[e];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // segments with the same first row (levels without rows) share a slot
-    int g = 0;
-    s_grp[0] = 0;
-    for (int seg = 1; seg <= nseg; ++seg) {
-      if (s_cs[seg] != s_cs[seg - 1]) ++g;
-      s_grp[seg] = g;
-    }
-    const int dummy = g + 1;
-    for (int jc = 0; jc < NC; ++jc) s_slot[jc] = dummy;
-    for (int seg = 0; seg <= nseg; ++seg)
-      if (s_cs[seg] < NC) s_slot[s_cs[seg]] = s_grp[seg];
-  }
+  s_SP[(size_t)NC * THREADS + threadIdx.x] = 1.0;
   __syncthreads();
 
   const uint32_t sm_colP = (uint32_t)__cvta_generic_to_shared(s_colP);
@@ -181,8 +149,6 @@ level_reg_kernel(const LevelArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* myX = s_X + threadIdx.x;
   double* mySP = s_SP + threadIdx.x;
-  const int tc_first = s_cs[nseg];              // cold rows >= this index are constant over a tile
-  const int nblk = 1 << (c - B);
 
 #pragma unroll 1
   for (;;) {
@@ -192,9 +158,16 @@ level_reg_kernel(const LevelArgs a) {
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if (chunk >= a.n_chunks) break;
     if (lane == 0) s_chunk[wib] = chunk;
-    unsigned long long cand = (unsigned long long)chunk * (unsigned long long)a.tiles_per_warp;
+    // (SpaRyser launches have one phase: c stays a launch constant, out of the register file)
+    const bool big = !SKIP || chunk < a.n_chunks_big;
+    const int c = big ? a.c : a.c_small;
+    const unsigned long long tile_first = big ? a.tile_first : a.tile_first_small;
+    const unsigned long long n_tiles = big ? a.n_tiles : a.n_tiles_small;
+    const int tc_first = a.cold_start[c - B];     // cold rows >= this index are constant over a tile
+    const int nblk = 1 << (c - B);
+    unsigned long long cand = (unsigned long long)(chunk - (big ? 0u : a.n_chunks_big)) * (unsigned long long)a.tiles_per_warp;
     unsigned long long cand_hi = cand + (unsigned long long)a.tiles_per_warp;
-    if (cand_hi > a.n_tiles) cand_hi = a.n_tiles;
+    if (cand_hi > n_tiles) cand_hi = n_tiles;
 
     myX[(size_t)NC * THREADS] = 0.0;
     reinterpret_cast<unsigned long long*>(myX)[(size_t)(NC + 1) * THREADS] = 0ull;
@@ -206,7 +179,7 @@ level_reg_kernel(const LevelArgs a) {
         const unsigned long long t = cand + lane;
         bool alive = t < cand_hi;
         if (SKIP && tc_first < NC) {
-          const unsigned long long s = (a.tile_first + (alive ? t : cand)) << c;
+          const unsigned long long s = (tile_first + (alive ? t : cand)) << c;
           const unsigned long long g = s ^ (s >> 1);
           for (int jc = tc_first; jc < NC; ++jc) {
             double xr = s_xbc[jc];
@@ -231,7 +204,7 @@ level_reg_kernel(const LevelArgs a) {
       __syncwarp();
 
       // ---- explicit X at the tile start (cf. gpu_exact_sparse.cu:497-503) -----------------------
-      const unsigned long long s = (a.tile_first + my_tile) << c;
+      const unsigned long long s = (tile_first + my_tile) << c;
       const unsigned long long g = s ^ (s >> 1);
       double xh[HT];
 #pragma unroll
@@ -245,16 +218,16 @@ level_reg_kernel(const LevelArgs a) {
       {
         // cold rows, from the last (highest level) to the first, building the suffix products
         double run = 1.0;
-        if (tc_first == NC) mySP[s_grp[nseg] * THREADS] = 1.0;     // no tile-constant rows: empty product
         for (int jc = NC - 1; jc >= 0; --jc) {
           double x = s_xbc[jc];
           for (int k = c - 1; k < n - 1; ++k)
             x = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], x);
           myX[jc * THREADS] = x;
           run *= x;
-          mySP[s_slot[jc] * THREADS] = run;
+          mySP[jc * THREADS] = run;
         }
       }
+      const int tile_odd = (int)((tile_first + my_tile) & 1ull);
 
 #pragma unroll 1
       for (int blk = 0; blk < nblk; ++blk) {
@@ -264,7 +237,6 @@ level_reg_kernel(const LevelArgs a) {
         const int z = (blk != 0) ? (__ffs(blk) - 1) : 0;     // k - B
         const int k = B + z;
         const int up = (k + 1 < c) ? ((blk >> (z + 1)) & 1) : 0;
-        const int tile_odd = (int)((a.tile_first + my_tile) & 1ull);
         if (blk == (nblk >> 1)) {
           const double f = -2.0 * (double)tile_odd;
           const double* col = s_colP + (c - 1) * HSP;
@@ -273,27 +245,49 @@ level_reg_kernel(const LevelArgs a) {
         }
         const uint32_t hi_addr = sm_colP + ((blk != 0) ? (uint32_t)(k * HSP * 8) + (up ? neg_off : 0u) : zero_off);
         // column B-1 flips in the middle of the block; its direction is bit B of the index
-        const uint32_t low_addr = sm_low0 + (uint32_t)((blk & 1) * (HS * LBS * 8));
+        const uint32_t low_addr = sm_low0 + (uint32_t)((blk & 1) * (HS * LB * 8));
 
-        // ---- cold rows of level <= k: update, refresh SP[z .. 0] (per-thread direction) ----
+        // ---- cold rows of level <= k (rows [0, top)): update, refresh their suffix products (per-thread
+        // direction).  G rows at a time, every load before the first store, so that the shared-memory
+        // round trips of a group overlap; only the product chain is serial. ----
         double Q;
-        if (blk != 0) {
-          const int upt = (k + 1 < c) ? up : tile_odd;
-          const double sg = upt ? -1.0 : 1.0;
-          double run = mySP[s_grp[z + 1] * THREADS];
-          const double* dk = s_dcold + k * NCP;
-          double* px = myX + (size_t)s_cs[z + 1] * THREADS;
-          int jc = s_cs[z + 1] - 1;
-          for (; jc >= 0; --jc) {
-            px -= THREADS;
-            const double x = fma(sg, dk[jc], *px);
-            *px = x;
-            run *= x;
-            mySP[s_slot[jc] * THREADS] = run;
+        {
+          const int top = (blk != 0) ? a.cold_start[z + 1] : 0;
+          double run = mySP[(size_t)top * THREADS];
+          if (top > 0) {
+            const int upt = (k + 1 < c) ? up : tile_odd;
+            const double sg = upt ? -1.0 : 1.0;
+            const double* dk = s_dcold + k * NCP;
+            int jc = top;
+            if (jc & (G - 1)) {
+              // the rows that do not fill a group: same code with the missing rows switched off
+              const int r = jc & (G - 1);
+              jc -= r;
+              double* px = myX + (size_t)jc * THREADS;
+              double* ps = mySP + (size_t)jc * THREADS;
+              double x[G], pr[G];
+#pragma unroll
+              for (int i = 0; i < G - 1; ++i) x[i] = fma(sg, (i < r) ? dk[jc + i] : 0.0, (i < r) ? px[i * THREADS] : 1.0);
+#pragma unroll
+              for (int i = G - 2; i >= 0; --i) { run *= x[i]; pr[i] = run; }
+#pragma unroll
+              for (int i = 0; i < G - 1; ++i)
+                if (i < r) { px[i * THREADS] = x[i]; ps[i * THREADS] = pr[i]; }
+            }
+            while (jc > 0) {
+              jc -= G;
+              double* px = myX + (size_t)jc * THREADS;
+              double* ps = mySP + (size_t)jc * THREADS;
+              double x[G], pr[G];
+#pragma unroll
+              for (int i = 0; i < G; ++i) x[i] = fma(sg, dk[jc + i], px[i * THREADS]);
+#pragma unroll
+              for (int i = G - 1; i >= 0; --i) { run *= x[i]; pr[i] = run; }
+#pragma unroll
+              for (int i = 0; i < G; ++i) { px[i * THREADS] = x[i]; ps[i * THREADS] = pr[i]; }
+            }
           }
           Q = run;
-        } else {
-          Q = mySP[0];
         }
 
         // ---- register-cold rows: one update, one multiply ----
@@ -314,7 +308,7 @@ level_reg_kernel(const LevelArgs a) {
 #pragma unroll
           for (int i = 0; i < HS; ++i) {
             double mt;
-            lds_f64(low_addr + (uint32_t)((i * LBS + (B - 1)) * 8), mt);
+            lds_f64(low_addr + (uint32_t)((i * LB + (B - 1)) * 8), mt);
             double d;
             lds_f64(hi_addr + (uint32_t)(i * 8), d);
             xh[i] = (xh[i] + d) + mt;
@@ -328,7 +322,7 @@ level_reg_kernel(const LevelArgs a) {
           static_for<0, B>([&](auto Lc) {
             constexpr int L = decltype(Lc)::value;
             constexpr int SL = LL::count(L), base = LL::base(L);
-            constexpr int NG = (SL + SPB_LV_CHMAX - 1) / SPB_LV_CHMAX;   // chain groups of at most CHMAX slots, sizes as even as possible
+            constexpr int NG = (SL + 2) / 3;        // chain groups of at most 3 slots, sizes as even as possible
             constexpr int cnt = NB >> L;
             double PL[NG > 1 ? cnt : 1];            // products across chain groups
             double tmp = 0.0, prev = 0.0;
@@ -336,78 +330,41 @@ level_reg_kernel(const LevelArgs a) {
               constexpr int gi = decltype(Gc)::value;
               constexpr int t0 = gi * (SL / NG) + (gi < SL % NG ? gi : SL % NG);
               constexpr int CH = SL / NG + (gi < SL % NG ? 1 : 0);
-              // the level's walk is cut in two halves that advance side by side (twice the independent chains):
-              // the second half starts at u = 2^(B-1), where X differs from the block start by the columns
-              // B-2 and B-1 (every lower column has flipped an even number of times) -- the image's entry MIDX
-              constexpr bool SPLIT = SPB_LV_SPLIT && cnt >= 4;
-              constexpr int half = SPLIT ? cnt / 2 : cnt;
-              double v[CH], vb[SPLIT ? CH : 1], m[CH][LB];
+              double v[CH], m[CH][LB];
 #pragma unroll
               for (int t = 0; t < CH; ++t) {
                 const int i = base + t0 + t;
 #pragma unroll
                 for (int qq = (L & ~1); qq < LB; qq += 2)       // only columns >= L flip inside this level
-                  lds_f64x2(low_addr + (uint32_t)((i * LBS + qq) * 8), m[t][qq], m[t][qq + 1]);
+                  lds_f64x2(low_addr + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
                 double d;
                 lds_f64(hi_addr + (uint32_t)(i * 8), d);
                 v[t] = xh[i] + d;
-                if constexpr (SPLIT) {
-                  double mid;
-                  lds_f64(low_addr + (uint32_t)((i * LBS + MIDX) * 8), mid);
-                  vb[t] = v[t] + mid;
-                }
               }
-              double prevb = 0.0, tmpb = 0.0;
 #pragma unroll
-              for (int w2 = 0; w2 < half; ++w2) {
+              for (int w = 0; w < cnt; ++w) {
+                if (w > 0) {
+                  const int u = w << L;
+                  const int K = ctz_c(u);
 #pragma unroll
-                for (int hb = 0; hb < (SPLIT ? 2 : 1); ++hb) {
-                  const int w = w2 + hb * half;
-                  double pr;
-                  if (hb == 0) {
-                    if (w2 > 0) {
-                      const int u = w << L;
-                      const int K = ctz_c(u);
-#pragma unroll
-                      for (int t = 0; t < CH; ++t) {
-                        if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
-                        else v[t] -= m[t][K];
-                      }
-                    }
-                    pr = v[0];
-#pragma unroll
-                    for (int t = 1; t < CH; ++t) pr *= v[t];
-                  } else {
-                    if (w2 > 0) {
-                      const int u = w << L;
-                      const int K = ctz_c(u);
-#pragma unroll
-                      for (int t = 0; t < CH; ++t) {
-                        if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) vb[t] += m[t][K];
-                        else vb[t] -= m[t][K];
-                      }
-                    }
-                    pr = vb[0];
-#pragma unroll
-                    for (int t = 1; t < CH; ++t) pr *= vb[t];
-                  }
-                  if constexpr (NG > 1) {
-                    if (gi > 0) pr *= PL[w];
-                    if (gi < NG - 1) { PL[w] = pr; continue; }
-                  }
-                  // fold: level 0 pairs up with alternating signs, level L combines the sums below it
-                  double& pv = (hb == 0) ? prev : prevb;
-                  double& tm = (hb == 0) ? tmp : tmpb;
-                  if (L == 0) {
-                    if ((w & 1) == 0) pv = pr; else T[w >> 1] = pv - pr;
-                  } else {
-                    if ((w & 1) == 0) tm = pr * T[w]; else T[w >> 1] = fma(pr, T[w], tm);
+                  for (int t = 0; t < CH; ++t) {
+                    if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
+                    else v[t] -= m[t][K];
                   }
                 }
-              }
-              if constexpr (SPLIT) {
+                double pr = v[0];
 #pragma unroll
-                for (int t = 0; t < CH; ++t) v[t] = vb[t];
+                for (int t = 1; t < CH; ++t) pr *= v[t];
+                if constexpr (NG > 1) {
+                  if (gi > 0) pr *= PL[w];
+                  if (gi < NG - 1) { PL[w] = pr; continue; }
+                }
+                // fold: level 0 pairs up with alternating signs, level L combines the sums below it
+                if (L == 0) {
+                  if ((w & 1) == 0) prev = pr; else T[w >> 1] = prev - pr;
+                } else {
+                  if ((w & 1) == 0) tmp = pr * T[w]; else T[w >> 1] = fma(pr, T[w], tmp);
+                }
               }
 #pragma unroll
               for (int t = 0; t < CH; ++t) xh[base + t0 + t] = v[t];

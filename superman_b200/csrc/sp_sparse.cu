@@ -64,7 +64,7 @@ struct spd_sparse_plan {
   int lvB = 0, lvS0 = 0, lvS = 0, lvR = 0, NC = 0, NCP = 0, HSP = 0;
   double lv_instr = 0.0;       // FP64 instructions per Gray index of the chosen engine (host model)
   double *d_colT_hot = nullptr, *d_lowR = nullptr, *d_dcold = nullptr, *d_xb_hot = nullptr, *d_xb_cold = nullptr;
-  int* d_cold_start = nullptr;
+  int cold_start[SPB_LV_MAXSEG] = {0};
   bool pending = false;
   spd_run_info info;
 };
@@ -142,21 +142,42 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
     while (tiles_left) {
       if (use_level) {
         // persistent grid: every warp pulls chunks of tiles_per_warp tiles from the lane's atomic queue and
-        // leaves one partial sum (and one visited count) per chunk; at most 2^20 chunks per launch
-        unsigned long long chunks = (tiles_left + (unsigned)tiles_per_warp - 1) / (unsigned)tiles_per_warp;
-        if (chunks > max_blocks) chunks = max_blocks;
-        unsigned long long nt = chunks * (unsigned)tiles_per_warp;
-        if (nt > tiles_left) nt = tiles_left;
+        // leaves one partial sum (and one visited count) per chunk; at most 2^20 chunks per launch.  The last
+        // eighth of a SkipPer launch goes out in tiles a quarter as long, so that the warps finish together (a chunk of
+        // full-length tiles is 1/14 of a warp's share at config-3 size).
+        // (SkipPer only: its chunks are 8 tiles per lane; SpaRyser's one-tile chunks lose less at the end than
+        // short tiles cost)
+        int c_small = p->skip ? c - env_int("SP_LEVEL_TAIL_SHIFT", 2) : c;
+        if (c_small < B + 1) c_small = B + 1;
+        unsigned long long nt = tiles_left;                          // tiles of 2^c taken by this launch
+        unsigned long long big = nt, small = 0;
+        if (c_small < c && nt >= 8ull * (unsigned)tiles_per_warp) {
+          big = (nt - nt / 8) / (unsigned)tiles_per_warp * (unsigned)tiles_per_warp;
+          small = (nt - big) << (c - c_small);
+        }
+        unsigned long long chunks_big = (big + (unsigned)tiles_per_warp - 1) / (unsigned)tiles_per_warp;
+        unsigned long long chunks_small = (small + (unsigned)tiles_per_warp - 1) / (unsigned)tiles_per_warp;
+        if (chunks_big + chunks_small > max_blocks) {
+          // too long for one launch: full-length tiles only, the rest comes with the next trip
+          if (nt > max_blocks * (unsigned)tiles_per_warp) nt = max_blocks * (unsigned)tiles_per_warp;
+          big = nt; small = 0;
+          chunks_big = (big + (unsigned)tiles_per_warp - 1) / (unsigned)tiles_per_warp; chunks_small = 0;
+        }
+        const unsigned long long chunks = chunks_big + chunks_small;
         if ((rc = lane_reserve_partials(&L, (size_t)chunks + 4096)) != SPD_OK) return rc;
         if ((rc = lane_reserve_aux(&L, (size_t)chunks)) != SPD_OK) return rc;
         LevelArgs la;
         la.colT_hot = p->d_colT_hot; la.lowR = p->d_lowR; la.dcold = p->d_dcold;
-        la.xb_hot = p->d_xb_hot; la.xb_cold = p->d_xb_cold; la.cold_start = p->d_cold_start;
+        la.xb_hot = p->d_xb_hot; la.xb_cold = p->d_xb_cold;
+        memcpy(la.cold_start, p->cold_start, sizeof(la.cold_start));
         la.partials = L.d_partials; la.visited = L.d_aux; la.queue = L.d_queue;
-        la.tile_first = tile; la.n_tiles = nt; la.n_chunks = (unsigned)chunks;
-        la.n = n; la.NC = p->NC; la.NCP = p->NCP; la.HSP = p->HSP; la.c = c; la.tiles_per_warp = tiles_per_warp;
+        la.tile_first = tile; la.n_tiles = big;
+        la.tile_first_small = (tile + big) << (c - c_small); la.n_tiles_small = small;
+        la.n_chunks = (unsigned)chunks; la.n_chunks_big = (unsigned)chunks_big;
+        la.n = n; la.NC = p->NC; la.NCP = p->NCP; la.HSP = p->HSP; la.c = c; la.c_small = c_small;
+        la.tiles_per_warp = tiles_per_warp;
         const int HS = p->lvS0 + (p->lvB - 1) * p->lvS, LBv = p->lvB + (p->lvB & 1);
-        const size_t smem = level_smem_bytes(n, p->lvB, HS, p->HSP, LBv, p->NC, p->NCP, c, SPB_REG_THREADS);
+        const size_t smem = level_smem_bytes(n, p->lvB, HS, p->HSP, LBv, p->NC, p->NCP, SPB_REG_THREADS);
         if (smem > 220 * 1024) { set_error("level engine needs %zu B of shared memory", smem); return SPD_ELIMIT; }
         SPB_CUDA(cudaMemsetAsync(L.d_queue, 0, 2 * sizeof(unsigned int), L.stream));
         unsigned nb = 0;
@@ -259,7 +280,8 @@ int spd_sparse_plan_create_packed(int device, const double* mat_t, const double*
     if ((rc = up(img->dcold, (size_t)(n - 1) * img->NCP * 8, (void**)&p->d_dcold)) != SPD_OK) return fail(rc);
     if ((rc = up(img->xb_hot, (size_t)img->HSP * 8, (void**)&p->d_xb_hot)) != SPD_OK) return fail(rc);
     if ((rc = up(img->xb_cold, (size_t)img->NCP * 8, (void**)&p->d_xb_cold)) != SPD_OK) return fail(rc);
-    if ((rc = up(img->cold_start, (size_t)(n - img->B + 2) * 4, (void**)&p->d_cold_start)) != SPD_OK) return fail(rc);
+    if (n - img->B + 2 > SPB_LV_MAXSEG) { set_error("level table too long"); return fail(SPD_ELIMIT); }
+    memcpy(p->cold_start, img->cold_start, (size_t)(n - img->B + 2) * sizeof(int));
   }
   // the sources are the caller's: wait until the copies have left them
   if (cudaStreamSynchronize(L.stream) != cudaSuccess) { set_error("sparse plan upload failed"); return fail(SPD_ECUDA); }
@@ -273,9 +295,7 @@ int spd_sparse_plan_create_packed(int device, const double* mat_t, const double*
     memset(&la, 0, sizeof(la));           // partials == nullptr: prepare only
     la.n_chunks = 1;
     const int HS = p->lvS0 + (p->lvB - 1) * p->lvS, LBv = p->lvB + (p->lvB & 1);
-    int cc = n - 1 < 12 ? n - 1 : 12;
-    if (cc < p->lvB + 1) cc = p->lvB + 1;
-    const size_t smem = level_smem_bytes(n, p->lvB, HS, p->HSP, LBv, p->NC, p->NCP, cc, SPB_REG_THREADS);
+    const size_t smem = level_smem_bytes(n, p->lvB, HS, p->HSP, LBv, p->NC, p->NCP, SPB_REG_THREADS);
     unsigned bps = 0;
     (void)level_launch(p->lvB, p->lvS0, p->lvS, p->skip, L.stream, &la, L.sm_count, smem, &bps);
   } else if (n >= SPB_SPARSE_NMIN && n <= SPB_SPARSE_NMAX) {
