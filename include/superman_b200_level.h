@@ -23,7 +23,7 @@ SPL_FN int spl_regcold(int B, int S0, int S, int skip) {
   return (spl_slots(B, S0, S) <= 12 ? 8 : spl_slots(B, S0, S) <= 16 ? 4 : spl_slots(B, S0, S) <= 24 ? 8 : 0) -
          ((skip && (spl_slots(B, S0, S) == 11 || spl_slots(B, S0, S) == 12 || spl_slots(B, S0, S) == 15 ||
                     spl_slots(B, S0, S) == 16)) ? 4 : 0) -
-         ((!skip && B == 3 && spl_slots(B, S0, S) == 24) ? 4 : 0);   /* 3 x 8 slots: 32 register rows spill at 168 */
+         ((!skip && ((B == 3 && spl_slots(B, S0, S) == 24) || spl_slots(B, S0, S) == 22)) ? 4 : 0);   /* 30+ register rows spill at 168 */
 }
 
 SPL_FN int spl_minblocks(int B, int S0, int S, int skip) {

@@ -110,6 +110,7 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
   using LL = LevelLayout<B, S0, S, R>;
   constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
   constexpr int G = (HT > 24) ? 2 : 4;          // cold rows refreshed together (fewer where registers are short)
+  constexpr bool PAIR = true;                   // neighbouring slots fetch their high-column entries together
   extern __shared__ __align__(16) double dsm[];
   const int n = a.n, NC = a.NC, NCP = a.NCP;
   double* s_colP = dsm;                         //  D
@@ -140,12 +141,11 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
   for (int e = threadIdx.x; e < HT; e += THREADS) s_xbh[e] = a.xb_hot[e];
   for (int e = threadIdx.x; e < NC; e += THREADS) s_xbc[e] = a.xb_cold[e];
   s_SP[(size_t)NC * THREADS + threadIdx.x] = 1.0;
-  __syncthreads();
 
   const uint32_t sm_colP = (uint32_t)__cvta_generic_to_shared(s_colP);
-  const uint32_t sm_low0 = (uint32_t)__cvta_generic_to_shared(s_low0);
   const uint32_t neg_off = (uint32_t)((size_t)(n - 1) * HSP * 8);       // colN - colP
   const uint32_t zero_off = 2u * neg_off;                              // zero - colP
+  const uint32_t sm_low0 = (uint32_t)__cvta_generic_to_shared(s_low0);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* myX = s_X + threadIdx.x;
   double* mySP = s_SP + threadIdx.x;
@@ -295,10 +295,19 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
           double r0 = 1.0, r1 = 1.0;
 #pragma unroll
           for (int i = HS; i < HT; ++i) {
-            double d;
-            lds_f64(hi_addr + (uint32_t)(i * 8), d);
-            xh[i] += d;
-            if (i & 1) r1 *= xh[i]; else r0 *= xh[i];
+            if ((i & 1) == 0 && i + 1 < HT) {          // an aligned pair: one 16-byte load
+              double d0, d1;
+              lds_f64x2(hi_addr + (uint32_t)(i * 8), d0, d1);
+              xh[i] += d0;
+              xh[i + 1 < HT ? i + 1 : i] += d1;
+              r0 *= xh[i];
+              r1 *= xh[i + 1 < HT ? i + 1 : i];
+            } else if ((i & 1) == 0 || i == HS) {
+              double d;
+              lds_f64(hi_addr + (uint32_t)(i * 8), d);
+              xh[i] += d;
+              if (i & 1) r1 *= xh[i]; else r0 *= xh[i];
+            }
           }
           Q *= r0 * r1;
         }
@@ -330,16 +339,27 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
               constexpr int gi = decltype(Gc)::value;
               constexpr int t0 = gi * (SL / NG) + (gi < SL % NG ? gi : SL % NG);
               constexpr int CH = SL / NG + (gi < SL % NG ? 1 : 0);
-              double v[CH], m[CH][LB];
+              double v[CH], m[CH][LB], d[CH];
+              // the high column's entries of the group's slots: neighbours share one 16-byte load
+#pragma unroll
+              for (int t = 0; t < CH; ++t) {
+                const int i = base + t0 + t;
+                if (!PAIR) {
+                  lds_f64(hi_addr + (uint32_t)(i * 8), d[t]);
+                } else if ((i & 1) == 0) {
+                  if (t + 1 < CH) lds_f64x2(hi_addr + (uint32_t)(i * 8), d[t], d[t + 1 < CH ? t + 1 : t]);
+                  else lds_f64(hi_addr + (uint32_t)(i * 8), d[t]);
+                } else if (t == 0) {
+                  lds_f64(hi_addr + (uint32_t)(i * 8), d[t]);
+                }                                       // (an odd slot after the first came with its neighbour)
+              }
 #pragma unroll
               for (int t = 0; t < CH; ++t) {
                 const int i = base + t0 + t;
 #pragma unroll
                 for (int qq = (L & ~1); qq < LB; qq += 2)       // only columns >= L flip inside this level
                   lds_f64x2(low_addr + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
-                double d;
-                lds_f64(hi_addr + (uint32_t)(i * 8), d);
-                v[t] = xh[i] + d;
+                v[t] = xh[i] + d[t];
               }
 #pragma unroll
               for (int w = 0; w < cnt; ++w) {
@@ -372,10 +392,12 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
           });
           if (active) {                               // idle lanes of a last, partial round repeat lane 0's tile
             myX[(size_t)NC * THREADS] = fma(Q, T[0], myX[(size_t)NC * THREADS]);
-            reinterpret_cast<unsigned long long*>(myX)[(size_t)(NC + 1) * THREADS] += 1ull;
+            if (SKIP) reinterpret_cast<unsigned long long*>(myX)[(size_t)(NC + 1) * THREADS] += 1ull;
           }
         }
       }
+      if (!SKIP && active)                            // SpaRyser evaluates every block: counted once per tile
+        reinterpret_cast<unsigned long long*>(myX)[(size_t)(NC + 1) * THREADS] += (unsigned long long)nblk;
       __syncwarp();
     }
 
