@@ -141,6 +141,7 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
   for (int e = threadIdx.x; e < HT; e += THREADS) s_xbh[e] = a.xb_hot[e];
   for (int e = threadIdx.x; e < NC; e += THREADS) s_xbc[e] = a.xb_cold[e];
   s_SP[(size_t)NC * THREADS + threadIdx.x] = 1.0;
+  __syncthreads();
 
   const uint32_t sm_colP = (uint32_t)__cvta_generic_to_shared(s_colP);
   const uint32_t neg_off = (uint32_t)((size_t)(n - 1) * HSP * 8);       // colN - colP

@@ -17,6 +17,7 @@
 #include "sp_sched.h"
 #include "superman_b200_level.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -277,6 +278,21 @@ int sp_sparse_plan_open(int device, const double *dmat_in, const double *xbase, 
     level_sorted[j] = lvl[perm[j]];
     xb[j] = xbase[perm[j]];
     for (int k = 0; k < n; ++k) mt[(size_t)k * n + j] = dmat_t[(size_t)k * n + perm[j]];
+  }
+
+  /* development aid: SP_LEVEL_DUMP=<file> gets the matrix as the plan walks it (rows by level, columns in plan
+   * order) for tools/skip_structure.py */
+  if (getenv("SP_LEVEL_DUMP")) {
+    FILE *f = fopen(getenv("SP_LEVEL_DUMP"), "w");
+    if (f) {
+      fprintf(f, "%d %d\n", n, skip);
+      for (int j = 0; j < n; ++j) {
+        fprintf(f, "%d %.17g", level_sorted[j], xb[j]);
+        for (int k = 0; k < n; ++k) fprintf(f, " %.17g", mt[(size_t)k * n + j]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
   }
 
   /* 3. engine: LevelRyser (B, S0, S) with the lowest modelled cost, if the matrix fits its slots */
