@@ -144,7 +144,8 @@ typedef struct level_pack_out {
   double *colT_hot, *lowR, *dcold, *xb_hot, *xb_cold;
   int *cold_start;
   int NC, NCP, HSP;
-  double cost;                 /* modelled FP64 instructions per index */
+  double cost;                 /* planning cost per index (FP64 instructions, the cold refresh weighted x3) */
+  double fp64_per_index;       /* FP64 instructions the kernel executes per index for this packing */
 } level_pack_out;
 
 static void pack_free(level_pack_out *o) {
@@ -228,6 +229,19 @@ static int level_pack(int n, int B, int S0, int S, int R, const int *lvl, const 
   for (int z = 0; z < 16 && B + z <= n; ++z, w *= 0.5)
     coldc += w * 3.0 * (double)o->cold_start[(z + 1 <= n - B + 1) ? z + 1 : n - B + 1];
   o->cost = (hot + 2.0 * R + (double)((1 << B) + B) + coldc) / (double)(1 << B);
+  /* what the block loop executes (level_reg.cuh): per level SL slots x 2^(B-L) values, one add and one multiply
+   * each, less one multiply per value (a product of SL factors); pair sums 2^(B-1) + sum_{L>=1} 2^(B-L); the
+   * block's accumulate; R register-cold rows (add + multiply) and their two-chain product; the expected cold
+   * refresh (one FMA and one multiply per row touched) */
+  {
+    double ex = 0.0;
+    for (int L = 0; L < B; ++L) {
+      const double SL = (double)(L == 0 ? S0 : S), cnt = (double)(1 << (B - L));
+      ex += SL * cnt + (SL - 1.0) * cnt + (L == 0 ? 0.5 * cnt : cnt);
+    }
+    ex += 1.0 + (R > 0 ? 2.0 * R + 2.0 : 0.0) + coldc * (2.0 / 3.0);
+    o->fp64_per_index = ex / (double)(1 << B);
+  }
   o->NC = NC; o->NCP = NCP; o->HSP = HSP;
   return 1;
 }
@@ -343,7 +357,7 @@ int sp_sparse_plan_open(int device, const double *dmat_in, const double *xbase, 
     img.NC = best.NC; img.NCP = best.NCP; img.HSP = best.HSP;
     img.colT_hot = best.colT_hot; img.lowR = best.lowR; img.dcold = best.dcold;
     img.xb_hot = best.xb_hot; img.xb_cold = best.xb_cold; img.cold_start = best.cold_start;
-    img.instr_per_index = best.cost;
+    img.instr_per_index = best.fp64_per_index;
   } else {
     img.B = 0;
   }
