@@ -157,8 +157,8 @@ static void pack_free(level_pack_out *o) {
  * level < B, R register-cold rows, the other rows cold, sorted by level.  lvl[] / dmat_t / xbase are in the
  * caller's row order.  Returns 0 when some level has more rows than the slots at or below it can take,
  * < 0 on allocation failure, 1 on success. */
-static int level_pack(int n, int B, int S0, int S, int R, const int *lvl, const double *dmat_t, const double *xbase,
-                      level_pack_out *o) {
+static int level_pack(int n, int B, int S0, int S, int R, int fill_free, const int *lvl, const double *dmat_t,
+                      const double *xbase, level_pack_out *o) {
   memset(o, 0, sizeof(*o));
   const int HS = S0 + (B - 1) * S, HT = HS + R, HSP = HT + (HT & 1), LB = B + (B & 1);
   int slot_row[64], order[64], cold[64];
@@ -184,11 +184,23 @@ static int level_pack(int n, int B, int S0, int S, int R, const int *lvl, const 
     if (placed < 0) return 0;
     slot_row[placed] = j;
   }
+  /* SpaRyser: a level slot that is still free does its work anyway (on the neutral row), so it takes a cold row
+   * instead -- a row of level >= B has no entry in the low columns and is simply constant over the block.  The
+   * cold rows of lowest level go first (they are refreshed most often), into the cheapest free slots (highest
+   * level: fewest values per block).  SkipPer keeps them cold: its block test looks at the cold product only. */
+  int moved = 0;
+  if (fill_free) {
+    for (int L = B - 1; L >= 0 && moved < ncold; --L) {
+      const int base = L == 0 ? 0 : S0 + (L - 1) * S, count = L == 0 ? S0 : S;
+      for (int t = 0; t < count && moved < ncold; ++t)
+        if (slot_row[base + t] < 0) slot_row[base + t] = cold[moved++];
+    }
+  }
   /* the R cold rows of lowest level (refreshed most often) stay in registers too */
-  const int nrc = R < ncold ? R : ncold;
-  for (int t = 0; t < nrc; ++t) slot_row[HS + t] = cold[t];
-  const int NC = ncold - nrc;
-  const int *coldp = cold + nrc;
+  const int nrc = R < ncold - moved ? R : ncold - moved;
+  for (int t = 0; t < nrc; ++t) slot_row[HS + t] = cold[moved + t];
+  const int NC = ncold - moved - nrc;
+  const int *coldp = cold + moved + nrc;
   const int NCP = NC + (NC & 1) + (NC == 0 ? 2 : 0);
   o->colT_hot = (double *)calloc((size_t)(n - 1) * HSP, sizeof(double));
   o->lowR = (double *)calloc((size_t)(HS > 0 ? HS : 1) * LB, sizeof(double));
@@ -333,7 +345,7 @@ int sp_sparse_plan_open(int device, const double *dmat_in, const double *xbase, 
           if (forceS0 && forceS0 != S0) continue;
           const int R = spl_regcold(B, S0, S, skip != 0);
           level_pack_out o;
-          const int r = level_pack(n, B, S0, S, R, lvl, dmat_t, xbase, &o);
+          const int r = level_pack(n, B, S0, S, R, skip == 0 && env_int_c("SP_LEVEL_FILL", 1) != 0, lvl, dmat_t, xbase, &o);
           if (r < 0) { rc = SP_ENOMEM; sp_set_error("out of memory"); goto done; }
           if (r == 0) continue;
           fits = 1;
