@@ -26,6 +26,12 @@ SPL_FN int spl_regcold(int B, int S0, int S, int skip) {
          ((!skip && ((B == 3 && spl_slots(B, S0, S) == 24) || spl_slots(B, S0, S) == 22)) ? 4 : 0);   /* 30+ register rows spill at 168 */
 }
 
+/* configurations with many hot slots read the low-column entries of their slots as uniform-register operands of
+ * the FP64 instructions (kernel parameters) instead of loading two shared-memory images per block: measured
+ * -3.5 % at 16 slots, +4 % at 11-12 (profiles/r02_level_uniform_operand_experiment.log); the 168-register
+ * configurations (22+ slots) keep the images */
+SPL_FN int spl_uniform_low(int hot_slots) { return hot_slots >= 13 && hot_slots <= 20; }
+
 SPL_FN int spl_minblocks(int B, int S0, int S, int skip) {
   return spl_slots(B, S0, S) + spl_regcold(B, S0, S, skip) <= 20 ? 4
        : (spl_slots(B, S0, S) + spl_regcold(B, S0, S, skip) <= 30 || !skip) ? 3 : 2;

@@ -45,6 +45,7 @@
 #include "superman_b200_level.h"
 
 #define SPB_LV_MAXSEG 64    // n - B + 2 <= 63
+#define SPB_LV_MAXLOW 128   // hot slots (<= 32) x low columns (<= 4)
 
 namespace spb {
 
@@ -61,6 +62,8 @@ struct LevelArgs {
   // packed device image (doubles unless noted), see sp_sparse.cu: level_pack()
   const double* colT_hot;    // [(n-1) * HSP]   colT_hot[k*HSP + s]  = D[slot s][k]   (hot slots, then R register-cold)
   const double* lowR;        // [HS * LB]       lowR[s*LB + q]       = D[slot s][q], q < B
+  double low[SPB_LV_MAXLOW]; //                 the same image by value, for the configurations that read it as uniform-register
+                             //                 operands (spl_uniform_low)
   const double* dcold;       // [(n-1) * NCP]   dcold[k*NCP + jc]    = D[cold row jc][k]
   const double* xb_hot;      // [HS + R]
   const double* xb_cold;     // [NC]
@@ -95,7 +98,7 @@ struct LevelLayout {
 
 // bytes of dynamic shared memory the kernel needs (host and device agree through this one function)
 __host__ __device__ inline size_t level_smem_bytes(int n, int B, int HS, int HSP, int LB, int NC, int NCP, int threads) {
-  const size_t dbl = 2 * (size_t)(n - 1) * HSP + HSP + 2 * (size_t)HS * LB + (size_t)(n - 1) * NCP + HSP + NCP +
+  const size_t dbl = 2 * (size_t)(n - 1) * HSP + HSP + (spl_uniform_low(HS) ? 0 : 2 * (size_t)HS * LB) + (size_t)(n - 1) * NCP + HSP + NCP +
                      (size_t)(NC + 2) * threads + (size_t)(NC + 1) * threads;
   return dbl * sizeof(double);
 }
@@ -110,6 +113,7 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
   using LL = LevelLayout<B, S0, S, R>;
   constexpr int HS = LL::HS, HT = LL::HT, HSP = LL::HSP, LB = LL::LB, NB = 1 << B, WARPS = THREADS / 32;
   constexpr int G = (HT > 24) ? 2 : 4;          // cold rows refreshed together (fewer where registers are short)
+  constexpr bool UROP = spl_uniform_low(HS) != 0;   // low-column entries as uniform-register operands (no image in shared memory)
   constexpr bool PAIR = true;                   // neighbouring slots fetch their high-column entries together
   extern __shared__ __align__(16) double dsm[];
   const int n = a.n, NC = a.NC, NCP = a.NCP;
@@ -117,8 +121,8 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
   double* s_colN = s_colP + (size_t)(n - 1) * HSP;   // -D
   double* s_zero = s_colN + (size_t)(n - 1) * HSP;   //  0 (first block of a tile: X is already explicit)
   double* s_low0 = s_zero + HSP;
-  double* s_low1 = s_low0 + HS * LB;           // column B-1 negated
-  double* s_dcold = s_low1 + HS * LB;
+  double* s_low1 = s_low0 + (UROP ? 0 : HS * LB);   // column B-1 negated
+  double* s_dcold = s_low1 + (UROP ? 0 : HS * LB);
   double* s_xbh = s_dcold + (size_t)(n - 1) * NCP;
   double* s_xbc = s_xbh + HSP;
   double* s_X = s_xbc + NCP;                    // [NC + 2][THREADS]
@@ -132,7 +136,7 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
     s_colN[e] = -v;
   }
   for (int e = threadIdx.x; e < HSP; e += THREADS) s_zero[e] = 0.0;
-  for (int e = threadIdx.x; e < HS * LB; e += THREADS) {
+  for (int e = threadIdx.x; e < (UROP ? 0 : HS * LB); e += THREADS) {
     const double v = a.lowR[e];
     s_low0[e] = v;
     s_low1[e] = (e % LB == B - 1) ? -v : v;
@@ -247,6 +251,7 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
         const uint32_t hi_addr = sm_colP + ((blk != 0) ? (uint32_t)(k * HSP * 8) + (up ? neg_off : 0u) : zero_off);
         // column B-1 flips in the middle of the block; its direction is bit B of the index
         const uint32_t low_addr = sm_low0 + (uint32_t)((blk & 1) * (HS * LB * 8));
+        const double sB = (blk & 1) ? -1.0 : 1.0;            // (the uniform-operand form of the same choice)
 
         // ---- cold rows of level <= k (rows [0, top)): update, refresh their suffix products (per-thread
         // direction).  G rows at a time, every load before the first store, so that the shared-memory
@@ -317,11 +322,15 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
           // exact zeros: only the block's net effect on the hot slots (high column + column B-1)
 #pragma unroll
           for (int i = 0; i < HS; ++i) {
-            double mt;
-            lds_f64(low_addr + (uint32_t)((i * LB + (B - 1)) * 8), mt);
             double d;
             lds_f64(hi_addr + (uint32_t)(i * 8), d);
-            xh[i] = (xh[i] + d) + mt;
+            if constexpr (UROP) {
+              xh[i] = fma(sB, a.low[i * LB + (B - 1)], xh[i] + d);
+            } else {
+              double mt;
+              lds_f64(low_addr + (uint32_t)((i * LB + (B - 1)) * 8), mt);
+              xh[i] = (xh[i] + d) + mt;
+            }
           }
         } else {
           // ---- hot slots: level L takes 2^(B-L) values; the slots of a level advance together, CH
@@ -340,7 +349,8 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
               constexpr int gi = decltype(Gc)::value;
               constexpr int t0 = gi * (SL / NG) + (gi < SL % NG ? gi : SL % NG);
               constexpr int CH = SL / NG + (gi < SL % NG ? 1 : 0);
-              double v[CH], m[CH][LB], d[CH];
+              [[maybe_unused]] double m[UROP ? 1 : CH][LB];
+              double v[CH], d[CH];
               // the high column's entries of the group's slots: neighbours share one 16-byte load
 #pragma unroll
               for (int t = 0; t < CH; ++t) {
@@ -357,9 +367,11 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
 #pragma unroll
               for (int t = 0; t < CH; ++t) {
                 const int i = base + t0 + t;
+                if constexpr (!UROP) {
 #pragma unroll
-                for (int qq = (L & ~1); qq < LB; qq += 2)       // only columns >= L flip inside this level
-                  lds_f64x2(low_addr + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
+                  for (int qq = (L & ~1); qq < LB; qq += 2)     // only columns >= L flip inside this level
+                    lds_f64x2(low_addr + (uint32_t)((i * LB + qq) * 8), m[t][qq], m[t][qq + 1]);
+                }
                 v[t] = xh[i] + d[t];
               }
 #pragma unroll
@@ -369,8 +381,15 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
                   const int K = ctz_c(u);
 #pragma unroll
                   for (int t = 0; t < CH; ++t) {
-                    if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
-                    else v[t] -= m[t][K];
+                    if constexpr (UROP) {
+                      const double mk = a.low[(base + t0 + t) * LB + K];    // constant bank -> uniform register
+                      if (K == B - 1) v[t] = fma(sB, mk, v[t]);
+                      else if (((u >> (K + 1)) & 1) == 0) v[t] += mk;
+                      else v[t] -= mk;
+                    } else {
+                      if (K == B - 1 || ((u >> (K + 1)) & 1) == 0) v[t] += m[t][K];
+                      else v[t] -= m[t][K];
+                    }
                   }
                 }
                 double pr = v[0];

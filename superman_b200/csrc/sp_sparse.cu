@@ -65,6 +65,7 @@ struct spd_sparse_plan {
   double lv_instr = 0.0;       // FP64 instructions per Gray index of the chosen engine (host model)
   double *d_colT_hot = nullptr, *d_lowR = nullptr, *d_dcold = nullptr, *d_xb_hot = nullptr, *d_xb_cold = nullptr;
   int cold_start[SPB_LV_MAXSEG] = {0};
+  double low[SPB_LV_MAXLOW] = {0.0};
   bool pending = false;
   spd_run_info info;
 };
@@ -168,6 +169,7 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
         if ((rc = lane_reserve_aux(&L, (size_t)chunks)) != SPD_OK) return rc;
         LevelArgs la;
         la.colT_hot = p->d_colT_hot; la.lowR = p->d_lowR; la.dcold = p->d_dcold;
+        memcpy(la.low, p->low, sizeof(la.low));
         la.xb_hot = p->d_xb_hot; la.xb_cold = p->d_xb_cold;
         memcpy(la.cold_start, p->cold_start, sizeof(la.cold_start));
         la.partials = L.d_partials; la.visited = L.d_aux; la.queue = L.d_queue;
@@ -277,6 +279,8 @@ int spd_sparse_plan_create_packed(int device, const double* mat_t, const double*
     p->NC = img->NC; p->NCP = img->NCP; p->HSP = img->HSP;
     if ((rc = up(img->colT_hot, (size_t)(n - 1) * img->HSP * 8, (void**)&p->d_colT_hot)) != SPD_OK) return fail(rc);
     if ((rc = up(img->lowR, (size_t)HS * LBv * 8, (void**)&p->d_lowR)) != SPD_OK) return fail(rc);
+    if (HS * LBv > SPB_LV_MAXLOW) { set_error("low-column image too long"); return fail(SPD_ELIMIT); }
+    memcpy(p->low, img->lowR, (size_t)HS * LBv * sizeof(double));
     if ((rc = up(img->dcold, (size_t)(n - 1) * img->NCP * 8, (void**)&p->d_dcold)) != SPD_OK) return fail(rc);
     if ((rc = up(img->xb_hot, (size_t)img->HSP * 8, (void**)&p->d_xb_hot)) != SPD_OK) return fail(rc);
     if ((rc = up(img->xb_cold, (size_t)img->NCP * 8, (void**)&p->d_xb_cold)) != SPD_OK) return fail(rc);
