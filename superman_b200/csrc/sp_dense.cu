@@ -192,32 +192,67 @@ static int dense_enqueue(spd_dense_plan* p, unsigned long long lo, unsigned long
   const unsigned long long len = hi - lo;
 
   if (p->quad) {
-    // double-double mode (-q): one kernel over the whole range, X in shared memory; the block sums come back as
-    // (high, low) pairs and both halves go through the compensated reduction
+    // double-double mode (-q): the 16-aligned body of the range goes through the block kernel (rows outside, 16
+    // running products), the ragged ends (< 16 indices each) through the loop kernel; X in shared memory in both.
+    // The block sums come back as (high, low) pairs and all of them go through the compensated reduction.
     const size_t smem_bytes = ((size_t)n * n + 2 * (size_t)n * DDK_THREADS) * sizeof(double);
-    if (smem_bytes > 40 * 1024)
+    if (smem_bytes > 40 * 1024) {
       SPB_CUDA(cudaFuncSetAttribute(ryser_dd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES));
+      SPB_CUDA(cudaFuncSetAttribute(ryser_dd_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPB_SMEM_OPTIN_BYTES));
+    }
     int bps = 1;
-    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ryser_dd_kernel, DDK_THREADS, smem_bytes));
-    unsigned long long blocks = (unsigned long long)L.sm_count * (unsigned)(bps > 0 ? bps : 1) * 8ull;   // 8 waves: tail below 1 %
-    unsigned long long per_thread = (len + blocks * DDK_THREADS - 1) / (blocks * DDK_THREADS);
-    unsigned long long pt = 16;
-    while (pt < per_thread) pt <<= 1;                  // power of two: the flipped column stays warp-uniform
-    if (pt > 4096) pt = 4096;                          // short chains (accuracy is the point of this mode)
-    per_thread = pt;
-    blocks = (len + per_thread * DDK_THREADS - 1) / (per_thread * DDK_THREADS);
-    if (blocks == 0) blocks = 1;
-    if (blocks > (1ull << 22)) { set_error("range too long for one double-double launch"); return SPD_ELIMIT; }
-    int rc2 = lane_reserve_partials(&L, 2 * (size_t)blocks);
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ryser_dd_blk_kernel, DDK_THREADS, smem_bytes));
+    unsigned long long blo = (lo + 15ull) & ~15ull, bhi = hi & ~15ull;
+    if (n < 6 || bhi <= blo || bhi - blo < 16ull * DDK_THREADS || env_int("SP_DD_LOOP_KERNEL", 0) != 0) blo = bhi = lo;   // no body
+    struct Part { unsigned long long lo, hi, per_thread, blocks; bool blk; };
+    Part parts[3];
+    int np = 0;
+    size_t total = 0;
+    if (bhi > blo) {
+      const unsigned long long blen = bhi - blo;
+      unsigned long long blocks = (unsigned long long)L.sm_count * (unsigned)(bps > 0 ? bps : 1) * 8ull;   // 8 waves: tail below 1 %
+      unsigned long long per_thread = (blen + blocks * DDK_THREADS - 1) / (blocks * DDK_THREADS);
+      unsigned long long pt = 16;
+      while (pt < per_thread) pt <<= 1;                // power of two: the flipped column stays warp-uniform
+      if (pt > 4096) pt = 4096;                        // short chains (accuracy is the point of this mode)
+      blocks = (blen + pt * DDK_THREADS - 1) / (pt * DDK_THREADS);
+      if (blocks > (1ull << 22)) { set_error("range too long for one double-double launch"); return SPD_ELIMIT; }
+      parts[np++] = Part{blo, bhi, pt, blocks, true};
+      total += 2 * (size_t)blocks;
+    }
+    const unsigned long long edge[2][2] = {{lo, bhi > blo ? blo : hi}, {bhi > blo ? bhi : hi, hi}};
+    for (int e = 0; e < 2; ++e) {
+      const unsigned long long elo = edge[e][0], ehi = edge[e][1];
+      if (ehi <= elo) continue;
+      const unsigned long long elen = ehi - elo;
+      unsigned long long blocks = (unsigned long long)L.sm_count * (unsigned)(bps > 0 ? bps : 1) * 8ull;
+      unsigned long long per_thread = (elen + blocks * DDK_THREADS - 1) / (blocks * DDK_THREADS);
+      unsigned long long pt = 16;
+      while (pt < per_thread) pt <<= 1;
+      if (pt > 4096) pt = 4096;
+      blocks = (elen + pt * DDK_THREADS - 1) / (pt * DDK_THREADS);
+      if (blocks > (1ull << 22)) { set_error("range too long for one double-double launch"); return SPD_ELIMIT; }
+      parts[np++] = Part{elo, ehi, pt, blocks, false};
+      total += 2 * (size_t)blocks;
+    }
+    int rc2 = lane_reserve_partials(&L, total + 2);
     if (rc2 != SPD_OK) return rc2;
-    ryser_dd_kernel<<<(unsigned)blocks, DDK_THREADS, smem_bytes, L.stream>>>(p->d_mat_t, p->d_xbase, p->d_xbase_lo, n, lo, hi,
-                                                                             per_thread, L.d_partials);
-    SPB_CUDA(cudaGetLastError());
-    if ((rc2 = launch_reduce(L, L.d_partials, (size_t)blocks, L.d_result, 0, false)) != SPD_OK) return rc2;
-    if ((rc2 = launch_reduce(L, L.d_partials + blocks, (size_t)blocks, L.d_result, 0, true)) != SPD_OK) return rc2;
+    size_t off = 0;
+    for (int i = 0; i < np; ++i) {
+      if (parts[i].blk)
+        ryser_dd_blk_kernel<<<(unsigned)parts[i].blocks, DDK_THREADS, smem_bytes, L.stream>>>(
+            p->d_mat_t, p->d_xbase, p->d_xbase_lo, n, parts[i].lo, parts[i].hi, parts[i].per_thread, L.d_partials + off);
+      else
+        ryser_dd_kernel<<<(unsigned)parts[i].blocks, DDK_THREADS, smem_bytes, L.stream>>>(
+            p->d_mat_t, p->d_xbase, p->d_xbase_lo, n, parts[i].lo, parts[i].hi, parts[i].per_thread, L.d_partials + off);
+      SPB_CUDA(cudaGetLastError());
+      off += 2 * (size_t)parts[i].blocks;
+    }
+    if (total == 0) { SPB_CUDA(cudaMemsetAsync(L.d_partials, 0, sizeof(double), L.stream)); total = 1; }
+    if ((rc2 = launch_reduce(L, L.d_partials, total, L.d_result, 0, false)) != SPD_OK) return rc2;
     SPB_CUDA(cudaMemcpyAsync(L.h_result, L.d_result, sizeof(double), cudaMemcpyDeviceToHost, L.stream));
     SPB_CUDA(cudaEventRecord(L.ev1, L.stream));
-    p->info.launches = 3;
+    p->info.launches = np + 1;
     p->info.path = SPD_PATH_DENSE_DD;
     p->pending = true;
     return SPD_OK;

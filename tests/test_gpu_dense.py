@@ -275,6 +275,10 @@ def test_quad_precision_mode(sp, oracle):
         assert tot * sp.nw_factor(n) == pytest.approx(want, rel=5e-16)
         for algo in (5, 6):
             assert sp.dense_ryser(A, n, algo, gpu_num=1) == pytest.approx(want, rel=5e-16)
+        # orders around the block kernel's limits (n < 6 and ranges shorter than 2048 indices take the loop kernel)
+        for m in (3, 5, 6, 7, 12, 13):
+            Am = _rand(rng, m, 0.8, "dbl")
+            assert sp.dense_ryser(Am, m, 4) == pytest.approx(oracle.perm_ld(Am), rel=5e-16), m
         e = _golden.known_perman()["chesapeake"]
         a = _golden.dense_from(e)
         exact = int(e["exact"])
