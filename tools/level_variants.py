@@ -40,6 +40,8 @@ names = sys.argv[1:] or sorted(os.listdir(os.path.join(R, "tools", "_bin")))
 for spec in names:
     name, *kv = spec.split(":")
     lib = os.path.join(R, "tools", "_bin", name, "libsuperman_b200.so")
+    if name == "main":
+        lib = os.path.join(R, "superman_b200", "libsuperman_b200.so")
     if not os.path.exists(lib):
         continue
     env = dict(os.environ, SUPERMAN_B200_LIB=lib)
