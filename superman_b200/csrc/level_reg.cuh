@@ -5,8 +5,8 @@
 // a row whose lowest non-zero column is L ("level" L) can only change when a column >= L flips.
 //
 //   hot rows (level < B): X in registers, in fixed slots: S0 for level 0 (the most expensive level:
-//     2^B values per block) and S for each other level (the host packs the rows into slots; free
-//     slots hold the neutral row x = 1, entries 0).  A level-L slot takes only
+//     2^B values per block) and S for each other level (the host packs the rows into slots; a free
+//     slot takes a cold row in SpaRyser plans, else the neutral row x = 1, entries 0).  A level-L slot takes only
 //     2^(B-L) distinct values inside a block, so it costs 2^(B-L) updates and multiplies into its
 //     level's 2^(B-L) products PL_L[.] instead of 2^B of each.  The 2^B terms of a block,
 //     term_u = PL_0[u] * PL_1[u>>1] * ... * PL_{B-1}[u>>(B-1)] * Q, are summed with their signs by
@@ -27,6 +27,9 @@
 // choice between shared-memory images (D, -D, zeros; two low-column images), so the block loop's
 // addresses are block-uniform; the one update whose direction depends on the tile's parity (the
 // middle block of a tile) adds the column like an even tile, and odd tiles take it out twice first.
+// Configurations with 13-20 hot slots (spl_uniform_low) have no low-column images: the entries are kernel
+// parameters and reach the FP64 instructions as uniform-register operands (LDCU.128, DADD R, R, UR); column
+// B-1's direction is then the factor sB of one FMA per slot and block.
 //
 // Work distribution: a persistent grid; every warp pulls chunks of tiles from an atomic counter and
 // leaves one partial sum per chunk (bit-reproducible whichever warp took which chunk).
