@@ -111,7 +111,9 @@ typedef struct spd_level_image {
   const double *xb_hot;         /* [HSP] */
   const double *xb_cold;        /* [NCP] */
   const int *cold_start;        /* [nov - B + 2] */
-  double instr_per_index;       /* the host model's FP64 instructions per Gray index (reported in spd_run_info.aux1) */
+  double instr_per_index;       /* FP64 instructions per Gray index of this packing (reported in spd_run_info.aux1) */
+  int skip_long_tiles;          /* SkipPer: 1 when tiles twice the default length cost less (the host measured how
+                                 * many more tiles the shorter ones let the tile filter drop), else 0 */
 } spd_level_image;
 int  spd_sparse_plan_create_packed(int device, const double *mat_t, const double *xbase, const int *level_sorted,
                                    int nov, int skip, const spd_level_image *img, spd_sparse_plan **plan);

@@ -62,6 +62,7 @@ struct spd_sparse_plan {
   std::vector<int> level;      // sorted ascending: level[j] of the row now at position j
   // LevelRyser image (level_reg.cuh); lvB == 0 when the matrix does not fit its slots
   int lvB = 0, lvS0 = 0, lvS = 0, lvR = 0, NC = 0, NCP = 0, HSP = 0;
+  int skip_long_tiles = 0;     // host's choice between 2^21 and 2^20 tiles per whole-space SkipPer run
   double lv_instr = 0.0;       // FP64 instructions per Gray index of the chosen engine (host model)
   double *d_colT_hot = nullptr, *d_lowR = nullptr, *d_dcold = nullptr, *d_xb_hot = nullptr, *d_xb_cold = nullptr;
   int cold_start[SPB_LV_MAXSEG] = {0};
@@ -113,7 +114,7 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
     if (use_level) B = p->lvB;
     // tile size: SpaRyser is fastest with 2^12-index tiles at n = 33 (less start-up work per index),
     // SkipPer with 2^11 (its tile filter drops more when tiles are finer): 2^20 resp. 2^21 tiles per launch
-    const int tiles_log2 = env_int("SP_SPARSE_TILES_LOG2", p->skip ? 21 : 20);
+    const int tiles_log2 = env_int("SP_SPARSE_TILES_LOG2", (p->skip && !p->skip_long_tiles) ? 21 : 20);
     c = env_int("SP_SPARSE_TILE_LOG2", 0);
     if (c <= 0) {
       c = ilog2_ull(len) - tiles_log2;
@@ -260,6 +261,7 @@ int spd_sparse_plan_create_packed(int device, const double* mat_t, const double*
   p->skip = skip ? 1 : 0;
   p->level.assign(level_sorted, level_sorted + n);
   p->lv_instr = img->instr_per_index;
+  p->skip_long_tiles = img->skip_long_tiles;
   auto fail = [&](int code) { spd_sparse_plan_destroy(p); return code; };
   auto up = [&](const void* src, size_t bytes, void** dst) -> int {
     int r = lane_arena_alloc(&L, bytes ? bytes : 8, dst);

@@ -374,6 +374,39 @@ int sp_sparse_plan_open(int device, const double *dmat_in, const double *xbase, 
     img.B = 0;
   }
 
+  /* 3b. SkipPer tile length.  The kernel drops a tile when one of its tile-constant rows (level >= c, c = log2 of
+   * the tile length) is zero; shorter tiles have more such rows and may drop more, longer tiles pay the tile
+   * prologue and the filter less often.  With the survival rates s(c) measured on sampled tiles, the time per index
+   * goes as   s(c) * (1 + 0.116 * 2^(11-c)) + 0.035 * 2^(11-c)
+   * (prologue 11.6 % and filter 3.5 % of the block work at c = 11, ncu at n = 33): take c = 12 over the default 11
+   * when that is smaller.  Measured on four n = 33 matrices (s(11) = s(12) on all of them): -7 ... -10 % on three,
+   * +3 % on the fourth, whose lanes share fewer zero blocks when the tile bits move up by one. */
+  if (skip && img.B && n - 1 > 12) {
+    double surv[2] = {0.0, 0.0};
+    unsigned long long rs = 0x9E3779B97F4A7C15ull;
+    const int samples = 2048;
+    for (int ci = 0; ci < 2; ++ci) {
+      const int c = 11 + ci;
+      int alive = 0;
+      for (int smp = 0; smp < samples; ++smp) {
+        rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17;                  /* xorshift64 */
+        const unsigned long long i = (rs >> 8) & ((1ull << (n - 1)) - 1) & ~((1ull << c) - 1);
+        const unsigned long long g = i ^ (i >> 1);
+        int ok = 1;
+        for (int j = n - 1; j >= 0 && ok && level_sorted[j] >= c; --j) {
+          double x = xb[j];
+          for (int k = c; k < n - 1; ++k)
+            if ((g >> k) & 1ull) x += mt[(size_t)k * n + j];
+          if (x == 0.0) ok = 0;
+        }
+        alive += ok;
+      }
+      surv[ci] = (double)alive / samples;
+    }
+    const double t11 = surv[0] * 1.116 + 0.035, t12 = surv[1] * 1.058 + 0.0175;
+    img.skip_long_tiles = (t12 < t11 && env_int_c("SP_SKIP_LONG_TILES", 1) != 0) ? 1 : 0;
+  }
+
   /* 4. hand the images to the device */
   rc = spd_sparse_plan_create_packed(device, mt, xb, level_sorted, n, skip, &img, out);
   if (rc != SPD_OK) sp_set_error("%s", spd_last_error());
