@@ -153,7 +153,7 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
         if (c_small < B + 1) c_small = B + 1;
         unsigned long long nt = tiles_left;                          // tiles of 2^c taken by this launch
         unsigned long long big = nt, small = 0;
-        if (c_small < c && nt >= 8ull * (unsigned)tiles_per_warp) {
+        if (c_small < c && c >= 11 && nt >= 8ull * (unsigned)tiles_per_warp) {      // (short tiles are mostly prologue)
           big = (nt - nt / 8) / (unsigned)tiles_per_warp * (unsigned)tiles_per_warp;
           small = (nt - big) << (c - c_small);
         }

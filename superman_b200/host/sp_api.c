@@ -389,11 +389,15 @@ static double sparse_common(const double *mat, const int *cptrs, const int *rows
   sparse_job job = {dmat_t, x, nov, skip};
   const unsigned long long end = 1ull << (nov - 1);
   while (gpu_num > 1 && (end >> 14) < (unsigned long long)gpu_num) gpu_num--;
-  /* SkipPer's work per index is irregular: give the queue 4x more chunks than SpaRyser */
+  /* The sparse kernels work in tiles of 2^11-2^12 indices and need about 2^20 of them per launch to fill the
+   * persistent grid: the reference's 2^(nov-30) chunks (x4 for SkipPer in round 1: 256 at n = 36) made launches of
+   * 2^27 indices with 2^8-index tiles that are mostly prologue -- SkipPer n = 36 took 78 ms in 256 chunks against
+   * 25 ms in one piece.  Four chunks per device (two in flight, two to even out), as for the dense path. */
   unsigned long long chunks = 0;
   if (mode == SP_SCHED_DYNAMIC) {
     chunks = sp_dynamic_chunks(nov, 30, gpu_num);
-    if (skip) { int k = 0; while (k < 2 && end / (chunks * 2) >= (1ull << 22)) { chunks *= 2; ++k; } }
+    const unsigned long long cap = 4ull * (unsigned long long)(gpu_num > 0 ? gpu_num : 1);
+    if (chunks > cap) chunks = cap;
   }
   double sum = 0.0;
   rc = sp_sched_run(&g_sparse_ops, &job, mode, gpu_num, g_first_device, 0ull, end, 14, chunks, &sum, stats);
