@@ -392,11 +392,15 @@ static double sparse_common(const double *mat, const int *cptrs, const int *rows
   /* The sparse kernels work in tiles of 2^11-2^12 indices and need about 2^20 of them per launch to fill the
    * persistent grid: the reference's 2^(nov-30) chunks (x4 for SkipPer in round 1: 256 at n = 36) made launches of
    * 2^27 indices with 2^8-index tiles that are mostly prologue -- SkipPer n = 36 took 78 ms in 256 chunks against
-   * 25 ms in one piece.  Four chunks per device (two in flight, two to even out), as for the dense path. */
+   * 25 ms in one piece.  Two chunks per device, both in flight (8 x B200, n = 36: SkipPer 6.9 / 8.5 / 9.7 ms and SpaRyser
+   * 4.3 / 5.1 / 6.1 ms with 2 / 4 / 8 chunks per device: what finer chunks even out is less than what their
+   * shorter tiles cost). */
   unsigned long long chunks = 0;
   if (mode == SP_SCHED_DYNAMIC) {
     chunks = sp_dynamic_chunks(nov, 30, gpu_num);
-    const unsigned long long cap = 4ull * (unsigned long long)(gpu_num > 0 ? gpu_num : 1);
+    const char *e = getenv("SP_SPARSE_CHUNKS_PER_DEVICE");                 /* development knob */
+    const unsigned long long per_dev = (e && atoi(e) > 0) ? (unsigned long long)atoi(e) : 2ull;
+    const unsigned long long cap = per_dev * (unsigned long long)(gpu_num > 0 ? gpu_num : 1);
     if (chunks > cap) chunks = cap;
   }
   double sum = 0.0;

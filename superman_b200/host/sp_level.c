@@ -381,10 +381,12 @@ int sp_sparse_plan_open(int device, const double *dmat_in, const double *xbase, 
    * (prologue 11.6 % and filter 3.5 % of the block work at c = 11, ncu at n = 33): take c = 12 over the default 11
    * when that is smaller.  Measured on four n = 33 matrices (s(11) = s(12) on all of them): -7 ... -10 % on three,
    * +3 % on the fourth, whose lanes share fewer zero blocks when the tile bits move up by one. */
-  if (skip && img.B && n - 1 > 12) {
+  if (skip && img.B && n - 1 > 12 && !(flags & SP_PLAN_WHOLE_SPACE)) {
+    img.skip_long_tiles = 1;      /* pieces of a range: their launches are short of tiles as it is */
+  } else if (skip && img.B && n - 1 > 12) {
     double surv[2] = {0.0, 0.0};
     unsigned long long rs = 0x9E3779B97F4A7C15ull;
-    const int samples = 2048;
+    const int samples = 512;
     for (int ci = 0; ci < 2; ++ci) {
       const int c = 11 + ci;
       int alive = 0;
