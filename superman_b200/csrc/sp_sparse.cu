@@ -145,15 +145,15 @@ static int sparse_enqueue(spd_sparse_plan* p, unsigned long long lo, unsigned lo
       if (use_level) {
         // persistent grid: every warp pulls chunks of tiles_per_warp tiles from the lane's atomic queue and
         // leaves one partial sum (and one visited count) per chunk; at most 2^20 chunks per launch.  The last
-        // eighth of a SkipPer launch goes out in tiles a quarter as long, so that the warps finish together (a chunk of
-        // full-length tiles is 1/14 of a warp's share at config-3 size).
-        // (SkipPer only: its chunks are 8 tiles per lane; SpaRyser's one-tile chunks lose less at the end than
-        // short tiles cost)
+        // eighth of a SkipPer launch goes out in tiles a quarter as long, so that the warps finish together: its
+        // chunks are 8 tiles per lane, and a chunk of full-length tiles is 1/14 of a warp's share at config-3 size.
+        // (Not for SpaRyser, whose one-tile chunks lose less at the end than short tiles cost, and not below
+        // 2^11-index tiles, where the short ones would be mostly prologue.)
         int c_small = p->skip ? c - env_int("SP_LEVEL_TAIL_SHIFT", 2) : c;
         if (c_small < B + 1) c_small = B + 1;
         unsigned long long nt = tiles_left;                          // tiles of 2^c taken by this launch
         unsigned long long big = nt, small = 0;
-        if (c_small < c && c >= 11 && nt >= 8ull * (unsigned)tiles_per_warp) {      // (short tiles are mostly prologue)
+        if (c_small < c && c >= 11 && nt >= 8ull * (unsigned)tiles_per_warp) {
           big = (nt - nt / 8) / (unsigned)tiles_per_warp * (unsigned)tiles_per_warp;
           small = (nt - big) << (c - c_small);
         }
