@@ -258,9 +258,9 @@ static int level_pack(int n, int B, int S0, int S, int R, int fill_free, const i
   return 1;
 }
 
-int sp_sparse_plan_open(int device, const double *dmat_in, const double *xbase, int nov, int skip, int flags,
-                        spd_sparse_plan **out) {
+int sp_level_plan_build(const double *dmat_in, const double *xbase, int nov, int skip, int flags, sp_level_plan *out) {
   if (!dmat_in || !xbase || !out) { sp_set_error("null argument"); return SP_EINVAL; }
+  memset(out, 0, sizeof(*out));
   if (nov < 2 || nov > 64) { sp_set_error("sparse Ryser supports 2 <= n <= 64 (got %d)", nov); return SP_ELIMIT; }
   const int n = nov;
   int rc = SP_OK;
@@ -409,12 +409,40 @@ int sp_sparse_plan_open(int device, const double *dmat_in, const double *xbase, 
     img.skip_long_tiles = (t12 < t11 && env_int_c("SP_SKIP_LONG_TILES", 1) != 0) ? 1 : 0;
   }
 
-  /* 4. hand the images to the device */
-  rc = spd_sparse_plan_create_packed(device, mt, xb, level_sorted, n, skip, &img, out);
-  if (rc != SPD_OK) sp_set_error("%s", spd_last_error());
+  /* the plan owns what the image points to */
+  out->n = n; out->skip = skip;
+  out->mat_t = mt; mt = NULL;
+  memcpy(out->xbase, xb, sizeof(double) * (size_t)n);
+  memcpy(out->level_sorted, level_sorted, sizeof(int) * (size_t)n);
+  out->img = img;
+  if (img.B) {
+    out->owned[0] = best.colT_hot; out->owned[1] = best.lowR; out->owned[2] = best.dcold;
+    out->owned[3] = best.xb_hot; out->owned[4] = best.xb_cold; out->owned[5] = best.cold_start;
+    memset(&best, 0, sizeof(best));
+  }
 done:
   pack_free(&best);
   free(mt);
   free(dperm);
+  return rc;
+}
+
+void sp_level_plan_free(sp_level_plan *p) {
+  if (!p) return;
+  free(p->mat_t);
+  for (int i = 0; i < 6; ++i) free(p->owned[i]);
+  memset(p, 0, sizeof(*p));
+}
+
+int sp_sparse_plan_open(int device, const double *dmat_t, const double *xbase, int nov, int skip, int flags,
+                        spd_sparse_plan **out) {
+  if (!out) { sp_set_error("null argument"); return SP_EINVAL; }
+  sp_level_plan plan;
+  int rc = sp_level_plan_build(dmat_t, xbase, nov, skip, flags, &plan);
+  if (rc != SP_OK) return rc;
+  /* hand the images to the device */
+  rc = spd_sparse_plan_create_packed(device, plan.mat_t, plan.xbase, plan.level_sorted, plan.n, skip, &plan.img, out);
+  if (rc != SPD_OK) sp_set_error("%s", spd_last_error());
+  sp_level_plan_free(&plan);
   return rc;
 }

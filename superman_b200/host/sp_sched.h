@@ -48,6 +48,18 @@ unsigned long long sp_sched_boundary(unsigned long long lo, unsigned long long h
 #define SP_PLAN_WHOLE_SPACE 1
 int sp_sparse_plan_open(int device, const double *dmat_t, const double *xbase, int nov, int skip, int flags,
                         spd_sparse_plan **plan);
+/* the planning half on its own (no device involved; unit-tested on the CPU): what sp_sparse_plan_open hands to
+ * spd_sparse_plan_create_packed */
+typedef struct sp_level_plan {
+  int n, skip;
+  double *mat_t;              /* [n*n] mat_t[k*n + j]: rows ordered by level, columns in plan order */
+  double xbase[64];           /* in the same row order */
+  int level_sorted[64];
+  spd_level_image img;        /* img.B == 0: hot/cold or shared-memory kernel */
+  void *owned[6];             /* the arrays img points to */
+} sp_level_plan;
+int  sp_level_plan_build(const double *dmat_t, const double *xbase, int nov, int skip, int flags, sp_level_plan *out);
+void sp_level_plan_free(sp_level_plan *plan);
 
 void sp_set_error(const char *fmt, ...);
 int sp_first_device(void);            /* what sp_set_first_device stored (sp_api.c) */

@@ -229,3 +229,98 @@ def test_libconnect_exports_the_reference_names():
     lib.read_calculate_return.restype = C.c_double
     v = lib.read_calculate_return(b"/nonexistent", 5, 1, 1, 1, 1)
     assert v != v                  # NaN: no such file (and no compute without a GPU)
+
+
+class _LevelImage(C.Structure):
+    _fields_ = [("B", C.c_int), ("S0", C.c_int), ("S", C.c_int), ("R", C.c_int),
+                ("NC", C.c_int), ("NCP", C.c_int), ("HSP", C.c_int),
+                ("colT_hot", C.POINTER(C.c_double)), ("lowR", C.POINTER(C.c_double)), ("dcold", C.POINTER(C.c_double)),
+                ("xb_hot", C.POINTER(C.c_double)), ("xb_cold", C.POINTER(C.c_double)), ("cold_start", C.POINTER(C.c_int)),
+                ("instr_per_index", C.c_double), ("skip_long_tiles", C.c_int)]
+
+
+class _LevelPlan(C.Structure):
+    _fields_ = [("n", C.c_int), ("skip", C.c_int), ("mat_t", C.POINTER(C.c_double)),
+                ("xbase", C.c_double * 64), ("level_sorted", C.c_int * 64), ("img", _LevelImage),
+                ("owned", C.c_void_p * 6)]
+
+
+def _replay(X0, cols):
+    """Ryser / Nijenhuis-Wilf sum over all Gray indices for rows with start values X0[r] and column entries
+    cols[k][r]: sum_i (-1)^i prod_r (X0[r] + sum_k gray(i)_k cols[k][r])."""
+    nk = cols.shape[0]
+    i = np.arange(1 << nk, dtype=np.int64)
+    g = i ^ (i >> 1)
+    bits = ((g[:, None] >> np.arange(nk)[None, :]) & 1).astype(np.float64)        # [2^nk, nk]
+    X = X0[None, :] + bits @ cols
+    return float(np.sum(np.where(i & 1, -1.0, 1.0) * np.prod(X, axis=1)))
+
+
+def test_sparse_planner_packs_every_row_exactly_once(sp, oracle):
+    """host/sp_level.c on the CPU: whatever column order, row order, engine and slot configuration the planner
+    chooses, the packed images it would upload (hot slots, register-cold rows, cold rows; free slots neutral or
+    holding a cold row) must describe the same matrix -- replaying the Nijenhuis-Wilf sum from the images gives the
+    oracle's permanent.  Also the structural promises the kernel relies on (level order, cold_start, low-column
+    image = the first B columns of the hot image, instruction count)."""
+    from superman_b200 import _ffi
+    build = _ffi.lib.sp_level_plan_build
+    build.restype = C.c_int
+    build.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.POINTER(_LevelPlan)]
+    free = _ffi.lib.sp_level_plan_free
+    free.argtypes = [C.POINTER(_LevelPlan)]
+    rng = np.random.default_rng(2024)
+    engines = set()
+    for trial in range(40):
+        n = int(rng.integers(7, 15))                                 # n = 14: the SkipPer tile-length sampling runs too
+        dens = float(rng.choice([0.15, 0.25, 0.4, 0.7]))
+        A = (rng.random((n, n)) < dens) * rng.integers(1, 5, (n, n)).astype(np.float64)
+        A[np.arange(n), rng.permutation(n)] = 1.0
+        want = oracle.perm_ld(A)
+        dmat_t = np.ascontiguousarray(A.T)                           # dmat_t[k*n + j] = A[j][k]
+        xbase = np.ascontiguousarray(A[:, n - 1] - A.sum(axis=1) / 2.0)
+        for skip in (0, 1):
+            for flags in (0, 1):                                      # 1 = SP_PLAN_WHOLE_SPACE (may reorder columns)
+                plan = _LevelPlan()
+                rc = build(dmat_t.ctypes.data_as(C.POINTER(C.c_double)), xbase.ctypes.data_as(C.POINTER(C.c_double)),
+                           n, skip, flags, C.byref(plan))
+                assert rc == 0
+                try:
+                    lv = list(plan.level_sorted[:n])
+                    assert lv == sorted(lv)
+                    mt = np.ctypeslib.as_array(plan.mat_t, shape=(n, n)).copy()     # [k][j]
+                    xb = np.array(plan.xbase[:n])
+                    for j in range(n):                                # level = first flippable column with an entry
+                        nz = np.nonzero(mt[:n - 1, j])[0]
+                        assert lv[j] == (int(nz[0]) if len(nz) else n)
+                    got = _replay(xb, mt[:n - 1, :]) * sp.nw_factor(n)
+                    assert got == pytest.approx(want, rel=1e-12), (trial, skip, flags, "row / column order")
+                    im = plan.img
+                    engines.add(im.B)
+                    if im.B == 0:
+                        continue
+                    B, S0, S, R, NC, NCP, HSP = im.B, im.S0, im.S, im.R, im.NC, im.NCP, im.HSP
+                    HS = S0 + (B - 1) * S
+                    LB = B + (B & 1)
+                    assert HS + R <= HSP and B in (3, 4) and 1 <= S0 <= S
+                    hot = np.ctypeslib.as_array(im.colT_hot, shape=(n - 1, HSP))
+                    low = np.ctypeslib.as_array(im.lowR, shape=(HS, LB))
+                    cold = np.ctypeslib.as_array(im.dcold, shape=(n - 1, NCP))
+                    xh = np.ctypeslib.as_array(im.xb_hot, shape=(HSP,))
+                    xc = np.ctypeslib.as_array(im.xb_cold, shape=(NCP,))
+                    cs = np.ctypeslib.as_array(im.cold_start, shape=(n - B + 2,))
+                    assert np.array_equal(low[:, :B], hot[:B, :HS].T)
+                    # a slot of level L (or a register-cold / cold row) has no entry in a column it does not expect
+                    for s in range(HS):
+                        L = 0 if s < S0 else 1 + (s - S0) // S
+                        assert not hot[:L, s].any()
+                    assert not hot[:B, HS:HS + R].any() and not cold[:B, :NC].any()
+                    assert list(cs) == sorted(cs) and cs[0] == 0 and cs[-1] == NC
+                    for i in range(n - B + 1):                        # rows [cs[i], ...) have level >= B + i
+                        assert not cold[B:B + i, cs[i]:NC].any()
+                    got = _replay(np.concatenate([xh[:HS + R], xc[:NC]]),
+                                  np.concatenate([hot[:, :HS + R], cold[:, :NC]], axis=1)) * sp.nw_factor(n)
+                    assert got == pytest.approx(want, rel=1e-12), (trial, skip, flags, B, S0, S, R)
+                    assert 2.0 < im.instr_per_index < 2.0 * n + 2
+                finally:
+                    free(C.byref(plan))
+    assert engines & {3, 4}, engines                                   # the LevelRyser packing was exercised
