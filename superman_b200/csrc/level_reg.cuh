@@ -189,7 +189,17 @@ level_reg_kernel(const __grid_constant__ LevelArgs a) {
         if (SKIP && tc_first < NC) {
           const unsigned long long s = (tile_first + (alive ? t : cand)) << c;
           const unsigned long long g = s ^ (s >> 1);
-          for (int jc = tc_first; jc < NC; ++jc) {
+          int jc = tc_first;
+          for (; jc + 4 <= NC; jc += 4) {              // four rows at a time (independent chains)
+            double x0 = s_xbc[jc], x1 = s_xbc[jc + 1], x2 = s_xbc[jc + 2], x3 = s_xbc[jc + 3];
+            for (int k = c; k < n - 1; ++k) {
+              const double f = (double)((g >> k) & 1ull);
+              const double* dk = s_dcold + k * NCP + jc;
+              x0 = fma(f, dk[0], x0); x1 = fma(f, dk[1], x1); x2 = fma(f, dk[2], x2); x3 = fma(f, dk[3], x3);
+            }
+            alive = alive && (x0 != 0.0) && (x1 != 0.0) && (x2 != 0.0) && (x3 != 0.0);
+          }
+          for (; jc < NC; ++jc) {
             double xr = s_xbc[jc];
             for (int k = c; k < n - 1; ++k)
               xr = fma((double)((g >> k) & 1ull), s_dcold[k * NCP + jc], xr);
