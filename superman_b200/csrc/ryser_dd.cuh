@@ -139,7 +139,7 @@ ryser_dd_kernel(const double* __restrict__ mat_t, const double* __restrict__ xba
 // chains to hide that with), then moved on by the high column that opens the next block and written back once.
 // Requirements: lo and per_thread multiples of 16, hi - lo a multiple of 16, n >= 6 (the host sends the ragged
 // ends of a range through ryser_dd_kernel).
-__global__ void __launch_bounds__(DDK_THREADS)
+__global__ void __launch_bounds__(DDK_THREADS, 3)      // shared memory (2n doubles per thread) admits three blocks at n = 30 ... 44
 ryser_dd_blk_kernel(const double* __restrict__ mat_t, const double* __restrict__ xbase, const double* __restrict__ xbase_lo,
                     int n, unsigned long long lo, unsigned long long hi, unsigned long long per_thread,
                     double* __restrict__ partials) {
@@ -174,17 +174,42 @@ ryser_dd_blk_kernel(const double* __restrict__ mat_t, const double* __restrict__
       const double sk = ((sn >> (k + 1)) & 1ull) ? -1.0 : 1.0;
       const double* colk = colT + (k < n - 1 ? k : 0) * n;       // (k = n-1 only after the very last block: unused)
       dd_t P[16];
-      for (int j = 0; j < n; ++j) {
+      // two rows per trip: the walk of a row is one chain of 16 dependent double-double additions, and two of them
+      // side by side (plus the 16 independent products) keep the FP64 pipe fed
+      int j = 0;
+      for (; j + 1 < n; j += 2) {
+        dd_t x{Xh[j * DDK_THREADS], Xl[j * DDK_THREADS]};
+        dd_t y{Xh[(j + 1) * DDK_THREADS], Xl[(j + 1) * DDK_THREADS]};
+        const double m0 = colT[j], m1 = colT[n + j], m2 = colT[2 * n + j], m3 = s3 * colT[3 * n + j];
+        const double q0 = colT[j + 1], q1 = colT[n + j + 1], q2 = colT[2 * n + j + 1], q3 = s3 * colT[3 * n + j + 1];
+        const double ck = sk * colk[j], dk = sk * colk[j + 1];
+        if (j == 0) P[0] = dd_mul(x, y); else P[0] = dd_mul(dd_mul(P[0], x), y);
+#pragma unroll
+        for (int u = 1; u < 16; ++u) {
+          const int K = (u & 1) ? 0 : (u & 2) ? 1 : (u & 4) ? 2 : 3;
+          const double m = K == 0 ? m0 : K == 1 ? m1 : K == 2 ? m2 : m3;
+          const double q = K == 0 ? q0 : K == 1 ? q1 : K == 2 ? q2 : q3;
+          const bool add = (K == 3 || ((u >> (K + 1)) & 1) == 0);
+          x = dd_add_d(x, add ? m : -m);
+          y = dd_add_d(y, add ? q : -q);
+          if (j == 0) P[u] = dd_mul(x, y); else P[u] = dd_mul(dd_mul(P[u], x), y);
+        }
+        x = dd_add_d(x, ck);
+        y = dd_add_d(y, dk);
+        Xh[j * DDK_THREADS] = x.h; Xl[j * DDK_THREADS] = x.l;
+        Xh[(j + 1) * DDK_THREADS] = y.h; Xl[(j + 1) * DDK_THREADS] = y.l;
+      }
+      if (j < n) {                                                 // odd n: the last row on its own (n >= 6: P is set)
         dd_t x{Xh[j * DDK_THREADS], Xl[j * DDK_THREADS]};
         const double m0 = colT[j], m1 = colT[n + j], m2 = colT[2 * n + j], m3 = s3 * colT[3 * n + j];
         const double ck = sk * colk[j];
-        if (j == 0) P[0] = x; else P[0] = dd_mul(P[0], x);
+        P[0] = dd_mul(P[0], x);
 #pragma unroll
         for (int u = 1; u < 16; ++u) {
           const int K = (u & 1) ? 0 : (u & 2) ? 1 : (u & 4) ? 2 : 3;
           const double m = K == 0 ? m0 : K == 1 ? m1 : K == 2 ? m2 : m3;
           x = dd_add_d(x, (K == 3 || ((u >> (K + 1)) & 1) == 0) ? m : -m);
-          if (j == 0) P[u] = x; else P[u] = dd_mul(P[u], x);
+          P[u] = dd_mul(P[u], x);
         }
         x = dd_add_d(x, ck);
         Xh[j * DDK_THREADS] = x.h; Xl[j * DDK_THREADS] = x.l;
